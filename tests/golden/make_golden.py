@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under ``tests/golden/`` from the reference checkout.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py [--traces]
+
+Produces
+* ``kat_log2.json``    -- the losses the reference itself logged (``{s1,s2,d1,d2}/log2``), parsed
+                          verbatim; rows whose input CSVs are missing are kept but flagged.
+* ``rhs_vectors.npz``  -- outputs of the reference's OWN ``ODEFunc`` / ``Lambda`` classes (their
+                          source is ``exec``-ed straight out of ``/root/reference/train-*.py`` at
+                          generation time, nothing is copied into this repo) on seeded (t, y)
+                          probes, including out-of-table times (the V = -80 fallback).
+* ``traces_*.npz``     -- (``--traces``) oracle trajectories/currents used by the GPU parity tests.
+"""
+import argparse
+import ast
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+from scipy.interpolate import interp1d
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = '/root/reference'
+sys.path.insert(0, ROOT)
+
+
+def reference_classes(script, names=('Lambda', 'ODEFunc')):
+    """exec the named top-level classes of a reference script in an isolated namespace."""
+    path = os.path.join(REF, script)
+    with open(path) as fh:
+        src = fh.read()
+    tree = ast.parse(src)
+    ns = {'torch': torch, 'nn': nn, 'np': np, 'interp1d': interp1d,
+          'device': torch.device('cpu')}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in names:
+            exec(compile(ast.get_source_segment(src, node), path, 'exec'), ns)
+    return {n: ns[n] for n in names if n in ns}
+
+
+def parse_log2(model):
+    rows = []
+    section = None
+    with open(os.path.join(REF, model, 'log2')) as fh:
+        for line in fh:
+            line = line.rstrip('\n')
+            m = re.match(r'^(.*) prediction \| Total Loss ([0-9.]+)$', line)
+            if m:
+                rows.append({'section': 'top', 'name': m.group(1), 'loss': float(m.group(2))})
+                continue
+            m = re.match(r'^(.*) prediction:$', line)
+            if m:
+                section = m.group(1)
+                continue
+            m = re.match(r'^\s+(-?[0-9.]+)(mV|ms) \| Total Loss ([0-9.]+)$', line)
+            if m:
+                rows.append({'section': section, 'name': m.group(1) + m.group(2),
+                             'value': float(m.group(1)), 'loss': float(m.group(3))})
+    for r in rows:
+        r['inputs_present'] = not (r['section'] == 'top' and r['name'] != 'AP 2Hz')
+    return rows
+
+
+SCRIPT = {'s1': 'train-s1.py', 's2': 'train-s2.py', 'd1': 'train-d1.py', 'd2': 'train-d2.py'}
+
+
+def make_kat():
+    out = {m: parse_log2(m) for m in SCRIPT}
+    with open(os.path.join(HERE, 'kat_log2.json'), 'w') as fh:
+        json.dump(out, fh, indent=1)
+    n = sum(sum(r['inputs_present'] for r in rows) for rows in out.values())
+    print('kat_log2.json: %d reproducible rows' % n)
+
+
+def make_rhs_vectors():
+    from neural_ode_ion_channels_b200 import protocols
+    t_tab, v_tab = protocols.ap2hz()
+    rng = np.random.RandomState(1234)
+    n = 48
+    tq = np.concatenate([rng.uniform(0, 3499.9, n - 8), [0.0, 3499.9, 3499.95, 3600.0, 1e4],
+                         rng.uniform(3500, 5000, 3)])
+    aq = rng.uniform(0, 1, n)
+    rq = rng.uniform(0, 1, n)
+    blob = {'t': tq, 'a': aq, 'r': rq}
+    for model, script in SCRIPT.items():
+        cls = reference_classes(script)
+        func = cls['ODEFunc']()
+        func.load_state_dict(torch.load(os.path.join(REF, model, 'model-state-dict.pt')))
+        func.eval()
+        func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        gt = cls['Lambda']()
+        gt.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        n_state = 2 if model in ('s1', 's2') else 6
+        ygt = rng.uniform(0, 1, (n, n_state))
+        blob[model + '_ygt'] = ygt
+        for st_dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
+            o_nn, o_gt = [], []
+            with torch.no_grad():
+                for i in range(n):
+                    t = torch.tensor(tq[i]).to(st_dtype)
+                    y = torch.tensor([[aq[i], rq[i]]]).to(st_dtype)
+                    o_nn.append(func(t, y).double().numpy().reshape(-1))
+                    o_gt.append(gt(t, torch.tensor(ygt[i:i + 1]).to(st_dtype)).double().numpy())
+            blob['%s_nn_%s' % (model, tag)] = np.array(o_nn)
+            blob['%s_gt_%s' % (model, tag)] = np.array(o_gt)
+    np.savez_compressed(os.path.join(HERE, 'rhs_vectors.npz'), **blob)
+    print('rhs_vectors.npz: %d probes x 4 models' % n)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--traces', action='store_true')
+    args = ap.parse_args()
+    torch.set_num_threads(1)
+    make_kat()
+    make_rhs_vectors()
+    if args.traces:
+        from tests.golden import make_traces
+        make_traces.main()
+
+
+if __name__ == '__main__':
+    main()
