@@ -1,0 +1,158 @@
+/*
+ * ikr.h -- C ABI of the B200-native IKr neural-ODE integrator (libikr_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of chonlei/neural-ode-ion-channels:
+ * batched `odeint(func, y0, t, method, rtol, atol)` of the hERG NN-f / NN-d models, forward and
+ * backward.  Each entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout).  Plain pointers and sizes only; no torch types; every buffer (including
+ * the workspace) is owned by the caller; the library keeps no device allocation and no global
+ * state; calls are stream-ordered and never synchronise.
+ *
+ * Replaces, on the reference side:
+ *   - `torchdiffeq.odeint(func, y0, t[, method='dopri5'])`     train-s1.py:322,327; table-1.py:404,413;
+ *                                                               train-r1.py:934,941; train-d0.py:428,436
+ *   - `ODEFunc.forward` NN-f / NN-d (the RHS the solver calls)  train-s1.py:231-247; train-d2.py:257-272
+ *   - `ODEFunc._v` (protocol interpolation, host scipy)         train-s1.py:218-229
+ *   - observation `I = g a r (V - E)` and the loss reductions   train-s1.py:328-329; table-1.py:414-415;
+ *                                                               train-d0.py:509 (sum of squares)
+ *   - backward through the solver (torchdiffeq autograd)        absent from the reference
+ */
+#ifndef IKR_H_
+#define IKR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IKR_ABI_VERSION 1
+
+/* dtype codes */
+#define IKR_F32 0
+#define IKR_F64 1
+/* method codes */
+#define IKR_DOPRI5 0
+#define IKR_RK4 1
+/* per-trajectory status codes (status_out) -- torchdiffeq's host asserts become lane codes */
+#define IKR_OK 0
+#define IKR_DT_UNDERFLOW 1  /* "underflow in dt"                     */
+#define IKR_MAX_STEPS 2     /* "max_num_steps exceeded"              */
+#define IKR_NONFINITE 3     /* "non-finite values in state `y`"      */
+#define IKR_CKPT_OVERFLOW 4 /* step-checkpoint capacity too small    */
+/* return codes (0 ok, negative = argument / launch error) */
+#define IKR_ERR_ARG (-1)
+#define IKR_ERR_UNSUPPORTED (-2)
+#define IKR_ERR_WORKSPACE (-3)
+#define IKR_ERR_LAUNCH (-4)
+#define IKR_ERR_DEVICE (-5)
+
+/* Model + solver descriptor (POD, host memory).  Mirrors the attributes of the reference
+ * `ODEFunc` (train-s1.py:181-216 / train-d2.py:191-232) and the `odeint` keyword arguments. */
+typedef struct ikr_desc {
+  int32_t n_layers;       /* hidden Linear(n,n) count L (architectures/sNN.py: n_layers)         */
+  int32_t n_nodes;        /* hidden width n             (architectures/sNN.py: n_nodes)          */
+  int32_t nn_d;           /* 0: NN-f  da/dt = net/netscale; 1: NN-d  da/dt = HH + net/netscale   */
+  int32_t method;         /* IKR_DOPRI5 | IKR_RK4                                                */
+  int32_t state_dtype;    /* dtype of y0 / y_out / k (torchdiffeq: y0.dtype)                     */
+  int32_t mlp_dtype;      /* dtype of the MLP weights and arithmetic                             */
+  int32_t time_f32;       /* rk4: grid arithmetic in fp32 (caller passed an fp32 `t`)            */
+  int32_t rk4_perturb;    /* rk4 `perturb` option (default 0)                                    */
+  int32_t table_len;      /* protocol table samples                                              */
+  int32_t table_uniform;  /* 1: table_t[i] ~= table_t0 + i / table_inv_dt (index hint only)      */
+  double table_t0;
+  double table_inv_dt;
+  double p[8];            /* p1..p8 (p1..p4 used when nn_d)                                       */
+  double vrange;          /* 100   */
+  double netscale;        /* 1000  */
+  double negative_slope;  /* LeakyReLU slope 0.01 */
+  double rtol, atol;      /* dopri5 tolerances (torchdiffeq defaults 1e-7 / 1e-9)                */
+  double first_step;      /* <= 0: Hairer initial-step heuristic                                  */
+  double safety, ifactor, dfactor; /* 0.9, 10, 0.2                                               */
+  int64_t max_num_steps;  /* per output interval, torchdiffeq semantics                          */
+  int32_t tile_m;         /* 0: library picks the trajectories-per-CTA tile                      */
+  int32_t reserved;
+} ikr_desc;
+
+/* Batch I/O of one forward call.  All pointers are DEVICE pointers unless stated.
+ * Layouts follow torchdiffeq: y_out is (T, B, 2) in the state dtype.                            */
+typedef struct ikr_io {
+  int64_t B;              /* trajectories                                                        */
+  int64_t T;              /* output times                                                        */
+  int64_t G;              /* rk4: grid points (== T and grid == t_out unless step_size given)    */
+  const void* weights;    /* packed MLP parameters, see ikr_packed_weight_elems()                */
+  const double* table_t;  /* [table_len] protocol time (ms)                                      */
+  const double* table_v;  /* [table_len] protocol voltage (mV)                                   */
+  const void* y0;         /* [B,2] state dtype: (a, r)                                           */
+  const double* t_out;    /* [T] strictly increasing output times (fp64 copy of `t`)             */
+  const double* grid;     /* [G] rk4 step grid (fp64)                                            */
+  const double* v_out;    /* [T] V(t_out) for the current / loss epilogue (nullable)             */
+  const void* g;          /* [B] state dtype conductance (nullable => 1)                         */
+  const void* e_rev;      /* [B] state dtype reversal potential (nullable => use e_scalar)       */
+  double e_scalar;
+  const void* data;       /* [T, data_B] state dtype measured current (nullable)                 */
+  int64_t data_B;         /* 1 (shared trace) or B                                               */
+  void* y_out;            /* [T,B,2] state dtype (nullable)                                      */
+  void* i_out;            /* [T,B]  state dtype current (nullable; needs v_out)                  */
+  double* loss_out;       /* [B,2]  per-trajectory (sum sq. error, sum abs error) (nullable)     */
+  int32_t* stats_out;     /* [B,4]  n_accept, n_reject, nfe, status                              */
+  /* step checkpoints for ikr_backward (all nullable when no backward is wanted) */
+  int64_t ckpt_cap;       /* capacity in accepted steps per trajectory                           */
+  double* ckpt_t;         /* [ckpt_cap, B, 2] (t0, dt)                                           */
+  void* ckpt_y;           /* [ckpt_cap, B, 4] state dtype (a0, r0, f0_a, f0_r)                   */
+} ikr_io;
+
+/* Inputs/outputs of the backward sweep (discrete adjoint of the accepted-step sequence).        */
+typedef struct ikr_bwd_io {
+  const void* grad_y;     /* [T,B,2] state dtype dL/dy_out (nullable if fused loss is used)      */
+  int32_t fused_loss;     /* 0: use grad_y; 1: L = sum (I - data)^2 ; 2: L = sum |I - data|      */
+  const void* weights_bwd;/* packed parameters in backward layout (same buffer as `weights`)     */
+  void* grad_weights;     /* [n_params] fp32/fp64 (mlp dtype... accumulated in >= state dtype)   */
+  void* grad_y0;          /* [B,2] (nullable)                                                    */
+  void* grad_g;           /* [B]   (nullable)                                                    */
+} ikr_bwd_io;
+
+int ikr_abi_version(void);
+const char* ikr_error_string(int code);
+
+/* number of elements (of the MLP dtype) of the packed parameter buffer, and the documented
+ * layout: [w0[:,0] | w0[:,1] | b0] (npad each) | L x Wt[k][npad] (forward, K-major)
+ * | L x b[npad] | w_last[npad] | b_last (padded to 8) | L x W[o][npad] (backward, original rows).
+ * npad = n rounded up to 8.  Source tensors: state_dict keys net.{2i}.weight/.bias
+ * (train-s1.py:186-205, 263).                                                                    */
+int64_t ikr_packed_weight_elems(const ikr_desc* d);
+int64_t ikr_param_count(const ikr_desc* d);
+
+/* out[8] = npad, off_w0, off_wt, off_bh, off_wl, off_wn, total elems, chunk rows kc */
+int ikr_packed_layout(const ikr_desc* d, int64_t out[8]);
+
+/* trajectories per CTA the library will use for (desc, B) on the current device */
+int32_t ikr_tile_m(const ikr_desc* d, int64_t B);
+/* out[8] = tile_m, threads/CTA, grid, dynamic smem bytes, n_tiles, kc, chunks/layer, SM count */
+int ikr_launch_geometry(const ikr_desc* d, int64_t B, int64_t out[8]);
+
+size_t ikr_workspace_bytes(const ikr_desc* d, int64_t B, int64_t T, int32_t with_backward);
+
+/* Forward integration of B independent trajectories (== B separate B=1 reference calls).       */
+int ikr_forward(const ikr_desc* d, const ikr_io* io, void* workspace, size_t workspace_bytes,
+                void* cuda_stream);
+
+/* Backward sweep: gradients of a scalar loss w.r.t. the MLP parameters (and optionally y0, g). */
+int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, void* workspace,
+                 size_t workspace_bytes, void* cuda_stream);
+
+/* V(t) of the protocol table at T query times (scipy interp1d linear semantics; out-of-table
+ * => -80 like the callers' ValueError branch, train-s1.py:234-237).                             */
+int ikr_interp_protocol(const ikr_desc* d, const double* table_t, const double* table_v,
+                        const double* t_query, int64_t T, double* v_out, void* cuda_stream);
+
+/* FMA-pipe micro-benchmark used by bench.py for the roofline denominator: runs `iters`
+ * dependent-free FFMA (dtype F32) or DFMA (F64) per thread on every SM and returns the elapsed
+ * milliseconds through *ms_out (this one entry point synchronises the stream).                  */
+int ikr_fma_peak(int32_t dtype, int64_t iters, double* tflops_out, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IKR_H_ */

@@ -1,2 +1,17 @@
-"""B200-native batched ``odeint`` for the hERG/IKr neural-ODE models (NN-f / NN-d)."""
+"""B200-native batched ``odeint`` for the hERG/IKr neural-ODE models (NN-f / NN-d).
+
+Public surface (mirrors what the reference scripts use on this path):
+
+* ``odeint(func, y0, t, *, rtol, atol, method, options)`` -- torchdiffeq-compatible entry point
+* ``integrate(...)``                                   -- same, plus fused current / loss epilogue
+* ``ODEFunc`` / ``ODEFuncNNf`` / ``ODEFuncNNd``         -- the reference's ODE-func modules
+* ``ARCHITECTURES`` / ``build_net``                    -- architectures/s00..s11
+* ``protocols``                                        -- voltage-clamp protocol tables
+"""
 from . import protocols  # noqa: F401
+from .models import (ARCHITECTURES, PARAMETER_SETS, ODEFunc, ODEFuncNNd, ODEFuncNNf,  # noqa: F401
+                     build_net, load_weights)
+from .solver import IkrResult, describe, integrate, odeint  # noqa: F401
+
+__all__ = ['odeint', 'integrate', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
+           'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols']

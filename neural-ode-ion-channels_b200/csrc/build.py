@@ -1,0 +1,46 @@
+"""Build libikr_b200.so (sm_100a only) in-tree with nvcc.  Used by __graft_entry__.build()."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, 'libikr_b200.so')
+SOURCES = ['ikr_capi.cu']
+HEADERS = ['ikr_math.h', 'ikr_device.cuh', 'ikr_forward.cuh', 'ikr_backward.cuh',
+           os.path.join('..', '..', 'include', 'ikr.h')]
+
+NVCC_FLAGS = [
+    '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+    '-fmad=false',          # solver arithmetic must not be contracted (torchdiffeq semantics);
+                            # the MLP inner loops use explicit fma intrinsics
+    '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v', '--expt-relaxed-constexpr',
+]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(HERE, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(HERE, s) for s in SOURCES] + ['-o', OUT]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = res.stdout + res.stderr
+    with open(os.path.join(HERE, 'build.log'), 'w') as fh:
+        fh.write(' '.join(cmd) + '\n' + log)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(log)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed building libikr_b200.so (see csrc/build.log)')
+    return OUT
+
+
+if __name__ == '__main__':
+    build(force=True, verbose=True)
+    print(OUT)

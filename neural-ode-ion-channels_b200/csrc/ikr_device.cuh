@@ -1,0 +1,288 @@
+// ikr_device.cuh -- device building blocks shared by the forward and backward kernels:
+// mbarrier / bulk-copy (TMA) wrappers, the packed-parameter view, and the register-tiled
+// trajectory-tile MLP (one CTA evaluates the MLP of M trajectories at once; hidden-layer weights
+// are streamed L2 -> shared memory by cp.async.bulk into a ring of chunks, activations stay in
+// shared memory feature-major, every thread owns an 8 x TN register tile of the output).
+#ifndef IKR_DEVICE_CUH_
+#define IKR_DEVICE_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ikr_math.h"
+
+namespace ikr {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ float ikr_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double ikr_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// ---------------------------------------------------------------------------------------------
+// Packed parameters (element offsets into one buffer of the MLP dtype; see include/ikr.h)
+// ---------------------------------------------------------------------------------------------
+struct MlpView {
+  const void* base;
+  int L, n, npad;
+  int kc;   // k-rows per streamed weight chunk
+  int cpl;  // chunks per hidden layer
+  long long off_w0;  // [3][npad]   w0[:,0] | w0[:,1] | b0
+  long long off_wt;  // [L][n][npad] forward operand (k-major = W^T)
+  long long off_bh;  // [L][npad]
+  long long off_wl;  // [npad] + b_last
+  long long off_wn;  // [L][n][npad] backward operand (rows = out features)
+  double slope;
+};
+
+template <typename W>
+struct MlpTileCfg;
+template <>
+struct MlpTileCfg<float> {
+  static constexpr int TN = 8;  // output features per thread
+  static constexpr int V = 4;   // elements per 16-byte shared-memory vector
+};
+template <>
+struct MlpTileCfg<double> {
+  static constexpr int TN = 4;
+  static constexpr int V = 2;
+};
+constexpr int kTM = 8;      // trajectories per thread
+constexpr int kStages = 3;  // weight-chunk ring depth
+
+// Shared-memory resources of the trajectory-tile MLP
+template <typename W>
+struct MlpSmem {
+  W* xin;          // [2][M]   MLP inputs (nv, a)
+  W* Hs;           // [npad][M] activations, feature-major
+  W* Wr;           // [kStages][kc][npad] weight-chunk ring
+  uint64_t* full;  // [kStages]
+};
+
+struct MlpPipe {
+  unsigned q;       // next chunk (global sequence number) to consume
+  unsigned issued;  // (thread 0) chunks issued so far
+};
+
+template <typename W>
+__device__ __forceinline__ void mlp_issue_chunk(const MlpView& mv, const MlpSmem<W>& sm,
+                                                unsigned q) {
+  const unsigned stage = q % kStages;
+  const unsigned c = q % (unsigned)mv.cpl;
+  const unsigned layer = (q / (unsigned)mv.cpl) % (unsigned)mv.L;
+  const int k0 = (int)c * mv.kc;
+  const int rows = min(mv.kc, mv.n - k0);
+  const unsigned bytes = (unsigned)(rows * mv.npad * (int)sizeof(W));
+  const W* src = (const W*)mv.base + mv.off_wt + ((long long)layer * mv.n + k0) * mv.npad;
+  mbar_expect_tx(&sm.full[stage], bytes);
+  bulk_g2s(sm.Wr + (size_t)stage * mv.kc * mv.npad, src, bytes, &sm.full[stage]);
+}
+
+// prologue: fill the ring (thread 0).  Called once per kernel after barrier init.
+template <typename W>
+__device__ __forceinline__ void mlp_pipe_start(const MlpView& mv, const MlpSmem<W>& sm,
+                                               MlpPipe& pp) {
+  pp.q = 0;
+  pp.issued = 0;
+  if (mv.L > 0 && threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) mlp_issue_chunk<W>(mv, sm, pp.issued++);
+  }
+}
+// epilogue: wait for every chunk still in flight before the CTA exits
+template <typename W>
+__device__ __forceinline__ void mlp_pipe_drain(const MlpView& mv, const MlpSmem<W>& sm,
+                                               MlpPipe& pp) {
+  if (mv.L > 0 && threadIdx.x == 0) {
+    for (unsigned q = pp.q; q < pp.issued; ++q) mbar_wait(&sm.full[q % kStages], (q / kStages) & 1);
+  }
+}
+
+template <typename W>
+__device__ __forceinline__ W leaky(W x, W slope) { return x > (W)0 ? x : x * slope; }
+
+// row i (0..7) of a thread's register tile -> trajectory index inside the CTA tile.
+// Rows are split in 8/V groups of V consecutive trajectories so that every 16-byte
+// shared-memory vector access of a warp is contiguous (bank-conflict free).
+template <int V>
+__device__ __forceinline__ int tile_row(int i, int gm, int MG) {
+  return (i / V) * (MG * V) + gm * V + (i % V);
+}
+
+// Evaluate the MLP for the M trajectories of the CTA tile.  Inputs in sm.xin, result (the
+// network output before /netscale) returned to the owner threads tid < M.  Executed by every
+// thread of the CTA (contains barriers).  KEEP = also keep every layer's activations (backward).
+template <typename W>
+__device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W>& sm,
+                                              MlpPipe& pp, int M, int MG, int NG) {
+  constexpr int TN = MlpTileCfg<W>::TN;
+  constexpr int V = MlpTileCfg<W>::V;
+  const int tid = threadIdx.x;
+  const bool worker = tid < MG * NG;
+  const int gm = tid % MG;
+  const int gn = tid / MG;
+  const W slope = (W)mv.slope;
+  const W* P = (const W*)mv.base;
+
+  __syncthreads();  // xin written by the owners; Hs free (previous output layer finished)
+
+  // ---- layer 0: Linear(2, n) + LeakyReLU ----------------------------------------------------
+  if (worker) {
+    const W* w0 = P + mv.off_w0;
+    W nv[kTM], aa[kTM];
+#pragma unroll
+    for (int i = 0; i < kTM; ++i) {
+      int m = tile_row<V>(i, gm, MG);
+      nv[i] = sm.xin[m];
+      aa[i] = sm.xin[M + m];
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int col = gn * TN + j;
+      W wa = __ldg(w0 + col), wb = __ldg(w0 + mv.npad + col), bb = __ldg(w0 + 2 * mv.npad + col);
+#pragma unroll
+      for (int i = 0; i < kTM; ++i) {
+        W z = ikr_fma(wb, aa[i], ikr_fma(wa, nv[i], bb));
+        sm.Hs[(size_t)col * M + tile_row<V>(i, gm, MG)] = leaky(z, slope);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- hidden layers: Linear(n, n) + LeakyReLU, weights streamed through the ring ------------
+  for (int layer = 0; layer < mv.L; ++layer) {
+    W acc[kTM][TN];
+#pragma unroll
+    for (int i = 0; i < kTM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = (W)0;
+
+    for (int c = 0; c < mv.cpl; ++c) {
+      const unsigned q = pp.q;
+      const unsigned stage = q % kStages;
+      mbar_wait(&sm.full[stage], (q / kStages) & 1);
+      const int k0 = c * mv.kc;
+      const int rows = min(mv.kc, mv.n - k0);
+      if (worker) {
+        const W* Hk = sm.Hs + (size_t)k0 * M + gm * V;
+        const W* Wk = sm.Wr + (size_t)stage * mv.kc * mv.npad + gn * TN;
+#pragma unroll 2
+        for (int kk = 0; kk < rows; ++kk) {
+          W a[kTM], b[TN];
+          if (sizeof(W) == 4) {
+            float4 a0 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M);
+            float4 a1 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M + MG * V);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            float4 b0 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad);
+            float4 b1 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad + 4);
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+            b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              double2 av = *reinterpret_cast<const double2*>(Hk + (size_t)kk * M + g * MG * V);
+              a[2 * g] = av.x; a[2 * g + 1] = av.y;
+            }
+            double2 b0 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad);
+            double2 b1 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad + 2);
+            b[0] = b0.x; b[1] = b0.y; b[TN - 2] = b1.x; b[TN - 1] = b1.y;
+          }
+#pragma unroll
+          for (int i = 0; i < kTM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = ikr_fma(a[i], b[j], acc[i][j]);
+        }
+      }
+      __syncthreads();  // every warp is done with this ring stage (and, after the last chunk,
+                        // with the input activations)
+      pp.q = q + 1;
+      if (tid == 0) mlp_issue_chunk<W>(mv, sm, pp.issued++);
+    }
+
+    if (worker) {
+      const W* bh = P + mv.off_bh + (long long)layer * mv.npad + gn * TN;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        W bb = __ldg(bh + j);
+        W* dst = sm.Hs + (size_t)(gn * TN + j) * M + gm * V;
+        if (sizeof(W) == 4) {
+          float4 o0, o1;
+          o0.x = leaky(acc[0][j] + bb, slope); o0.y = leaky(acc[1][j] + bb, slope);
+          o0.z = leaky(acc[2][j] + bb, slope); o0.w = leaky(acc[3][j] + bb, slope);
+          o1.x = leaky(acc[4][j] + bb, slope); o1.y = leaky(acc[5][j] + bb, slope);
+          o1.z = leaky(acc[6][j] + bb, slope); o1.w = leaky(acc[7][j] + bb, slope);
+          *reinterpret_cast<float4*>(dst) = o0;
+          *reinterpret_cast<float4*>(dst + MG * V) = o1;
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            double2 o;
+            o.x = leaky(acc[2 * g][j] + bb, slope);
+            o.y = leaky(acc[2 * g + 1][j] + bb, slope);
+            *reinterpret_cast<double2*>(dst + g * MG * V) = o;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- output layer: Linear(n, 1), one owner thread per trajectory ---------------------------
+  W out = (W)0;
+  if (tid < M) {
+    const W* wl = P + mv.off_wl;
+    W s0 = (W)0, s1 = (W)0, s2 = (W)0, s3 = (W)0;
+    int k = 0;
+    for (; k + 3 < mv.n; k += 4) {
+      s0 = ikr_fma(sm.Hs[(size_t)(k + 0) * M + tid], __ldg(wl + k + 0), s0);
+      s1 = ikr_fma(sm.Hs[(size_t)(k + 1) * M + tid], __ldg(wl + k + 1), s1);
+      s2 = ikr_fma(sm.Hs[(size_t)(k + 2) * M + tid], __ldg(wl + k + 2), s2);
+      s3 = ikr_fma(sm.Hs[(size_t)(k + 3) * M + tid], __ldg(wl + k + 3), s3);
+    }
+    for (; k < mv.n; ++k) s0 = ikr_fma(sm.Hs[(size_t)k * M + tid], __ldg(wl + k), s0);
+    out = ((s0 + s1) + (s2 + s3)) + __ldg(wl + mv.npad);
+  }
+  return out;
+}
+
+}  // namespace ikr
+#endif  // IKR_DEVICE_CUH_

@@ -1,0 +1,260 @@
+// ikr_forward.cuh -- the forward integration kernel.
+//
+// One persistent CTA integrates a tile of M trajectories from t[0] to t[-1] inside ONE launch:
+// per-trajectory adaptive dopri5 (own dt, own error control, own dense output) or fixed-grid
+// RK4 (3/8 rule).  All lanes of a tile advance in lock-step *by RHS evaluation*, not by time: a
+// lane whose step is rejected simply retries while its neighbours move on; finished lanes are
+// masked.  The RHS evaluation is fused: V(t) interpolation + HH rates (owner thread of the lane,
+// ikr_math.h) and the MLP as a register-tiled tile GEMM (ikr_device.cuh).
+#ifndef IKR_FORWARD_CUH_
+#define IKR_FORWARD_CUH_
+
+#include "ikr_device.cuh"
+
+namespace ikr {
+
+struct FwdParams {
+  MlpView mlp;
+  SolverCfg cfg;
+  int method;       // 0 dopri5, 1 rk4
+  int time_f32;     // rk4
+  int rk4_perturb;  // rk4
+  int M, MG, NG;    // tile geometry
+  long long B;
+  int T;
+  int G;
+  long long n_tiles;
+  const void* y0;
+  const double* t_out;
+  const double* grid;
+  const double* v_out;
+  const void* g;
+  const void* e_rev;
+  double e_scalar;
+  const void* data;
+  long long data_B;
+  void* y_out;
+  void* i_out;
+  double* loss_out;
+  int* stats_out;
+  long long ckpt_cap;
+  double* ckpt_t;
+  void* ckpt_y;
+};
+
+template <typename S>
+struct Vec2;
+template <>
+struct Vec2<float> { typedef float2 type; };
+template <>
+struct Vec2<double> { typedef double2 type; };
+
+// shared memory carve-up (host and device agree through this one function)
+template <typename S, typename W>
+struct FwdSmemLayout {
+  size_t off_lanes, off_obs, off_xin, off_hs, off_wr, off_bar, total;
+  __host__ __device__ FwdSmemLayout(int M, int npad, int kc) {
+    size_t o = 0;
+    off_bar = o; o += 64;
+    off_lanes = o; o += (size_t)M * sizeof(Lane<S>); o = (o + 15) & ~(size_t)15;
+    off_obs = o; o += (size_t)M * 2 * sizeof(double); o = (o + 15) & ~(size_t)15;
+    off_xin = o; o += (size_t)2 * M * sizeof(W); o = (o + 127) & ~(size_t)127;
+    off_hs = o; o += (size_t)npad * M * sizeof(W); o = (o + 127) & ~(size_t)127;
+    off_wr = o; o += (size_t)kStages * kc * npad * sizeof(W);
+    total = o;
+  }
+};
+
+template <typename S, typename W>
+__global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int M = p.M;
+  const FwdSmemLayout<S, W> lay(M, p.mlp.npad, p.mlp.kc);
+  Lane<S>* lanes = reinterpret_cast<Lane<S>*>(smem_raw + lay.off_lanes);
+  double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);  // [M][2] sse, sae
+  MlpSmem<W> sm;
+  sm.full = reinterpret_cast<uint64_t*>(smem_raw + lay.off_bar);
+  sm.xin = reinterpret_cast<W*>(smem_raw + lay.off_xin);
+  sm.Hs = reinterpret_cast<W*>(smem_raw + lay.off_hs);
+  sm.Wr = reinterpret_cast<W*>(smem_raw + lay.off_wr);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  MlpPipe pp;
+  mlp_pipe_start<W>(p.mlp, sm, pp);
+
+  const SolverCfg& cfg = p.cfg;
+  const S* y0 = reinterpret_cast<const S*>(p.y0);
+  const S* gptr = reinterpret_cast<const S*>(p.g);
+  const S* eptr = reinterpret_cast<const S*>(p.e_rev);
+  const S* dptr = reinterpret_cast<const S*>(p.data);
+  S* y_out = reinterpret_cast<S*>(p.y_out);
+  S* i_out = reinterpret_cast<S*>(p.i_out);
+  S* ckpt_y = reinterpret_cast<S*>(p.ckpt_y);
+  const bool observe = (p.v_out != nullptr) && (p.i_out != nullptr || p.loss_out != nullptr);
+
+  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const long long b = tile * M + tid;  // trajectory owned by this thread (if tid < M)
+    const bool owner = tid < M;
+    const bool valid = owner && b < p.B;
+    S g_b = (S)1, e_b = (S)p.e_scalar;
+
+    // ---- output sample writer -----------------------------------------------------------
+    auto emit = [&](int idx, S a, S r) {
+      if (y_out) {
+        typename Vec2<S>::type v;
+        v.x = a; v.y = r;
+        *reinterpret_cast<typename Vec2<S>::type*>(y_out + ((size_t)idx * p.B + b) * 2) = v;
+      }
+      if (observe) {
+        double cur = (double)(g_b * a * r) * (p.v_out[idx] - (double)e_b);
+        if (i_out) i_out[(size_t)idx * p.B + b] = (S)cur;
+        if (dptr) {
+          double d = (double)dptr[(size_t)idx * p.data_B + (p.data_B == 1 ? 0 : b)];
+          double diff = cur - d;
+          obs[2 * tid] += diff * diff;
+          obs[2 * tid + 1] += fabs(diff);
+        }
+      }
+    };
+    auto ckpt = [&](int step, double t0, double dt, S ya, S yr, S fa, S fr) -> bool {
+      if (!p.ckpt_t) return true;
+      if (step >= p.ckpt_cap) return false;
+      size_t o = (size_t)step * p.B + b;
+      p.ckpt_t[2 * o] = t0;
+      p.ckpt_t[2 * o + 1] = dt;
+      ckpt_y[4 * o] = ya; ckpt_y[4 * o + 1] = yr; ckpt_y[4 * o + 2] = fa; ckpt_y[4 * o + 3] = fr;
+      return true;
+    };
+
+    if (owner) {
+      Lane<S>& L = lanes[tid];
+      S ya = (S)0, yr = (S)1;
+      if (valid) {
+        ya = y0[2 * b]; yr = y0[2 * b + 1];
+        if (gptr) g_b = gptr[b];
+        if (eptr) e_b = eptr[b];
+      }
+      lane_reset<S>(L, ya, yr, p.t_out[0], valid);
+      obs[2 * tid] = 0.0; obs[2 * tid + 1] = 0.0;
+      if (valid) emit(0, ya, yr);
+    }
+
+    double nv, ain;
+    if (p.method == 0) {
+      // ================================ dopri5 ===========================================
+      if (owner) {
+        init_prepare_f0<S>(lanes[tid], cfg, &nv, &ain);
+        sm.xin[tid] = (W)nv; sm.xin[M + tid] = (W)ain;
+      }
+      W out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+      if (owner) {
+        Lane<S>& L = lanes[tid];
+        init_store_f0<S>(L, cfg, (double)out);
+        if (cfg.first_step > 0) {
+          L.dt = cfg.first_step;
+        } else {
+          init_prepare_f1<S>(L, cfg, &nv, &ain);
+          sm.xin[tid] = (W)nv; sm.xin[M + tid] = (W)ain;
+        }
+      }
+      if (!(cfg.first_step > 0)) {
+        out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+        if (owner) init_store_f1<S>(lanes[tid], cfg, (double)out);
+      }
+      if (owner && p.T <= 1 && lane_active(lanes[tid])) lanes[tid].status = LANE_DONE;
+
+      while (true) {
+        int act = 0;
+        if (owner) {
+          dp_check_before_step<S>(lanes[tid], cfg);
+          act = lane_active(lanes[tid]) ? 1 : 0;
+        }
+        if (!__syncthreads_or(act)) break;
+#pragma unroll 1
+        for (int s = 0; s < 6; ++s) {
+          if (owner) {
+            dp_prepare_stage<S>(lanes[tid], cfg, s, &nv, &ain);
+            sm.xin[tid] = (W)nv; sm.xin[M + tid] = (W)ain;
+          }
+          out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+          if (owner) dp_store_stage<S>(lanes[tid], cfg, s, (double)out);
+        }
+        if (owner) dp_finish_step<S>(lanes[tid], cfg, p.t_out, p.T, emit, ckpt);
+      }
+    } else {
+      // ================================ rk4 (3/8 rule) ====================================
+      if (owner && p.T <= 1 && lane_active(lanes[tid])) lanes[tid].status = LANE_DONE;
+      for (int gi = 0; gi + 1 < p.G; ++gi) {
+        const double g0 = p.grid[gi], g1 = p.grid[gi + 1];
+        int act = owner && lane_active(lanes[tid]) ? 1 : 0;
+        if (!__syncthreads_or(act)) break;
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+          if (owner) {
+            rk4_prepare_stage<S>(lanes[tid], cfg, s, g0, g1, p.time_f32 != 0, p.rk4_perturb != 0,
+                                 &nv, &ain);
+            sm.xin[tid] = (W)nv; sm.xin[M + tid] = (W)ain;
+          }
+          W out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+          if (owner) rk4_store_stage<S>(lanes[tid], cfg, s, (double)out);
+        }
+        if (owner) {
+          if (p.ckpt_t && lane_active(lanes[tid]))
+            ckpt(gi, g0, g1 - g0, lanes[tid].ya, lanes[tid].yr, lanes[tid].ka[0], lanes[tid].kr[0]);
+          rk4_finish_step<S>(lanes[tid], g0, g1, p.time_f32 != 0, p.t_out, p.T, emit);
+        }
+      }
+    }
+
+    if (valid) {
+      const Lane<S>& L = lanes[tid];
+      p.stats_out[4 * b + 0] = L.n_acc;
+      p.stats_out[4 * b + 1] = L.n_rej;
+      p.stats_out[4 * b + 2] = L.nfe;
+      p.stats_out[4 * b + 3] = L.status == LANE_DONE ? 0 : L.status;
+      if (p.loss_out) {
+        p.loss_out[2 * b] = obs[2 * tid];
+        p.loss_out[2 * b + 1] = obs[2 * tid + 1];
+      }
+    }
+    __syncthreads();  // lanes[] is re-initialised by the next tile
+  }
+  mlp_pipe_drain<W>(p.mlp, sm, pp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helper kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void ikr_interp_kernel(ProtocolTable tab, const double* tq, long long T, double* v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T) {
+    double out;
+    table_voltage(tab, tq[i], &out);
+    v[i] = out;
+  }
+}
+
+template <typename W>
+__global__ void ikr_fma_peak_kernel(W* sink, long long iters) {
+  // 16 independent accumulator chains per thread: enough ILP to saturate the FMA pipe
+  W a[16];
+  W x = (W)(1.0 + 1e-7 * threadIdx.x), y = (W)(1e-9 * blockIdx.x);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (W)i;
+  for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = ikr_fma(a[i], x, y);
+  }
+  W s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == (W)123.456) sink[0] = s;
+}
+
+}  // namespace ikr
+#endif  // IKR_FORWARD_CUH_

@@ -1,0 +1,436 @@
+"""Drop-in ``odeint`` for the reference's call sites, backed by the fused sm_100a kernels.
+
+    from neural_ode_ion_channels_b200 import odeint          # was: from torchdiffeq import odeint
+    func = ODEFunc(); func.load_state_dict(torch.load('d1/model-state-dict.pt')); func.eval()
+    func.set_fixed_form_voltage_protocol(t_np, v_np)         # train-s1.py:218-222
+    y = odeint(func, y0, t, method='dopri5')                 # (len(t), *y0.shape)
+
+Signature and semantics follow ``torchdiffeq.odeint`` 0.2.x as the reference uses it
+(``train-s1.py:322,327``, ``table-1.py:404,413``, ``train-d0.py:436``): ``rtol=1e-7, atol=1e-9``,
+``method`` in {None/'dopri5', 'rk4'}, unknown ``options`` only warn.  Differences, all additive:
+
+* ``y0`` may be ``(B, 2)``: B independent trajectories, each with its *own* adaptive step size
+  and error control (== B separate B=1 reference calls, not torchdiffeq's shared-dt batching).
+* the module is *introspected* (``describe``) -- ``func.forward`` is never called per stage.
+* ``integrate`` exposes the fused observation ``I = g a r (V - E)`` and loss reductions.
+
+There is no CPU path: tensors are moved to the current CUDA device and the C-ABI library
+``csrc/libikr_b200.so`` does the work; if it is missing this module raises.
+"""
+import ctypes
+import warnings
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .protocols import compact_table
+
+_ADAPTIVE_OPTS = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps'}
+_FIXED_OPTS = {'step_size', 'perturb'}
+_EXT_OPTS = {'tile_m', 'check_status', 'compact_table', 'ckpt_cap'}
+
+
+# =============================================================================================
+# module introspection (SURVEY 8b "module introspection contract")
+# =============================================================================================
+@dataclass
+class ModelSpec:
+    n_layers: int
+    n_nodes: int
+    nn_d: bool
+    p: tuple
+    vrange: float
+    netscale: float
+    negative_slope: float
+    linears: list            # the nn.Linear modules in order
+    mlp_dtype: torch.dtype
+
+
+def _scalar(x, name):
+    if isinstance(x, torch.Tensor):
+        if x.numel() != 1:
+            raise TypeError('ODE func attribute %s must be a scalar' % name)
+        return float(x.reshape(-1)[0].item())
+    return float(x)
+
+
+def describe(func) -> ModelSpec:
+    """Flatten a reference-style ODE func (``train-s1.py:181-216`` / ``train-d2.py:191-232``)
+    into a descriptor; anything that is not such a module raises ``TypeError``."""
+    net = getattr(func, 'net', None)
+    if not isinstance(net, nn.Sequential):
+        raise TypeError('odeint: func.net must be an nn.Sequential of Linear/LeakyReLU layers '
+                        '(got %r); this integrator has no generic-RHS / CPU fallback' % type(net))
+    mods = list(net)
+    if len(mods) < 5 or len(mods) % 2 == 0:
+        raise TypeError('odeint: func.net must be Linear(2,n), LeakyReLU, [Linear(n,n), '
+                        'LeakyReLU]*L, Linear(n,1) with L >= 1')
+    linears, slope = [], None
+    for i, m in enumerate(mods):
+        if i % 2 == 0:
+            if not isinstance(m, nn.Linear) or m.bias is None:
+                raise TypeError('odeint: func.net[%d] must be nn.Linear with bias' % i)
+            linears.append(m)
+        else:
+            if not isinstance(m, nn.LeakyReLU):
+                raise TypeError('odeint: func.net[%d] must be nn.LeakyReLU' % i)
+            if slope is not None and m.negative_slope != slope:
+                raise TypeError('odeint: all LeakyReLU slopes must agree')
+            slope = m.negative_slope
+    n = linears[0].out_features
+    if linears[0].in_features != 2 or linears[-1].out_features != 1:
+        raise TypeError('odeint: func.net must map 2 inputs to 1 output')
+    for m in linears[1:-1]:
+        if m.in_features != n or m.out_features != n:
+            raise TypeError('odeint: hidden layers must all be Linear(%d, %d)' % (n, n))
+    if linears[-1].in_features != n:
+        raise TypeError('odeint: last layer must be Linear(%d, 1)' % n)
+    dtypes = {p.dtype for p in net.parameters()}
+    if len(dtypes) != 1 or next(iter(dtypes)) not in (torch.float32, torch.float64):
+        raise TypeError('odeint: MLP parameters must be all float32 or all float64')
+    for k in ('p5', 'p6', 'p7', 'p8', 'vrange', 'netscale'):
+        if not hasattr(func, k):
+            raise TypeError('odeint: func lacks attribute %r of the reference ODEFunc' % k)
+    nn_d = all(hasattr(func, k) for k in ('p1', 'p2', 'p3', 'p4')) and hasattr(func, '_dadt')
+    p = tuple(_scalar(getattr(func, 'p%d' % i), 'p%d' % i) if (i >= 5 or nn_d) else 0.0
+              for i in range(1, 9))
+    return ModelSpec(n_layers=len(linears) - 2, n_nodes=n, nn_d=nn_d, p=p,
+                     vrange=_scalar(func.vrange, 'vrange'),
+                     netscale=_scalar(func.netscale, 'netscale'),
+                     negative_slope=float(slope), linears=linears,
+                     mlp_dtype=next(iter(dtypes)))
+
+
+def _protocol_arrays(func):
+    t = getattr(func, '_t_regular', None)
+    v = getattr(func, '_v_regular', None)
+    if t is None or v is None:
+        raise TypeError('odeint: call func.set_fixed_form_voltage_protocol(t, v) first')
+    t = np.ascontiguousarray(np.asarray(t, dtype=np.float64).reshape(-1))
+    v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+    if len(t) != len(v) or len(t) < 2:
+        raise TypeError('odeint: protocol table needs >= 2 samples of equal length')
+    if not np.all(np.diff(t) > 0):
+        raise TypeError('odeint: protocol table times must be strictly increasing')
+    return t, v
+
+
+def _uniform_hint(t):
+    if len(t) < 3:
+        return 0, 0.0, 0.0
+    h = (t[-1] - t[0]) / (len(t) - 1)
+    if np.all(np.abs(t - (t[0] + h * np.arange(len(t)))) < 0.25 * h):
+        return 1, float(t[0]), float(1.0 / h)
+    return 0, 0.0, 0.0
+
+
+# =============================================================================================
+# device-side model: packed weights + protocol table
+# =============================================================================================
+def _make_desc(spec: ModelSpec, state_dtype, method, tab_len, uniform, rtol, atol, opts,
+               time_f32=False):
+    d = _cabi.IkrDesc()
+    d.n_layers, d.n_nodes, d.nn_d = spec.n_layers, spec.n_nodes, int(spec.nn_d)
+    d.method = _cabi.DOPRI5 if method == 'dopri5' else _cabi.RK4
+    d.state_dtype = _cabi.F32 if state_dtype == torch.float32 else _cabi.F64
+    d.mlp_dtype = _cabi.F32 if spec.mlp_dtype == torch.float32 else _cabi.F64
+    d.time_f32 = int(time_f32)
+    d.rk4_perturb = int(bool(opts.get('perturb', False)))
+    d.table_len = tab_len
+    d.table_uniform, d.table_t0, d.table_inv_dt = uniform
+    for i in range(8):
+        d.p[i] = spec.p[i]
+    d.vrange, d.netscale, d.negative_slope = spec.vrange, spec.netscale, spec.negative_slope
+    d.rtol, d.atol = float(rtol), float(atol)
+    fs = opts.get('first_step', None)
+    d.first_step = float(fs) if fs is not None else 0.0
+    d.safety = float(opts.get('safety', 0.9))
+    d.ifactor = float(opts.get('ifactor', 10.0))
+    d.dfactor = float(opts.get('dfactor', 0.2))
+    d.max_num_steps = int(opts.get('max_num_steps', 2 ** 31 - 1))
+    d.tile_m = int(opts.get('tile_m', 0))
+    return d
+
+
+def pack_weights(spec: ModelSpec, desc, device):
+    """Pack the state-dict tensors into the kernel layout documented in ``include/ikr.h``
+    (``[w0[:,0] | w0[:,1] | b0] | L x W^T[k][npad] | L x b[npad] | w_last | b_last | L x W``)."""
+    lay = _cabi.packed_layout(desc)
+    npad, n, L = lay['npad'], spec.n_nodes, spec.n_layers
+    dt = spec.mlp_dtype
+    buf = torch.zeros(lay['total'], dtype=dt, device=device)
+    lin = spec.linears
+    w0 = lin[0].weight.detach().to(device=device, dtype=dt)
+    o = lay['off_w0']
+    buf[o:o + n] = w0[:, 0]
+    buf[o + npad:o + npad + n] = w0[:, 1]
+    buf[o + 2 * npad:o + 2 * npad + n] = lin[0].bias.detach().to(device=device, dtype=dt)
+    wt = buf[lay['off_wt']:lay['off_wt'] + L * n * npad].view(L, n, npad)
+    wn = buf[lay['off_wn']:lay['off_wn'] + L * n * npad].view(L, n, npad)
+    bh = buf[lay['off_bh']:lay['off_bh'] + L * npad].view(L, npad)
+    for l in range(L):
+        w = lin[1 + l].weight.detach().to(device=device, dtype=dt)      # (out, in)
+        wt[l, :, :n] = w.t()
+        wn[l, :, :n] = w
+        bh[l, :n] = lin[1 + l].bias.detach().to(device=device, dtype=dt)
+    o = lay['off_wl']
+    buf[o:o + n] = lin[-1].weight.detach().to(device=device, dtype=dt).reshape(-1)
+    buf[o + npad] = lin[-1].bias.detach().to(device=device, dtype=dt).reshape(-1)[0]
+    return buf
+
+
+def unpack_grads(spec: ModelSpec, flat):
+    """Split the flat gradient (state-dict order: w0, b0, (W_l, b_l)*, w_last, b_last) into
+    per-parameter tensors shaped like ``spec.linears``' parameters."""
+    out, o = [], 0
+    for m in spec.linears:
+        for p in (m.weight, m.bias):
+            k = p.numel()
+            out.append(flat[o:o + k].view_as(p))
+            o += k
+    return out
+
+
+class _DeviceModel:
+    """Packed weights + protocol table resident on one GPU (cached on the func object)."""
+
+    def __init__(self, func, device, use_compaction):
+        self.spec = describe(func)
+        t, v = _protocol_arrays(func)
+        self.table_key = (t.ctypes.data, v.ctypes.data, len(t), float(t[0]), float(t[-1]),
+                          float(v.sum()), use_compaction)
+        if use_compaction:
+            t, v = compact_table(t, v)
+        self.uniform = _uniform_hint(t)
+        self.tab_len = len(t)
+        self.tab_t = torch.from_numpy(t).to(device)
+        self.tab_v = torch.from_numpy(v).to(device)
+        self.device = device
+        self.weights = None
+        self.weights_key = None
+
+    def weights_for(self, desc):
+        key = tuple((p.data_ptr(), p._version) for m in self.spec.linears
+                    for p in (m.weight, m.bias))
+        if self.weights is None or key != self.weights_key:
+            self.weights = pack_weights(self.spec, desc, self.device)
+            self.weights_key = key
+        return self.weights
+
+
+def _device_model(func, device, use_compaction):
+    cache = func.__dict__.setdefault('_ikr_b200_cache', {})
+    dm = cache.get(device)
+    t, v = _protocol_arrays(func)
+    key = (t.ctypes.data, v.ctypes.data, len(t), float(t[0]), float(t[-1]), float(v.sum()),
+           use_compaction)
+    if dm is None or dm.table_key != key:
+        dm = _DeviceModel(func, device, use_compaction)
+        cache[device] = dm
+    else:
+        dm.spec = describe(func)
+    return dm
+
+
+# =============================================================================================
+# integrate
+# =============================================================================================
+@dataclass
+class IkrResult:
+    y: Optional[torch.Tensor]            # (T, B, 2) state dtype
+    current: Optional[torch.Tensor]      # (T, B)
+    sse: Optional[torch.Tensor]          # (B,) sum_i (I - data)^2   (fp64)
+    sae: Optional[torch.Tensor]          # (B,) sum_i |I - data|     (fp64)
+    stats: torch.Tensor                  # (B, 4) int32: n_accept, n_reject, nfe, status
+    ckpt: Optional[tuple] = None
+    geometry: Optional[dict] = None
+
+    @property
+    def nfe(self):
+        return int(self.stats[:, 2].sum().item())
+
+    def mae(self, T):
+        return self.sae / T
+
+
+def _resolve_device(y0, device):
+    if device is not None:
+        return torch.device(device)
+    if y0.is_cuda:
+        return y0.device
+    if not torch.cuda.is_available():
+        raise RuntimeError('neural_ode_ion_channels_b200.odeint needs a CUDA device (B200, '
+                           'sm_100a); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _rk4_grid(t_cpu, step_size):
+    """torchdiffeq's fixed-grid constructor for ``options={'step_size': h}`` (in t's dtype)."""
+    if step_size is None:
+        return t_cpu.to(torch.float64)
+    start, end = t_cpu[0], t_cpu[-1]
+    niters = torch.ceil((end - start) / step_size + 1).item()
+    grid = torch.arange(0, niters, dtype=t_cpu.dtype) * step_size + start
+    grid[-1] = t_cpu[-1]
+    return grid.to(torch.float64)
+
+
+def _split_options(method, options):
+    options = dict(options or {})
+    known = (_ADAPTIVE_OPTS if method == 'dopri5' else _FIXED_OPTS) | _EXT_OPTS
+    unknown = sorted(set(options) - known)
+    if unknown:
+        # torchdiffeq 0.2.x warns on unknown options (the reference passes the legacy
+        # grid_points/eps, train-d0.py:436) -- same here
+        warnings.warn('{}: Unexpected arguments {}'.format(
+            'Dopri5Solver' if method == 'dopri5' else 'RK4', {k: options[k] for k in unknown}))
+        for k in unknown:
+            options.pop(k)
+    return options
+
+
+def _raise_on_status(stats):
+    bad = stats[:, 3] != 0
+    if bool(bad.any().item()):
+        idx = torch.nonzero(bad).reshape(-1)
+        code = int(stats[idx[0], 3].item())
+        raise AssertionError('%s (trajectory %d%s)' % (
+            _cabi.STATUS_TEXT.get(code, 'solver failure %d' % code), int(idx[0].item()),
+            '' if idx.numel() == 1 else ' and %d more' % (idx.numel() - 1)))
+
+
+def integrate(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, g=None, E=-86.0,
+              data=None, want_y=True, want_current=False, want_ckpt=False, device=None):
+    """Forward integration with the fused observation/loss epilogue.
+
+    ``g`` (B,) conductances, ``E`` scalar or (B,) reversal potential, ``data`` (T,) or (T, B)
+    measured current: returns ``IkrResult`` with ``current = g a r (V(t) - E)`` and the
+    per-trajectory ``sse`` / ``sae`` reductions against ``data`` (``train-s1.py:328-329``,
+    ``train-d0.py:509``)."""
+    method = method or 'dopri5'
+    if method not in ('dopri5', 'rk4'):
+        raise ValueError('odeint: method must be dopri5 or rk4 (got %r); the B200 path '
+                         'implements the two solvers of the hot path only' % (method,))
+    opts = _split_options(method, options)
+    if not isinstance(y0, torch.Tensor) or y0.dim() != 2 or y0.shape[1] != 2:
+        raise TypeError('odeint: y0 must be a (B, 2) tensor of (a, r) states')
+    if y0.dtype not in (torch.float32, torch.float64):
+        raise TypeError('odeint: y0 must be float32 or float64')
+    t = torch.as_tensor(t)
+    if t.dim() != 1 or t.numel() < 1 or not t.is_floating_point():
+        raise TypeError('odeint: t must be a 1-D floating point tensor')
+    t_cpu = t.detach().cpu()
+    if t_cpu.numel() > 1 and not bool((t_cpu[1:] > t_cpu[:-1]).all()):
+        raise ValueError('odeint: t must be strictly increasing')
+
+    dev = _resolve_device(y0, device)
+    with torch.cuda.device(dev):
+        dm = _device_model(func, dev, opts.get('compact_table', True))
+        spec = dm.spec
+        if y0.dtype == torch.float32 and spec.mlp_dtype == torch.float64:
+            raise TypeError('odeint: float32 state with a float64 MLP is not supported')
+        B, T = y0.shape[0], t_cpu.numel()
+        desc = _make_desc(spec, y0.dtype, method, dm.tab_len, dm.uniform, rtol, atol, opts,
+                          time_f32=(t_cpu.dtype == torch.float32))
+        weights = dm.weights_for(desc)
+        lib = _cabi.lib()
+        stream = torch.cuda.current_stream(dev)
+        sptr = ctypes.c_void_p(stream.cuda_stream)
+
+        y0_d = y0.detach().to(dev, non_blocking=True).contiguous()
+        t_d = t_cpu.to(torch.float64).to(dev, non_blocking=True)
+        io = _cabi.IkrIO()
+        io.B, io.T = B, T
+        io.weights = weights.data_ptr()
+        io.table_t, io.table_v = dm.tab_t.data_ptr(), dm.tab_v.data_ptr()
+        io.y0, io.t_out = y0_d.data_ptr(), t_d.data_ptr()
+        keep = [y0_d, t_d, weights]
+        if method == 'rk4':
+            grid = _rk4_grid(t_cpu, opts.get('step_size')).to(dev)
+            io.grid, io.G = grid.data_ptr(), grid.numel()
+            keep.append(grid)
+        observe = want_current or data is not None
+        y_out = cur = loss = v_out = None
+        if observe:
+            v_out = torch.empty(T, dtype=torch.float64, device=dev)
+            _cabi.check(lib.ikr_interp_protocol(ctypes.byref(desc), dm.tab_t.data_ptr(),
+                                                dm.tab_v.data_ptr(), t_d.data_ptr(), T,
+                                                v_out.data_ptr(), sptr), 'ikr_interp_protocol')
+            io.v_out = v_out.data_ptr()
+            if g is not None:
+                g_d = torch.as_tensor(g).to(device=dev, dtype=y0.dtype).reshape(-1).contiguous()
+                if g_d.numel() == 1:
+                    g_d = g_d.expand(B).contiguous()
+                if g_d.numel() != B:
+                    raise ValueError('odeint: g must have B entries')
+                io.g = g_d.data_ptr()
+                keep.append(g_d)
+            if isinstance(E, torch.Tensor) and E.numel() > 1:
+                e_d = E.to(device=dev, dtype=y0.dtype).reshape(-1).contiguous()
+                if e_d.numel() != B:
+                    raise ValueError('odeint: E must be a scalar or have B entries')
+                io.e_rev = e_d.data_ptr()
+                keep.append(e_d)
+            else:
+                io.e_scalar = float(E)
+            if want_current:
+                cur = torch.empty((T, B), dtype=y0.dtype, device=dev)
+                io.i_out = cur.data_ptr()
+            if data is not None:
+                d_d = torch.as_tensor(data).to(device=dev, dtype=y0.dtype).contiguous()
+                if d_d.dim() == 1:
+                    d_d = d_d.reshape(T, 1)
+                if d_d.shape[0] != T or d_d.shape[1] not in (1, B):
+                    raise ValueError('odeint: data must be (T,) or (T, B)')
+                io.data, io.data_B = d_d.data_ptr(), d_d.shape[1]
+                loss = torch.empty((B, 2), dtype=torch.float64, device=dev)
+                io.loss_out = loss.data_ptr()
+                keep.append(d_d)
+        if want_y:
+            y_out = torch.empty((T, B, 2), dtype=y0.dtype, device=dev)
+            io.y_out = y_out.data_ptr()
+        stats = torch.empty((B, 4), dtype=torch.int32, device=dev)
+        io.stats_out = stats.data_ptr()
+        ckpt = None
+        if want_ckpt:
+            cap = int(opts.get('ckpt_cap', 0)) or (io.G if method == 'rk4' else 4096)
+            ck_t = torch.empty((cap, B, 2), dtype=torch.float64, device=dev)
+            ck_y = torch.empty((cap, B, 4), dtype=y0.dtype, device=dev)
+            io.ckpt_cap, io.ckpt_t, io.ckpt_y = cap, ck_t.data_ptr(), ck_y.data_ptr()
+            ckpt = (ck_t, ck_y)
+        _cabi.check(lib.ikr_forward(ctypes.byref(desc), ctypes.byref(io), None, 0, sptr),
+                    'ikr_forward')
+        if opts.get('check_status', True):
+            _raise_on_status(stats)
+        res = IkrResult(y=y_out, current=cur,
+                        sse=None if loss is None else loss[:, 0],
+                        sae=None if loss is None else loss[:, 1],
+                        stats=stats, ckpt=ckpt,
+                        geometry=_cabi.launch_geometry(desc, B))
+        res._keep = keep
+        res._desc, res._io = desc, io
+        return res
+
+
+def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):
+    """``torchdiffeq.odeint`` replacement: returns ``(len(t), *y0.shape)`` in ``y0.dtype`` on
+    ``y0``'s device."""
+    if event_fn is not None:
+        raise NotImplementedError('odeint: event handling is not part of the reference hot path')
+    squeeze = False
+    if isinstance(y0, torch.Tensor) and y0.dim() == 1:
+        y0, squeeze = y0.reshape(1, -1), True
+    needs_grad = torch.is_grad_enabled() and any(
+        p.requires_grad for p in getattr(func, 'net', nn.Sequential()).parameters())
+    if needs_grad:
+        from .adjoint import odeint_with_grad
+        y = odeint_with_grad(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+    else:
+        y = integrate(func, y0, t, rtol=rtol, atol=atol, method=method, options=options).y
+    if not y0.is_cuda:
+        y = y.to(y0.device)
+    return y[:, 0, :] if squeeze else y

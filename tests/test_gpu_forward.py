@@ -1,0 +1,382 @@
+"""GPU parity tests of the forward path (through the C ABI) against the CPU oracle.
+
+Tolerances (stated per north_star):
+* rk4, fp64 state + fp64 MLP: <= 1e-10 relative to the oracle.
+* dopri5, fp64/fp64: every accepted step reproduced from its checkpoint to <= 1e-10 relative
+  (step-wise parity); whole traces within the solver's own step-sequence sensitivity envelope
+  (the adaptive controller on this RHS is chaotic at the 1e-5 level -- see DESIGN.md), and within
+  10 x atol on a smooth protocol where the accept/reject sequence is reproduced.
+* dopri5, fp32 state "as shipped": reference-logged losses within 5e-5 absolute.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import neural_ode_ion_channels_b200 as ikr
+from neural_ode_ion_channels_b200 import protocols
+from oracle import ref_models as rm
+from oracle import ref_odeint as ro
+from tests import kat
+
+pytestmark = pytest.mark.gpu
+
+CUDA = torch.cuda.is_available()
+
+
+def _nn(study, double=False):
+    """(product module, oracle module) with identical weights."""
+    cls = ikr.ODEFuncNNd if study in ('s2', 'd2') else ikr.ODEFuncNNf
+    pset = 's' if study in ('s1', 's2') else 'd'
+    func = ikr.load_weights(cls(params=pset), kat.weights_path(study))
+    ofunc = kat.make_nn(study, mlp_follows_state=double)
+    if double:
+        func = func.double()
+        ofunc = ofunc.double()
+        ofunc.vrange = ofunc.vrange.double()
+        ofunc.netscale = ofunc.netscale.double()
+    return func, ofunc
+
+
+def _oracle_batch(ofunc, y0, t, **kw):
+    outs = []
+    with torch.no_grad():
+        for b in range(y0.shape[0]):
+            outs.append(ro.odeint(ofunc, y0[b:b + 1], t, **kw))
+    return torch.cat(outs, dim=1)
+
+
+def _rel(got, want, floor=1e-300):
+    return (np.abs(got - want) / np.maximum(np.abs(want), floor)).max()
+
+
+@pytest.mark.parametrize('study', ['s1', 'd2'])
+def test_rk4_fp64_matches_oracle_1e10(study):
+    torch.set_num_threads(1)
+    func, ofunc = _nn(study, double=True)
+    t_tab, v_tab = protocols.ap2hz()
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    ofunc.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 120., 241, dtype=torch.float64)
+    y0 = torch.tensor([[0., 1.], [0.3, 0.6], [0.9, 0.05]], dtype=torch.float64)
+    want = _oracle_batch(ofunc, y0, t, method='rk4').numpy()
+    got = ikr.odeint(func, y0.cuda(), t, method='rk4').cpu().numpy()
+    assert got.shape == want.shape == (241, 3, 2)
+    assert _rel(got, want) <= 1e-10
+    # off-grid outputs (options step_size): linear interpolation between grid points
+    t2 = torch.linspace(0., 120., 13, dtype=torch.float64)
+    want = _oracle_batch(ofunc, y0[:1], t2, method='rk4', options={'step_size': 0.7}).numpy()
+    got = ikr.odeint(func, y0[:1].cuda(), t2, method='rk4', options={'step_size': 0.7})
+    assert _rel(got.cpu().numpy(), want) <= 1e-10
+
+
+def test_rk4_fp32_as_shipped():
+    torch.set_num_threads(1)
+    func, ofunc = _nn('s1')
+    t_tab, v_tab = protocols.pr3_activation(40)
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    ofunc.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(900., 1100., 401)
+    y0 = torch.tensor([[0., 1.]])
+    want = _oracle_batch(ofunc, y0, t, method='rk4').numpy()
+    got = ikr.odeint(func, y0.cuda(), t, method='rk4').cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)   # fp32 state: ~400 steps of eps
+
+
+@pytest.mark.parametrize('arch', ['s03', 's10', 's06', 's01'])
+def test_rk4_fp64_architectures(arch):
+    """architectures/sNN.py sweep: tiny (n=10), n=100, wide (n=500), shallow nets."""
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    func = ikr.ODEFuncNNf(arch=arch, params='r').double()
+    L, n = ikr.ARCHITECTURES[arch]
+    ofunc = rm.NNfRhs(net=rm.build_mlp(L, n), inact=tuple(func.__dict__['p%d' % i] for i in (5, 6, 7, 8)),
+                      mlp_follows_state=True).double()
+    ofunc.net.load_state_dict(func.net.state_dict())
+    ofunc.vrange = ofunc.vrange.double()
+    ofunc.netscale = ofunc.netscale.double()
+    t_tab, v_tab = protocols.pr5_deactivation(-60)
+    for f in (func, ofunc):
+        f.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(990., 1010., 41, dtype=torch.float64)
+    y0 = torch.tensor([[0.02, 0.97], [0.5, 0.5]], dtype=torch.float64)
+    want = _oracle_batch(ofunc, y0, t, method='rk4').numpy()
+    got = ikr.odeint(func, y0.cuda(), t, method='rk4').cpu().numpy()
+    assert _rel(got, want) <= 1e-10
+
+
+@pytest.mark.parametrize('study', ['s1', 'd2'])
+def test_dopri5_fp64_stepwise_parity(study):
+    """Each accepted step of the CUDA run, restarted on the oracle from the step checkpoint
+    (t0, dt, y0, f0), must land on the next checkpoint: bit-level parity of the RK arithmetic
+    and of the dense output, independent of the chaotic step-size controller."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn(study, double=True)
+    t_tab, v_tab = protocols.ap2hz()
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    ofunc.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 400., 201, dtype=torch.float64)
+    y0 = torch.tensor([[0., 1.], [0.2, 0.7]], dtype=torch.float64)
+    res = ikr.integrate(func, y0.cuda(), t, want_ckpt=True)
+    stats = res.stats.cpu().numpy()
+    ck_t, ck_y = res.ckpt[0].cpu(), res.ckpt[1].cpu()
+    y_gpu = res.y.cpu()
+    solver = ro.Dopri5(ofunc, y0[:1], 1e-7, 1e-9)
+    worst = 0.0
+    for b in range(2):
+        n_acc = int(stats[b, 0])
+        assert stats[b, 3] == 0 and n_acc > 20
+        j_out = 1
+        for j in range(0, n_acc - 1, max(1, n_acc // 40)):   # ~40 steps sampled per trajectory
+            ts, dt = ck_t[j, b, 0], ck_t[j, b, 1]
+            yy = ck_y[j, b, :2].reshape(1, 2)
+            ff = ck_y[j, b, 2:].reshape(1, 2)
+            with torch.no_grad():
+                y1, f1, err, k = solver._rk_step(yy, ff, ts, dt, ts + dt)
+                coef = solver._mid_fit(yy, y1, k, dt)
+            want = torch.cat([y1.reshape(-1), f1.reshape(-1)]).numpy()
+            got = ck_y[j + 1, b].numpy()
+            worst = max(worst, _rel(got, want, 1e-30))
+            # dense output samples inside this step
+            inside = torch.nonzero((t > ts) & (t <= ts + dt)).reshape(-1)
+            for i in inside.tolist():
+                with torch.no_grad():
+                    yi = ro._dense_eval(coef, ts, ts + dt, t[i]).reshape(-1).numpy()
+                worst = max(worst, _rel(y_gpu[i, b].numpy(), yi, 1e-30))
+    assert worst <= 1e-10, worst
+
+
+def test_dopri5_fp64_smooth_protocol_within_10_atol():
+    """Constant-voltage protocol: the accept/reject sequence is reproduced and the traces agree
+    within 10 x atol (1e-8), the loss to 1e-8 relative."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn('d2', double=True)
+    tt = np.linspace(0, 500, 5001)
+    vv = np.full_like(tt, 20.0)
+    func.set_fixed_form_voltage_protocol(tt, vv)
+    ofunc.set_fixed_form_voltage_protocol(tt, vv)
+    t = torch.linspace(0., 500., 251, dtype=torch.float64)
+    y0 = torch.tensor([[0.1, 0.9]], dtype=torch.float64)
+    st = {}
+    with torch.no_grad():
+        want = ro.odeint(ofunc, y0, t, stats=st)
+    data = torch.zeros(251, dtype=torch.float64)
+    res = ikr.integrate(func, y0.cuda(), t, data=data, want_current=True, E=-86.0)
+    got = res.y.cpu()
+    stats = res.stats.cpu().numpy()[0]
+    assert (stats[0], stats[1]) == (st['n_accept'], st['n_reject'])
+    assert (got - want).abs().max().item() <= 1e-8
+    i_want = want[:, 0, 0] * want[:, 0, 1] * (20.0 + 86.0)
+    loss_want = i_want.abs().mean().item()
+    loss_got = res.sae.cpu()[0].item() / 251
+    assert abs(loss_got - loss_want) <= 1e-8 * abs(loss_want)
+
+
+def test_dopri5_fp64_envelope_on_ap_protocol():
+    """Whole-trace agreement on the AP protocol is limited by the controller's sensitivity: the
+    oracle differs from *itself* by ~2e-5 when its first step is perturbed by 1e-6.  The CUDA
+    trace must sit inside that envelope around a tight-tolerance solution."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn('s1', double=True)
+    t_tab, v_tab = protocols.ap2hz()
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    ofunc.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 600., 301, dtype=torch.float64)
+    y0 = torch.tensor([[0., 1.]], dtype=torch.float64)
+    with torch.no_grad():
+        base = ro.odeint(ofunc, y0, t)
+        tight = ro.odeint(ofunc, y0, t, rtol=1e-10, atol=1e-12)
+    oracle_err = (base - tight).abs().max().item()
+    got = ikr.odeint(func, y0.cuda(), t).cpu()
+    assert (got - tight).abs().max().item() <= 3 * oracle_err + 1e-9
+    # and a tight-tolerance CUDA run converges to the tight oracle
+    got_tight = ikr.odeint(func, y0.cuda(), t, rtol=1e-10, atol=1e-12).cpu()
+    assert (got_tight - tight).abs().max().item() <= 5e-8
+
+
+@pytest.mark.parametrize('study', kat.STUDIES)
+def test_logged_ap2hz_loss_fp32_as_shipped(study):
+    """Reference-logged AP-2Hz loss ({study}/log2:4) with the CUDA path in the NN leg."""
+    torch.set_num_threads(1)
+    row = kat.KAT[study][0]
+    t_tab, v_tab, t_out = kat.row_protocol(row)
+    i_gt = kat.gt_current(study, t_tab, v_tab, t_out).reshape(-1)
+    func, _ = _nn(study)
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    y = ikr.odeint(func, torch.tensor([[0., 1.]]).cuda(), t_out).cpu()
+    i_nn = (y[:, 0, 0] * y[:, 0, 1] * (func._v(t_out).reshape(-1) + 86))
+    loss = torch.mean(torch.abs(i_nn - i_gt)).item()
+    assert abs(loss - row['loss']) < 5e-5, (loss, row['loss'])
+
+
+def test_logged_step_protocol_losses_fp32_fused_loss():
+    """pr3 +40 mV and pr5 -120 mV rows of s1/log2 through the fused current/loss epilogue, with
+    both sweeps' trajectories in one batch each."""
+    torch.set_num_threads(1)
+    func, _ = _nn('s1')
+    for idx in (9, 11):
+        row = kat.KAT['s1'][idx]
+        t_tab, v_tab, t_out = kat.row_protocol(row)
+        i_gt = kat.gt_current('s1', t_tab, v_tab, t_out).reshape(-1)
+        func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        y0 = torch.tensor([[0., 1.]] * 5)
+        res = ikr.integrate(func, y0.cuda(), t_out, data=i_gt.float(), E=-86.0, want_y=False)
+        mae = (res.sae / len(t_out)).cpu().numpy()
+        assert np.all(np.abs(mae - row['loss']) < 5e-5), (mae, row['loss'])
+        assert np.all(mae == mae[0])          # identical lanes give identical results
+
+
+def test_batch_is_independent_trajectories_and_tile_invariant():
+    func, _ = _nn('d1')
+    t_tab, v_tab = protocols.pr4_inactivation_standin(-20)
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 300., 151)
+    rng = np.random.RandomState(3)
+    B = 333                                     # ragged: not a multiple of any tile
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1),
+                      dtype=torch.float32).cuda()
+    full = ikr.integrate(func, y0, t)
+    for tile in (8, 64):
+        part = ikr.integrate(func, y0[:77], t, options={'tile_m': tile})
+        assert torch.equal(part.y, full.y[:, :77])
+        assert torch.equal(part.stats, full.stats[:77])
+    assert full.geometry['n_tiles'] * full.geometry['tile_m'] >= B
+
+
+def test_fused_current_and_loss_epilogue():
+    func, _ = _nn('d1')
+    t_tab, v_tab = protocols.ap2hz()
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 150., 76)
+    B = 40
+    rng = np.random.RandomState(5)
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1),
+                      dtype=torch.float32).cuda()
+    g = torch.tensor(rng.lognormal(0, 0.2, B), dtype=torch.float32).cuda()
+    data = torch.tensor(rng.normal(0, 0.1, (76, B)), dtype=torch.float32).cuda()
+    res = ikr.integrate(func, y0, t, g=g, E=-86.0, data=data, want_current=True)
+    v = func._v(t).reshape(-1).cuda()
+    cur = (g[None, :] * res.y[:, :, 0] * res.y[:, :, 1]).double() * (v[:, None] + 86.0)
+    np.testing.assert_allclose(res.current.double().cpu().numpy(), cur.cpu().numpy(), rtol=2e-7,
+                               atol=1e-9)
+    diff = cur - data.double()
+    np.testing.assert_allclose(res.sse.cpu().numpy(), (diff ** 2).sum(0).cpu().numpy(), rtol=1e-10)
+    np.testing.assert_allclose(res.sae.cpu().numpy(), diff.abs().sum(0).cpu().numpy(), rtol=1e-10)
+    # shared (T,) data trace
+    res1 = ikr.integrate(func, y0, t, g=g, data=data[:, 0], want_y=False)
+    diff1 = cur - data[:, :1].double()
+    np.testing.assert_allclose(res1.sse.cpu().numpy(), (diff1 ** 2).sum(0).cpu().numpy(),
+                               rtol=1e-10)
+
+
+def test_out_of_table_time_uses_minus_80():
+    """dopri5 overshoots the table end (train-s1.py:234-237 fallback branch)."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn('s1', double=True)
+    tt = np.linspace(0, 100, 1001)
+    vv = np.where(tt < 50, -80.0, 20.0)
+    func.set_fixed_form_voltage_protocol(tt, vv)
+    ofunc.set_fixed_form_voltage_protocol(tt, vv)
+    t = torch.tensor([0., 30., 60., 100.], dtype=torch.float64)
+    y0 = torch.tensor([[0., 1.]], dtype=torch.float64)
+    st = {}
+    with torch.no_grad():
+        want = ro.odeint(ofunc, y0, t, stats=st)
+    res = ikr.integrate(func, y0.cuda(), t)
+    assert (res.y.cpu() - want).abs().max().item() < 1e-6
+    # rk4 evaluates exactly at the table end and beyond it with perturb/overshoot-free grid
+    t2 = torch.linspace(90., 100., 21, dtype=torch.float64)
+    want2 = _oracle_batch(ofunc, y0, t2, method='rk4').numpy()
+    got2 = ikr.odeint(func, y0.cuda(), t2, method='rk4').cpu().numpy()
+    assert _rel(got2, want2) <= 1e-10
+
+
+def test_edge_cases_and_status_codes():
+    func, _ = _nn('s1')
+    t_tab, v_tab = protocols.pr2_time_constant(30)
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    y0 = torch.tensor([[0., 1.], [0.1, 0.8]]).cuda()
+    # single output time: solution is y0
+    y = ikr.odeint(func, y0, torch.tensor([0.]))
+    assert torch.equal(y[0], y0)
+    # 1-D y0 like torchdiffeq accepts
+    y1 = ikr.odeint(func, y0[0], torch.linspace(0., 10., 3))
+    assert y1.shape == (3, 2)
+    # CPU tensors in, CPU tensors out
+    ycpu = ikr.odeint(func, y0.cpu(), torch.linspace(0., 10., 3))
+    assert not ycpu.is_cuda
+    # max_num_steps -> torchdiffeq's assertion text
+    with pytest.raises(AssertionError, match='max_num_steps exceeded'):
+        ikr.odeint(func, y0, torch.linspace(0., 2000., 3), options={'max_num_steps': 5})
+    # non-finite state
+    bad = torch.tensor([[float('nan'), 1.]]).cuda()
+    with pytest.raises(AssertionError, match='underflow in dt|non-finite'):
+        ikr.odeint(func, bad, torch.linspace(0., 10., 3))
+    # legacy option names only warn (train-d0.py:436)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter('always')
+        ikr.odeint(func, y0, torch.linspace(0., 10., 3),
+                   options={'grid_points': np.array([1.0]), 'eps': 1e-6})
+    assert any('Unexpected arguments' in str(w.message) for w in rec)
+    with pytest.raises(ValueError):
+        ikr.odeint(func, y0, torch.tensor([0., 2., 1.]))
+    with pytest.raises(TypeError):
+        ikr.odeint(torch.nn.Linear(2, 2), y0, torch.linspace(0., 10., 3))
+
+
+def test_reference_module_is_accepted_unchanged():
+    """A module that is *not* ours but looks like the reference's ODEFunc (attributes only) is
+    introspected and integrated; weights load from the shipped state-dict file."""
+    import torch.nn as nn
+
+    class ODEFunc(nn.Module):                  # shaped like train-s1.py:181-216
+        def __init__(self):
+            super().__init__()
+            self.net = ikr.build_net(5, 200)
+            self.vrange = torch.tensor([100.])
+            self.netscale = torch.tensor([1000.])
+            self.p5, self.p6, self.p7, self.p8 = rm.HH_B06[4:]
+
+        def set_fixed_form_voltage_protocol(self, t, v):
+            self._t_regular = t
+            self._v_regular = v
+
+    f = ODEFunc()
+    f.load_state_dict(torch.load(kat.weights_path('s1')))
+    f.eval()
+    mine, _ = _nn('s1')
+    t_tab, v_tab = protocols.pr3_activation(0)
+    f.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    mine.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 1500., 301)
+    y0 = torch.tensor([[0., 1.]]).cuda()
+    with torch.no_grad():
+        assert torch.equal(ikr.odeint(f, y0, t), ikr.odeint(mine, y0, t))
+
+
+def test_interp_kernel_matches_scipy():
+    import ctypes
+    from scipy.interpolate import interp1d
+    from neural_ode_ion_channels_b200 import _cabi, solver
+    t_tab, v_tab = protocols.ap2hz()
+    rng = np.random.RandomState(0)
+    tq = np.concatenate([rng.uniform(0, 3499.9, 5000), t_tab[::700], [3499.9, 3500.0, -1.0]])
+    func, _ = _nn('s1')
+    for compact in (False, True):
+        tt, vv = protocols.compact_table(t_tab, v_tab) if compact else (t_tab, v_tab)
+        spec = ikr.describe(func)
+        d = solver._make_desc(spec, torch.float32, 'dopri5', len(tt), solver._uniform_hint(tt),
+                              1e-7, 1e-9, {})
+        dt, dv = torch.from_numpy(tt).cuda(), torch.from_numpy(vv).cuda()
+        q = torch.from_numpy(tq).cuda()
+        out = torch.empty_like(q)
+        rc = _cabi.lib().ikr_interp_protocol(ctypes.byref(d), dt.data_ptr(), dv.data_ptr(),
+                                             q.data_ptr(), q.numel(), out.data_ptr(), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        want = np.full(len(tq), -80.0)
+        inside = (tq >= t_tab[0]) & (tq <= t_tab[-1])
+        want[inside] = interp1d(t_tab, v_tab)(tq[inside])
+        assert np.array_equal(out.cpu().numpy(), want)      # bit-exact, compacted or not
