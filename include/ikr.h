@@ -59,10 +59,6 @@ typedef struct ikr_desc {
   int32_t mlp_dtype;      /* dtype of the MLP weights and arithmetic                             */
   int32_t time_f32;       /* rk4: grid arithmetic in fp32 (caller passed an fp32 `t`)            */
   int32_t rk4_perturb;    /* rk4 `perturb` option (default 0)                                    */
-  int32_t table_len;      /* protocol table samples                                              */
-  int32_t table_uniform;  /* 1: table_t[i] ~= table_t0 + i / table_inv_dt (index hint only)      */
-  double table_t0;
-  double table_inv_dt;
   double p[8];            /* p1..p8 (p1..p4 used when nn_d)                                       */
   double vrange;          /* 100   */
   double netscale;        /* 1000  */
@@ -75,15 +71,22 @@ typedef struct ikr_desc {
   int32_t reserved;
 } ikr_desc;
 
-/* Batch I/O of one forward call.  All pointers are DEVICE pointers unless stated.
- * Layouts follow torchdiffeq: y_out is (T, B, 2) in the state dtype.                            */
+/* One JOB = one protocol table + one batch of trajectories, i.e. the shape of one reference
+ * `odeint` call (train-s1.py:326-327).  A forward call takes an array of jobs that share the MLP
+ * weights; their trajectory tiles are scheduled through one queue so the whole GPU stays busy.
+ * All pointers are DEVICE pointers.  Layouts follow torchdiffeq: y_out is (T, B, 2).            */
 typedef struct ikr_io {
   int64_t B;              /* trajectories                                                        */
   int64_t T;              /* output times                                                        */
   int64_t G;              /* rk4: grid points (== T and grid == t_out unless step_size given)    */
-  const void* weights;    /* packed MLP parameters, see ikr_packed_weight_elems()                */
+  const void* weights;    /* packed MLP parameters (job 0's pointer is used for the launch)      */
   const double* table_t;  /* [table_len] protocol time (ms)                                      */
   const double* table_v;  /* [table_len] protocol voltage (mV)                                   */
+  int32_t table_len;      /* protocol table samples                                              */
+  int32_t table_uniform;  /* 1: table_t[i] ~= table_t0 + i / table_inv_dt (index hint only)      */
+  double table_t0;
+  double table_inv_dt;
+  double cost_hint;       /* relative cost of one trajectory (e.g. protocol duration); 0 => T    */
   const void* y0;         /* [B,2] state dtype: (a, r)                                           */
   const double* t_out;    /* [T] strictly increasing output times (fp64 copy of `t`)             */
   const double* grid;     /* [G] rk4 step grid (fp64)                                            */
@@ -127,16 +130,19 @@ int64_t ikr_param_count(const ikr_desc* d);
 /* out[8] = npad, off_w0, off_wt, off_bh, off_wl, off_wn, total elems, chunk rows kc */
 int ikr_packed_layout(const ikr_desc* d, int64_t out[8]);
 
-/* trajectories per CTA the library will use for (desc, B) on the current device */
-int32_t ikr_tile_m(const ikr_desc* d, int64_t B);
+/* trajectories per CTA the library will use for jobs of the given batch sizes */
+int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B);
 /* out[8] = tile_m, threads/CTA, grid, dynamic smem bytes, n_tiles, kc, chunks/layer, SM count */
-int ikr_launch_geometry(const ikr_desc* d, int64_t B, int64_t out[8]);
+int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[8]);
 
-size_t ikr_workspace_bytes(const ikr_desc* d, int64_t B, int64_t T, int32_t with_backward);
+/* device workspace (caller-allocated) needed by ikr_forward / ikr_backward for n_jobs jobs   */
+size_t ikr_workspace_bytes(const ikr_desc* d, int32_t n_jobs, int64_t B_total,
+                           int32_t with_backward);
 
-/* Forward integration of B independent trajectories (== B separate B=1 reference calls).       */
-int ikr_forward(const ikr_desc* d, const ikr_io* io, void* workspace, size_t workspace_bytes,
-                void* cuda_stream);
+/* Forward integration: for every job, B independent trajectories (== B separate B=1 reference
+ * calls), each with its own adaptive step size.  `jobs` is a HOST array of n_jobs descriptors. */
+int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* workspace,
+                size_t workspace_bytes, void* cuda_stream);
 
 /* Backward sweep: gradients of a scalar loss w.r.t. the MLP parameters (and optionally y0, g). */
 int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, void* workspace,
@@ -144,8 +150,8 @@ int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, voi
 
 /* V(t) of the protocol table at T query times (scipy interp1d linear semantics; out-of-table
  * => -80 like the callers' ValueError branch, train-s1.py:234-237).                             */
-int ikr_interp_protocol(const ikr_desc* d, const double* table_t, const double* table_v,
-                        const double* t_query, int64_t T, double* v_out, void* cuda_stream);
+int ikr_interp_protocol(const ikr_io* table, const double* t_query, int64_t T, double* v_out,
+                        void* cuda_stream);
 
 /* FMA-pipe micro-benchmark used by bench.py for the roofline denominator: runs `iters`
  * dependent-free FFMA (dtype F32) or DFMA (F64) per thread on every SM and returns the elapsed

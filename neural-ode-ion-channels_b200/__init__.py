@@ -11,7 +11,7 @@ Public surface (mirrors what the reference scripts use on this path):
 from . import protocols  # noqa: F401
 from .models import (ARCHITECTURES, PARAMETER_SETS, ODEFunc, ODEFuncNNd, ODEFuncNNf,  # noqa: F401
                      build_net, load_weights)
-from .solver import IkrResult, describe, integrate, odeint  # noqa: F401
+from .solver import IkrResult, describe, integrate, integrate_many, odeint  # noqa: F401
 
-__all__ = ['odeint', 'integrate', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
+__all__ = ['odeint', 'integrate', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
            'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols']

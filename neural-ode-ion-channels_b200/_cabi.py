@@ -25,8 +25,6 @@ class IkrDesc(ctypes.Structure):
     _fields_ = [
         ('n_layers', c_i32), ('n_nodes', c_i32), ('nn_d', c_i32), ('method', c_i32),
         ('state_dtype', c_i32), ('mlp_dtype', c_i32), ('time_f32', c_i32), ('rk4_perturb', c_i32),
-        ('table_len', c_i32), ('table_uniform', c_i32),
-        ('table_t0', c_f64), ('table_inv_dt', c_f64),
         ('p', c_f64 * 8),
         ('vrange', c_f64), ('netscale', c_f64), ('negative_slope', c_f64),
         ('rtol', c_f64), ('atol', c_f64), ('first_step', c_f64),
@@ -39,7 +37,10 @@ class IkrDesc(ctypes.Structure):
 class IkrIO(ctypes.Structure):
     _fields_ = [
         ('B', c_i64), ('T', c_i64), ('G', c_i64),
-        ('weights', c_vp), ('table_t', c_vp), ('table_v', c_vp), ('y0', c_vp), ('t_out', c_vp),
+        ('weights', c_vp), ('table_t', c_vp), ('table_v', c_vp),
+        ('table_len', c_i32), ('table_uniform', c_i32), ('table_t0', c_f64),
+        ('table_inv_dt', c_f64), ('cost_hint', c_f64),
+        ('y0', c_vp), ('t_out', c_vp),
         ('grid', c_vp), ('v_out', c_vp), ('g', c_vp), ('e_rev', c_vp), ('e_scalar', c_f64),
         ('data', c_vp), ('data_B', c_i64),
         ('y_out', c_vp), ('i_out', c_vp), ('loss_out', c_vp), ('stats_out', c_vp),
@@ -78,19 +79,20 @@ def lib():
     L.ikr_param_count.restype = c_i64
     L.ikr_param_count.argtypes = [ctypes.POINTER(IkrDesc)]
     L.ikr_tile_m.restype = c_i32
-    L.ikr_tile_m.argtypes = [ctypes.POINTER(IkrDesc), c_i64]
+    L.ikr_tile_m.argtypes = [ctypes.POINTER(IkrDesc), c_i32, ctypes.POINTER(c_i64)]
     L.ikr_launch_geometry.restype = c_i32
-    L.ikr_launch_geometry.argtypes = [ctypes.POINTER(IkrDesc), c_i64, ctypes.POINTER(c_i64)]
+    L.ikr_launch_geometry.argtypes = [ctypes.POINTER(IkrDesc), c_i32, ctypes.POINTER(c_i64),
+                                      ctypes.POINTER(c_i64)]
     L.ikr_workspace_bytes.restype = ctypes.c_size_t
-    L.ikr_workspace_bytes.argtypes = [ctypes.POINTER(IkrDesc), c_i64, c_i64, c_i32]
+    L.ikr_workspace_bytes.argtypes = [ctypes.POINTER(IkrDesc), c_i32, c_i64, c_i32]
     L.ikr_forward.restype = c_i32
-    L.ikr_forward.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(IkrIO), c_vp,
+    L.ikr_forward.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(IkrIO), c_i32, c_vp,
                               ctypes.c_size_t, c_vp]
     L.ikr_backward.restype = c_i32
     L.ikr_backward.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(IkrIO),
                                ctypes.POINTER(IkrBwdIO), c_vp, ctypes.c_size_t, c_vp]
     L.ikr_interp_protocol.restype = c_i32
-    L.ikr_interp_protocol.argtypes = [ctypes.POINTER(IkrDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
+    L.ikr_interp_protocol.argtypes = [ctypes.POINTER(IkrIO), c_vp, c_i64, c_vp, c_vp]
     L.ikr_fma_peak.restype = c_i32
     L.ikr_fma_peak.argtypes = [c_i32, c_i64, ctypes.POINTER(c_f64), c_vp]
     if L.ikr_abi_version() != 1:
@@ -118,6 +120,8 @@ def packed_layout(desc):
 
 def launch_geometry(desc, B):
     out = (c_i64 * 8)()
-    check(lib().ikr_launch_geometry(ctypes.byref(desc), B, out), 'ikr_launch_geometry')
+    Bs = [int(B)] if not isinstance(B, (list, tuple)) else [int(b) for b in B]
+    arr = (c_i64 * len(Bs))(*Bs)
+    check(lib().ikr_launch_geometry(ctypes.byref(desc), len(Bs), arr, out), 'ikr_launch_geometry')
     return {'tile_m': out[0], 'threads': out[1], 'grid': out[2], 'smem': out[3],
             'n_tiles': out[4], 'kc': out[5], 'cpl': out[6], 'sms': out[7]}

@@ -30,7 +30,7 @@ class _OdeintFn(torch.autograd.Function):
         desc, io = res._desc, res._io
         dev = res.y.device
         with torch.cuda.device(dev):
-            dm = _device_model(ctx.func, dev, True)
+            dm = _device_model(ctx.func, dev)
             spec = dm.spec
             lib = _cabi.lib()
             n_par = lib.ikr_param_count(ctypes.byref(desc))
@@ -45,7 +45,7 @@ class _OdeintFn(torch.autograd.Function):
             bio.weights_bwd = io.weights
             bio.grad_weights = grad_flat.data_ptr()
             bio.grad_y0 = grad_y0.data_ptr()
-            ws_bytes = lib.ikr_workspace_bytes(ctypes.byref(desc), B, res.y.shape[0], 1)
+            ws_bytes = lib.ikr_workspace_bytes(ctypes.byref(desc), 1, B, 1)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             stream = torch.cuda.current_stream(dev)
             _cabi.check(lib.ikr_backward(ctypes.byref(desc), ctypes.byref(io), ctypes.byref(bio),

@@ -2,8 +2,10 @@
 // device allocation, no global state, stream-ordered, never synchronises (except ikr_fma_peak).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "../../include/ikr.h"
 #include "ikr_backward.cuh"
@@ -18,7 +20,7 @@ constexpr int kMaxThreads = 512;
 
 struct Geometry {
   int npad, TN, NG, kc, cpl;
-  int M, MG, threads;
+  int M, MG, threads, n_worker_warps;
   long long n_tiles;
   int grid;
   size_t smem;
@@ -72,37 +74,53 @@ void mlp_layout(const ikr_desc* d, int* npad, int* kc, int* cpl, long long off[5
   *total = o;
 }
 
-Geometry make_geometry(const ikr_desc* d, long long B) {
+// candidate trajectory-group counts MG (tile M = 8 MG): multiples of 4 keep the quarter-warp
+// mapping bank-conflict free; 1..3 only serve tiny batches.
+const int kMgCandidates[] = {1, 2, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64};
+
+Geometry make_geometry(const ikr_desc* d, int n_jobs, const long long* B) {
   Geometry g;
   long long off[5], total;
   mlp_layout(d, &g.npad, &g.kc, &g.cpl, off, &total);
   g.TN = d->mlp_dtype == IKR_F32 ? 8 : 4;
   g.NG = g.npad / g.TN;
   g.sms = device_sms();
-  int mg_cap = kMaxThreads / g.NG;
-  if (mg_cap > kMaxThreads / 8) mg_cap = kMaxThreads / 8;
-  if (mg_cap < 1) mg_cap = 1;
-  while (mg_cap > 1 && fwd_smem_dyn(d, 8 * mg_cap, g.npad, g.kc) > kSmemLimit) --mg_cap;
-  int m_cap = 8 * mg_cap;
-  int M;
-  if (d->tile_m > 0) {
-    M = round_up(d->tile_m, 8);
-    if (M > m_cap) M = m_cap;
-  } else {
-    long long per_wave = (long long)g.sms * m_cap;
-    long long waves = (B + per_wave - 1) / per_wave;
-    if (waves < 1) waves = 1;
-    long long per_cta = (B + (long long)g.sms * waves - 1) / ((long long)g.sms * waves);
-    M = round_up((int)(per_cta < 1 ? 1 : per_cta), 8);
-    if (M > m_cap) M = m_cap;
+  long long b_total = 0;
+  for (int j = 0; j < n_jobs; ++j) b_total += B[j];
+  double best_score = -1.0;
+  int best_mg = 1;
+  const int forced = d->tile_m > 0 ? round_up(d->tile_m, 8) / 8 : 0;
+  for (int mg : kMgCandidates) {
+    const int M = 8 * mg;
+    const int workers = tile_worker_threads(mg, g.NG);
+    const int threads = round_up(workers > M ? workers : M, 32);
+    if (threads > kMaxThreads) continue;
+    if (fwd_smem_dyn(d, M, g.npad, g.kc) > kSmemLimit) continue;
+    if (forced) {
+      if (mg <= forced) best_mg = mg;       // largest feasible candidate not above the request
+      continue;
+    }
+    long long tiles = 0;
+    for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + M - 1) / M;
+    const double waves = (double)tiles / g.sms;
+    const double wave_eff = waves / (double)((tiles + g.sms - 1) / g.sms);
+    const double fill = (double)b_total / ((double)tiles * M);
+    const int warps = (workers + 31) / 32;
+    const double balance = (workers / 32.0) / (4.0 * ((warps + 3) / 4));
+    const double amort = (double)M / (M + 6.0);   // per-evaluation owner-phase overhead
+    const double score = wave_eff * fill * balance * amort;
+    if (score > best_score) { best_score = score; best_mg = mg; }
   }
-  g.M = M;
-  g.MG = M / 8;
-  g.threads = round_up(g.MG * g.NG > M ? g.MG * g.NG : M, 32);
-  g.n_tiles = (B + M - 1) / M;
+  g.MG = best_mg;
+  g.M = 8 * best_mg;
+  const int workers = tile_worker_threads(g.MG, g.NG);
+  g.n_worker_warps = (workers + 31) / 32;
+  g.threads = round_up(workers > g.M ? workers : g.M, 32);
+  g.n_tiles = 0;
+  for (int j = 0; j < n_jobs; ++j) g.n_tiles += (B[j] + g.M - 1) / g.M;
   g.grid = (int)(g.n_tiles < g.sms ? g.n_tiles : g.sms);
   if (g.grid < 1) g.grid = 1;
-  g.smem = fwd_smem_dyn(d, M, g.npad, g.kc);
+  g.smem = fwd_smem_dyn(d, g.M, g.npad, g.kc);
   return g;
 }
 
@@ -118,10 +136,17 @@ MlpView make_view(const ikr_desc* d, const void* weights) {
   return v;
 }
 
-SolverCfg make_cfg(const ikr_desc* d, const double* tab_t, const double* tab_v) {
+ProtocolTable make_table(const ikr_io* io) {
+  ProtocolTable t;
+  t.t = io->table_t; t.v = io->table_v; t.len = io->table_len; t.uniform = io->table_uniform;
+  t.t0 = io->table_t0; t.inv_dt = io->table_inv_dt;
+  return t;
+}
+
+SolverCfg make_cfg(const ikr_desc* d) {
   SolverCfg c;
-  c.tab.t = tab_t; c.tab.v = tab_v; c.tab.len = d->table_len; c.tab.uniform = d->table_uniform;
-  c.tab.t0 = d->table_t0; c.tab.inv_dt = d->table_inv_dt;
+  c.tab.t = nullptr; c.tab.v = nullptr; c.tab.len = 0; c.tab.uniform = 0;
+  c.tab.t0 = 0; c.tab.inv_dt = 0;
   for (int i = 0; i < 8; ++i) c.hp.p[i] = d->p[i];
   c.ctl.safety = d->safety; c.ctl.ifactor = d->ifactor; c.ctl.dfactor = d->dfactor;
   c.vrange = d->vrange; c.netscale = d->netscale;
@@ -188,60 +213,99 @@ int64_t ikr_param_count(const ikr_desc* d) {
   return 2 * n + n + L * (n * n + n) + n + 1;
 }
 
-int32_t ikr_tile_m(const ikr_desc* d, int64_t B) {
-  if (!valid_desc(d) || B < 1) return IKR_ERR_ARG;
-  return make_geometry(d, B).M;
+int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B) {
+  if (!valid_desc(d) || n_jobs < 1 || !B) return IKR_ERR_ARG;
+  for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
+  return make_geometry(d, n_jobs, (const long long*)B).M;
 }
 
-int ikr_launch_geometry(const ikr_desc* d, int64_t B, int64_t out[8]) {
-  if (!valid_desc(d) || B < 1 || !out) return IKR_ERR_ARG;
-  Geometry g = make_geometry(d, B);
+int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[8]) {
+  if (!valid_desc(d) || n_jobs < 1 || !B || !out) return IKR_ERR_ARG;
+  for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
+  Geometry g = make_geometry(d, n_jobs, (const long long*)B);
   out[0] = g.M; out[1] = g.threads; out[2] = g.grid; out[3] = (int64_t)g.smem;
   out[4] = g.n_tiles; out[5] = g.kc; out[6] = g.cpl; out[7] = g.sms;
   return 0;
 }
 
-size_t ikr_workspace_bytes(const ikr_desc* d, int64_t B, int64_t T, int32_t with_backward) {
-  if (!valid_desc(d) || B < 1 || T < 1) return 0;
-  size_t bytes = 256;
-  if (with_backward) bytes += bwd_workspace_bytes(d, B);
+size_t ikr_workspace_bytes(const ikr_desc* d, int32_t n_jobs, int64_t B_total,
+                           int32_t with_backward) {
+  if (!valid_desc(d) || n_jobs < 1 || B_total < 1) return 0;
+  size_t bytes = 256 + (size_t)n_jobs * sizeof(FwdJob);
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (with_backward) bytes += bwd_workspace_bytes(d, B_total);
   return bytes;
 }
 
-int ikr_forward(const ikr_desc* d, const ikr_io* io, void* workspace, size_t workspace_bytes,
-                void* cuda_stream) {
-  (void)workspace;
-  (void)workspace_bytes;
-  if (!valid_desc(d) || !io) return IKR_ERR_ARG;
-  if (io->B < 1 || io->T < 1 || !io->weights || !io->table_t || !io->table_v || !io->y0 ||
-      !io->t_out || !io->stats_out || d->table_len < 2)
-    return IKR_ERR_ARG;
-  if (d->method == IKR_RK4 && (!io->grid || io->G < 1)) return IKR_ERR_ARG;
-  if ((io->i_out || io->loss_out) && !io->v_out) return IKR_ERR_ARG;
-  if (io->data && io->data_B != 1 && io->data_B != io->B) return IKR_ERR_ARG;
-  if (io->ckpt_t && (!io->ckpt_y || io->ckpt_cap < 1)) return IKR_ERR_ARG;
-  if (io->T > 2147483647LL || io->G > 2147483647LL) return IKR_ERR_ARG;
+int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* workspace,
+                size_t workspace_bytes, void* cuda_stream) {
+  if (!valid_desc(d) || !jobs || n_jobs < 1 || n_jobs > 4096) return IKR_ERR_ARG;
+  for (int j = 0; j < n_jobs; ++j) {
+    const ikr_io* io = &jobs[j];
+    if (io->B < 1 || io->T < 1 || !io->weights || !io->table_t || !io->table_v || !io->y0 ||
+        !io->t_out || !io->stats_out || io->table_len < 2)
+      return IKR_ERR_ARG;
+    if (d->method == IKR_RK4 && (!io->grid || io->G < 1)) return IKR_ERR_ARG;
+    if ((io->i_out || io->loss_out) && !io->v_out) return IKR_ERR_ARG;
+    if (io->data && io->data_B != 1 && io->data_B != io->B) return IKR_ERR_ARG;
+    if (io->ckpt_t && (!io->ckpt_y || io->ckpt_cap < 1)) return IKR_ERR_ARG;
+    if (io->T > 2147483647LL || io->G > 2147483647LL) return IKR_ERR_ARG;
+    if (io->weights != jobs[0].weights) return IKR_ERR_ARG;
+  }
+  const size_t need = 256 + (size_t)n_jobs * sizeof(FwdJob);
+  if (!workspace || workspace_bytes < need) return IKR_ERR_WORKSPACE;
 
-  Geometry g = make_geometry(d, io->B);
-  if (g.smem > kSmemLimit) return IKR_ERR_UNSUPPORTED;
+  // longest jobs first (LPT) so that the dynamic tile queue balances the SMs
+  std::vector<int> order(n_jobs);
+  for (int j = 0; j < n_jobs; ++j) order[j] = j;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    const double ca = jobs[a].cost_hint > 0 ? jobs[a].cost_hint : (double)jobs[a].T;
+    const double cb = jobs[b].cost_hint > 0 ? jobs[b].cost_hint : (double)jobs[b].T;
+    return ca > cb;
+  });
+  std::vector<long long> Bs(n_jobs);
+  for (int j = 0; j < n_jobs; ++j) Bs[j] = jobs[order[j]].B;
+  Geometry g = make_geometry(d, n_jobs, Bs.data());
+  if (g.smem > kSmemLimit || g.threads > kMaxThreads) return IKR_ERR_UNSUPPORTED;
+
+  std::vector<FwdJob> table(n_jobs);
+  long long tile = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    const ikr_io* io = &jobs[order[j]];
+    FwdJob& fj = table[j];
+    fj.tab = make_table(io);
+    fj.B = io->B; fj.T = (int)io->T; fj.G = (int)io->G;
+    fj.tile_begin = tile;
+    tile += (io->B + g.M - 1) / g.M;
+    fj.y0 = io->y0; fj.t_out = io->t_out; fj.grid = io->grid; fj.v_out = io->v_out;
+    fj.g = io->g; fj.e_rev = io->e_rev; fj.e_scalar = io->e_scalar;
+    fj.data = io->data; fj.data_B = io->data_B;
+    fj.y_out = io->y_out; fj.i_out = io->i_out; fj.loss_out = io->loss_out;
+    fj.stats_out = io->stats_out;
+    fj.ckpt_cap = io->ckpt_cap; fj.ckpt_t = io->ckpt_t; fj.ckpt_y = io->ckpt_y;
+  }
+
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  unsigned char* ws = (unsigned char*)workspace;
+  if (cudaMemsetAsync(ws, 0, 256, st) != cudaSuccess) return IKR_ERR_DEVICE;
+  // pageable source: the runtime stages the bytes before returning, `table` may die afterwards
+  if (cudaMemcpyAsync(ws + 256, table.data(), (size_t)n_jobs * sizeof(FwdJob),
+                      cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return IKR_ERR_DEVICE;
 
   FwdParams p;
-  p.mlp = make_view(d, io->weights);
-  p.cfg = make_cfg(d, io->table_t, io->table_v);
+  p.mlp = make_view(d, jobs[0].weights);
+  p.cfg = make_cfg(d);
   p.method = d->method;
   p.time_f32 = d->time_f32;
   p.rk4_perturb = d->rk4_perturb;
   p.M = g.M; p.MG = g.MG; p.NG = g.NG;
-  p.B = io->B; p.T = (int)io->T; p.G = (int)io->G;
+  p.n_worker_warps = g.n_worker_warps;
+  p.n_jobs = n_jobs;
   p.n_tiles = g.n_tiles;
-  p.y0 = io->y0; p.t_out = io->t_out; p.grid = io->grid; p.v_out = io->v_out;
-  p.g = io->g; p.e_rev = io->e_rev; p.e_scalar = io->e_scalar;
-  p.data = io->data; p.data_B = io->data_B;
-  p.y_out = io->y_out; p.i_out = io->i_out; p.loss_out = io->loss_out;
-  p.stats_out = io->stats_out;
-  p.ckpt_cap = io->ckpt_cap; p.ckpt_t = io->ckpt_t; p.ckpt_y = io->ckpt_y;
+  p.jobs = reinterpret_cast<const FwdJob*>(ws + 256);
+  p.queue = reinterpret_cast<unsigned long long*>(ws);
 
-  cudaStream_t st = (cudaStream_t)cuda_stream;
   if (d->state_dtype == IKR_F32) return launch_forward<float, float>(p, g, st);
   if (d->mlp_dtype == IKR_F32) return launch_forward<double, float>(p, g, st);
   return launch_forward<double, double>(p, g, st);
@@ -253,12 +317,12 @@ int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, voi
   return bwd_dispatch(d, io, bio, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
 }
 
-int ikr_interp_protocol(const ikr_desc* d, const double* table_t, const double* table_v,
-                        const double* t_query, int64_t T, double* v_out, void* cuda_stream) {
-  if (!d || !table_t || !table_v || !t_query || !v_out || T < 1 || d->table_len < 2)
+int ikr_interp_protocol(const ikr_io* table, const double* t_query, int64_t T, double* v_out,
+                        void* cuda_stream) {
+  if (!table || !table->table_t || !table->table_v || !t_query || !v_out || T < 1 ||
+      table->table_len < 2)
     return IKR_ERR_ARG;
-  ProtocolTable tab{table_t, table_v, d->table_len, d->table_uniform, d->table_t0,
-                    d->table_inv_dt};
+  ProtocolTable tab = make_table(table);
   int threads = 256;
   long long blocks = (T + threads - 1) / threads;
   ikr_interp_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)cuda_stream>>>(tab, t_query, T,

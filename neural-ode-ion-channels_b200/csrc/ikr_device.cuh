@@ -30,6 +30,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
                "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
   uint32_t ok;
   asm volatile(
@@ -95,7 +98,8 @@ struct MlpSmem {
   W* xin;          // [2][M]   MLP inputs (nv, a)
   W* Hs;           // [npad][M] activations, feature-major
   W* Wr;           // [kStages][kc][npad] weight-chunk ring
-  uint64_t* full;  // [kStages]
+  uint64_t* full;   // [kStages] chunk landed (TMA complete_tx)
+  uint64_t* empty;  // [kStages] every worker warp is done reading the chunk
 };
 
 struct MlpPipe {
@@ -117,27 +121,86 @@ __device__ __forceinline__ void mlp_issue_chunk(const MlpView& mv, const MlpSmem
   bulk_g2s(sm.Wr + (size_t)stage * mv.kc * mv.npad, src, bytes, &sm.full[stage]);
 }
 
-// prologue: fill the ring (thread 0).  Called once per kernel after barrier init.
+// Barrier initialisation (thread 0) + prologue filling the ring.  `n_worker_warps` warps arrive on
+// the empty barriers.  Must be followed by __syncthreads() before first use.
+template <typename W>
+__device__ __forceinline__ void mlp_pipe_init(const MlpSmem<W>& sm, int n_worker_warps) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], n_worker_warps);
+    }
+    mbar_fence_init();
+  }
+}
 template <typename W>
 __device__ __forceinline__ void mlp_pipe_start(const MlpView& mv, const MlpSmem<W>& sm,
                                                MlpPipe& pp) {
   pp.q = 0;
   pp.issued = 0;
-  if (mv.L > 0 && threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) mlp_issue_chunk<W>(mv, sm, pp.issued++);
   }
 }
-// epilogue: wait for every chunk still in flight before the CTA exits
+// epilogue: wait for every chunk still in flight before the CTA exits (call after a barrier)
 template <typename W>
 __device__ __forceinline__ void mlp_pipe_drain(const MlpView& mv, const MlpSmem<W>& sm,
                                                MlpPipe& pp) {
-  if (mv.L > 0 && threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
     for (unsigned q = pp.q; q < pp.issued; ++q) mbar_wait(&sm.full[q % kStages], (q / kStages) & 1);
   }
 }
 
 template <typename W>
 __device__ __forceinline__ W leaky(W x, W slope) { return x > (W)0 ? x : x * slope; }
+
+// Thread -> register-tile coordinates.  Threads are grouped in quarter-warps (8 lanes): the 8
+// lanes of a quarter-warp own 8 consecutive trajectory groups gm of ONE feature group gn, so the
+// activation vector load of a quarter-warp is one aligned 128-byte line and the weight vector
+// load is a broadcast -- no shared-memory bank conflicts.  MG = 8a + rem: a remainder column of
+// rem in {1, 2, 4} packs 8/rem feature groups per quarter-warp; other remainders use one partly
+// idle quarter-warp per feature group.
+struct TileCoord {
+  int gm, gn;
+  bool worker;
+};
+__host__ __device__ inline int tile_pack(int rem) { return (rem == 1 || rem == 2 || rem == 4) ? 8 / rem : 1; }
+__host__ __device__ inline int tile_worker_threads(int MG, int NG) {
+  const int a = MG / 8, rem = MG % 8;
+  int qw = a * NG;
+  if (rem != 0) {
+    const int pk = tile_pack(rem);
+    qw += (NG + pk - 1) / pk;
+  }
+  return qw * 8;
+}
+__device__ __forceinline__ TileCoord tile_coord(int tid, int MG, int NG) {
+  const int a = MG / 8, rem = MG % 8;
+  const int qw = tid >> 3, l8 = tid & 7;
+  TileCoord c;
+  const int n_full = a * NG;
+  if (qw < n_full) {
+    c.gn = qw / a;
+    c.gm = (qw - c.gn * a) * 8 + l8;
+    c.worker = true;
+  } else if (rem != 0) {
+    const int pk = tile_pack(rem);
+    const int r = qw - n_full;
+    if (pk > 1) {
+      c.gn = pk * r + l8 / rem;
+      c.gm = 8 * a + l8 % rem;
+      c.worker = c.gn < NG;
+    } else {
+      c.gn = r;
+      c.gm = 8 * a + l8;
+      c.worker = c.gn < NG && l8 < rem;
+    }
+  } else {
+    c.gn = 0; c.gm = 0; c.worker = false;
+  }
+  if (!c.worker) { c.gm = 0; c.gn = 0; }
+  return c;
+}
 
 // row i (0..7) of a thread's register tile -> trajectory index inside the CTA tile.
 // Rows are split in 8/V groups of V consecutive trajectories so that every 16-byte
@@ -147,47 +210,23 @@ __device__ __forceinline__ int tile_row(int i, int gm, int MG) {
   return (i / V) * (MG * V) + gm * V + (i % V);
 }
 
-// Evaluate the MLP for the M trajectories of the CTA tile.  Inputs in sm.xin, result (the
-// network output before /netscale) returned to the owner threads tid < M.  Executed by every
-// thread of the CTA (contains barriers).  KEEP = also keep every layer's activations (backward).
+// Hidden layers of the tile MLP: activations in sm.Hs (feature-major) are replaced layer by
+// layer; weights arrive through the full/empty mbarrier ring (no CTA-wide barrier per chunk:
+// warps drift up to kStages-1 chunks apart; thread 0 refills a ring slot one chunk late so that
+// it rarely waits for the slowest warp).  Two CTA barriers per layer remain (all reads of the
+// input activations before the in-place overwrite, all writes before the next layer reads).
 template <typename W>
-__device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W>& sm,
-                                              MlpPipe& pp, int M, int MG, int NG) {
+__device__ __forceinline__ void mlp_tile_hidden(const MlpView& mv, const MlpSmem<W>& sm,
+                                                MlpPipe& pp, int M, int MG, const TileCoord& tc) {
   constexpr int TN = MlpTileCfg<W>::TN;
   constexpr int V = MlpTileCfg<W>::V;
   const int tid = threadIdx.x;
-  const bool worker = tid < MG * NG;
-  const int gm = tid % MG;
-  const int gn = tid / MG;
   const W slope = (W)mv.slope;
   const W* P = (const W*)mv.base;
+  const int gm = tc.gm, gn = tc.gn;
+  const bool worker = tc.worker;
+  const bool warp_works = __any_sync(0xffffffffu, worker);
 
-  __syncthreads();  // xin written by the owners; Hs free (previous output layer finished)
-
-  // ---- layer 0: Linear(2, n) + LeakyReLU ----------------------------------------------------
-  if (worker) {
-    const W* w0 = P + mv.off_w0;
-    W nv[kTM], aa[kTM];
-#pragma unroll
-    for (int i = 0; i < kTM; ++i) {
-      int m = tile_row<V>(i, gm, MG);
-      nv[i] = sm.xin[m];
-      aa[i] = sm.xin[M + m];
-    }
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      int col = gn * TN + j;
-      W wa = __ldg(w0 + col), wb = __ldg(w0 + mv.npad + col), bb = __ldg(w0 + 2 * mv.npad + col);
-#pragma unroll
-      for (int i = 0; i < kTM; ++i) {
-        W z = ikr_fma(wb, aa[i], ikr_fma(wa, nv[i], bb));
-        sm.Hs[(size_t)col * M + tile_row<V>(i, gm, MG)] = leaky(z, slope);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- hidden layers: Linear(n, n) + LeakyReLU, weights streamed through the ring ------------
   for (int layer = 0; layer < mv.L; ++layer) {
     W acc[kTM][TN];
 #pragma unroll
@@ -198,45 +237,54 @@ __device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W
     for (int c = 0; c < mv.cpl; ++c) {
       const unsigned q = pp.q;
       const unsigned stage = q % kStages;
-      mbar_wait(&sm.full[stage], (q / kStages) & 1);
       const int k0 = c * mv.kc;
       const int rows = min(mv.kc, mv.n - k0);
-      if (worker) {
-        const W* Hk = sm.Hs + (size_t)k0 * M + gm * V;
-        const W* Wk = sm.Wr + (size_t)stage * mv.kc * mv.npad + gn * TN;
+      if (warp_works) {
+        mbar_wait(&sm.full[stage], (q / kStages) & 1);
+        if (worker) {
+          const W* Hk = sm.Hs + (size_t)k0 * M + gm * V;
+          const W* Wk = sm.Wr + (size_t)stage * mv.kc * mv.npad + gn * TN;
 #pragma unroll 2
-        for (int kk = 0; kk < rows; ++kk) {
-          W a[kTM], b[TN];
-          if (sizeof(W) == 4) {
-            float4 a0 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M);
-            float4 a1 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M + MG * V);
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-            float4 b0 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad);
-            float4 b1 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad + 4);
-            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
-            b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
-          } else {
+          for (int kk = 0; kk < rows; ++kk) {
+            W a[kTM], b[TN];
+            if (sizeof(W) == 4) {
+              float4 a0 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M);
+              float4 a1 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M + MG * V);
+              a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+              a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+              float4 b0 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad);
+              float4 b1 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad + 4);
+              b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+              b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
+            } else {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              double2 av = *reinterpret_cast<const double2*>(Hk + (size_t)kk * M + g * MG * V);
-              a[2 * g] = av.x; a[2 * g + 1] = av.y;
+              for (int g = 0; g < 4; ++g) {
+                double2 av = *reinterpret_cast<const double2*>(Hk + (size_t)kk * M + g * MG * V);
+                a[2 * g] = av.x; a[2 * g + 1] = av.y;
+              }
+              double2 b0 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad);
+              double2 b1 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad + 2);
+              b[0] = b0.x; b[1] = b0.y; b[TN - 2] = b1.x; b[TN - 1] = b1.y;
             }
-            double2 b0 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad);
-            double2 b1 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad + 2);
-            b[0] = b0.x; b[1] = b0.y; b[TN - 2] = b1.x; b[TN - 1] = b1.y;
+#pragma unroll
+            for (int i = 0; i < kTM; ++i)
+#pragma unroll
+              for (int j = 0; j < TN; ++j) acc[i][j] = ikr_fma(a[i], b[j], acc[i][j]);
           }
-#pragma unroll
-          for (int i = 0; i < kTM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = ikr_fma(a[i], b[j], acc[i][j]);
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&sm.empty[stage]);
+        if (tid == 0 && q >= 1) {
+          // refill the slot of the previous chunk once every worker warp has released it
+          const unsigned qp = q - 1;
+          mbar_wait(&sm.empty[qp % kStages], (qp / kStages) & 1);
+          mlp_issue_chunk<W>(mv, sm, qp + kStages);
+          pp.issued = qp + kStages + 1;
         }
       }
-      __syncthreads();  // every warp is done with this ring stage (and, after the last chunk,
-                        // with the input activations)
       pp.q = q + 1;
-      if (tid == 0) mlp_issue_chunk<W>(mv, sm, pp.issued++);
     }
+    __syncthreads();  // all reads of this layer's input activations are done
 
     if (worker) {
       const W* bh = P + mv.off_bh + (long long)layer * mv.npad + gn * TN;
@@ -265,6 +313,47 @@ __device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W
     }
     __syncthreads();
   }
+}
+
+// Evaluate the MLP for the M trajectories of the CTA tile.  Inputs in sm.xin, result (the
+// network output before /netscale) returned to the owner threads tid < M.  Executed by every
+// thread of the CTA (contains barriers).
+template <typename W>
+__device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W>& sm,
+                                              MlpPipe& pp, int M, int MG, int NG) {
+  constexpr int TN = MlpTileCfg<W>::TN;
+  constexpr int V = MlpTileCfg<W>::V;
+  const int tid = threadIdx.x;
+  const TileCoord tc = tile_coord(tid, MG, NG);
+  const W slope = (W)mv.slope;
+  const W* P = (const W*)mv.base;
+
+  __syncthreads();  // xin written by the owners; Hs free (previous output layer finished)
+
+  // ---- layer 0: Linear(2, n) + LeakyReLU ----------------------------------------------------
+  if (tc.worker) {
+    const W* w0 = P + mv.off_w0;
+    W nv[kTM], aa[kTM];
+#pragma unroll
+    for (int i = 0; i < kTM; ++i) {
+      int m = tile_row<V>(i, tc.gm, MG);
+      nv[i] = sm.xin[m];
+      aa[i] = sm.xin[M + m];
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int col = tc.gn * TN + j;
+      W wa = __ldg(w0 + col), wb = __ldg(w0 + mv.npad + col), bb = __ldg(w0 + 2 * mv.npad + col);
+#pragma unroll
+      for (int i = 0; i < kTM; ++i) {
+        W z = ikr_fma(wb, aa[i], ikr_fma(wa, nv[i], bb));
+        sm.Hs[(size_t)col * M + tile_row<V>(i, tc.gm, MG)] = leaky(z, slope);
+      }
+    }
+  }
+  __syncthreads();
+
+  mlp_tile_hidden<W>(mv, sm, pp, M, MG, tc);
 
   // ---- output layer: Linear(n, 1), one owner thread per trajectory ---------------------------
   W out = (W)0;

@@ -13,17 +13,15 @@
 
 namespace ikr {
 
-struct FwdParams {
-  MlpView mlp;
-  SolverCfg cfg;
-  int method;       // 0 dopri5, 1 rk4
-  int time_f32;     // rk4
-  int rk4_perturb;  // rk4
-  int M, MG, NG;    // tile geometry
+// One job = one protocol table + one batch of trajectories (one reference `odeint` call shape).
+// A launch integrates any number of jobs that share the MLP weights: tiles of all jobs go
+// through one dynamic queue (longest jobs first) so that every SM stays busy.
+struct FwdJob {
+  ProtocolTable tab;
   long long B;
   int T;
   int G;
-  long long n_tiles;
+  long long tile_begin;  // first global tile index of this job
   const void* y0;
   const double* t_out;
   const double* grid;
@@ -42,6 +40,20 @@ struct FwdParams {
   void* ckpt_y;
 };
 
+struct FwdParams {
+  MlpView mlp;
+  SolverCfg cfg;     // cfg.tab is overwritten per job
+  int method;        // 0 dopri5, 1 rk4
+  int time_f32;      // rk4
+  int rk4_perturb;   // rk4
+  int M, MG, NG;     // tile geometry
+  int n_worker_warps;
+  int n_jobs;
+  long long n_tiles;
+  const FwdJob* jobs;        // device array [n_jobs]
+  unsigned long long* queue; // device tile counter (zeroed by the host before launch)
+};
+
 template <typename S>
 struct Vec2;
 template <>
@@ -52,10 +64,12 @@ struct Vec2<double> { typedef double2 type; };
 // shared memory carve-up (host and device agree through this one function)
 template <typename S, typename W>
 struct FwdSmemLayout {
-  size_t off_lanes, off_obs, off_xin, off_hs, off_wr, off_bar, total;
+  size_t off_lanes, off_obs, off_xin, off_hs, off_wr, off_bar, off_job, off_tile, total;
   __host__ __device__ FwdSmemLayout(int M, int npad, int kc) {
     size_t o = 0;
     off_bar = o; o += 64;
+    off_job = o; o += (sizeof(FwdJob) + 15) & ~(size_t)15;
+    off_tile = o; o += 16;
     off_lanes = o; o += (size_t)M * sizeof(Lane<S>); o = (o + 15) & ~(size_t)15;
     off_obs = o; o += (size_t)M * 2 * sizeof(double); o = (o + 15) & ~(size_t)15;
     off_xin = o; o += (size_t)2 * M * sizeof(W); o = (o + 127) & ~(size_t)127;
@@ -73,48 +87,65 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
   const FwdSmemLayout<S, W> lay(M, p.mlp.npad, p.mlp.kc);
   Lane<S>* lanes = reinterpret_cast<Lane<S>*>(smem_raw + lay.off_lanes);
   double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);  // [M][2] sse, sae
+  FwdJob* jobp = reinterpret_cast<FwdJob*>(smem_raw + lay.off_job);
+  long long* tile_slot = reinterpret_cast<long long*>(smem_raw + lay.off_tile);
   MlpSmem<W> sm;
   sm.full = reinterpret_cast<uint64_t*>(smem_raw + lay.off_bar);
+  sm.empty = sm.full + kStages;
   sm.xin = reinterpret_cast<W*>(smem_raw + lay.off_xin);
   sm.Hs = reinterpret_cast<W*>(smem_raw + lay.off_hs);
   sm.Wr = reinterpret_cast<W*>(smem_raw + lay.off_wr);
 
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
-    mbar_fence_init();
-  }
+  mlp_pipe_init<W>(sm, p.n_worker_warps);
   __syncthreads();
   MlpPipe pp;
   mlp_pipe_start<W>(p.mlp, sm, pp);
 
-  const SolverCfg& cfg = p.cfg;
-  const S* y0 = reinterpret_cast<const S*>(p.y0);
-  const S* gptr = reinterpret_cast<const S*>(p.g);
-  const S* eptr = reinterpret_cast<const S*>(p.e_rev);
-  const S* dptr = reinterpret_cast<const S*>(p.data);
-  S* y_out = reinterpret_cast<S*>(p.y_out);
-  S* i_out = reinterpret_cast<S*>(p.i_out);
-  S* ckpt_y = reinterpret_cast<S*>(p.ckpt_y);
-  const bool observe = (p.v_out != nullptr) && (p.i_out != nullptr || p.loss_out != nullptr);
+  SolverCfg cfg = p.cfg;
+  const bool owner = tid < M;
 
-  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const long long b = tile * M + tid;  // trajectory owned by this thread (if tid < M)
-    const bool owner = tid < M;
-    const bool valid = owner && b < p.B;
-    S g_b = (S)1, e_b = (S)p.e_scalar;
+  while (true) {
+    // ---- fetch the next tile from the queue and stage its job descriptor --------------------
+    if (tid == 0) {
+      long long tile = (long long)atomicAdd(p.queue, 1ULL);
+      *tile_slot = tile;
+      if (tile < p.n_tiles) {
+        int j = 0;
+        while (j + 1 < p.n_jobs && p.jobs[j + 1].tile_begin <= tile) ++j;
+        *jobp = p.jobs[j];
+      }
+    }
+    __syncthreads();
+    const long long tile = *tile_slot;
+    if (tile >= p.n_tiles) break;
+    const FwdJob& job = *jobp;
+    cfg.tab = job.tab;
+    const S* y0 = reinterpret_cast<const S*>(job.y0);
+    const S* gptr = reinterpret_cast<const S*>(job.g);
+    const S* eptr = reinterpret_cast<const S*>(job.e_rev);
+    const S* dptr = reinterpret_cast<const S*>(job.data);
+    S* y_out = reinterpret_cast<S*>(job.y_out);
+    S* i_out = reinterpret_cast<S*>(job.i_out);
+    S* ckpt_y = reinterpret_cast<S*>(job.ckpt_y);
+    const bool observe = (job.v_out != nullptr) && (job.i_out != nullptr || job.loss_out != nullptr);
+    const long long jB = job.B;
+    const int T = job.T;
+    const long long b = (tile - job.tile_begin) * M + tid;  // trajectory owned by this thread
+    const bool valid = owner && b < jB;
+    S g_b = (S)1, e_b = (S)job.e_scalar;
 
     // ---- output sample writer -----------------------------------------------------------
     auto emit = [&](int idx, S a, S r) {
       if (y_out) {
         typename Vec2<S>::type v;
         v.x = a; v.y = r;
-        *reinterpret_cast<typename Vec2<S>::type*>(y_out + ((size_t)idx * p.B + b) * 2) = v;
+        *reinterpret_cast<typename Vec2<S>::type*>(y_out + ((size_t)idx * jB + b) * 2) = v;
       }
       if (observe) {
-        double cur = (double)(g_b * a * r) * (p.v_out[idx] - (double)e_b);
-        if (i_out) i_out[(size_t)idx * p.B + b] = (S)cur;
+        double cur = (double)(g_b * a * r) * (job.v_out[idx] - (double)e_b);
+        if (i_out) i_out[(size_t)idx * jB + b] = (S)cur;
         if (dptr) {
-          double d = (double)dptr[(size_t)idx * p.data_B + (p.data_B == 1 ? 0 : b)];
+          double d = (double)dptr[(size_t)idx * job.data_B + (job.data_B == 1 ? 0 : b)];
           double diff = cur - d;
           obs[2 * tid] += diff * diff;
           obs[2 * tid + 1] += fabs(diff);
@@ -122,11 +153,11 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
       }
     };
     auto ckpt = [&](int step, double t0, double dt, S ya, S yr, S fa, S fr) -> bool {
-      if (!p.ckpt_t) return true;
-      if (step >= p.ckpt_cap) return false;
-      size_t o = (size_t)step * p.B + b;
-      p.ckpt_t[2 * o] = t0;
-      p.ckpt_t[2 * o + 1] = dt;
+      if (!job.ckpt_t) return true;
+      if (step >= job.ckpt_cap) return false;
+      size_t o = (size_t)step * jB + b;
+      job.ckpt_t[2 * o] = t0;
+      job.ckpt_t[2 * o + 1] = dt;
       ckpt_y[4 * o] = ya; ckpt_y[4 * o + 1] = yr; ckpt_y[4 * o + 2] = fa; ckpt_y[4 * o + 3] = fr;
       return true;
     };
@@ -139,7 +170,7 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
         if (gptr) g_b = gptr[b];
         if (eptr) e_b = eptr[b];
       }
-      lane_reset<S>(L, ya, yr, p.t_out[0], valid);
+      lane_reset<S>(L, ya, yr, job.t_out[0], valid);
       obs[2 * tid] = 0.0; obs[2 * tid + 1] = 0.0;
       if (valid) emit(0, ya, yr);
     }
@@ -166,7 +197,7 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
         out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
         if (owner) init_store_f1<S>(lanes[tid], cfg, (double)out);
       }
-      if (owner && p.T <= 1 && lane_active(lanes[tid])) lanes[tid].status = LANE_DONE;
+      if (owner && T <= 1 && lane_active(lanes[tid])) lanes[tid].status = LANE_DONE;
 
       while (true) {
         int act = 0;
@@ -184,13 +215,13 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
           out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
           if (owner) dp_store_stage<S>(lanes[tid], cfg, s, (double)out);
         }
-        if (owner) dp_finish_step<S>(lanes[tid], cfg, p.t_out, p.T, emit, ckpt);
+        if (owner) dp_finish_step<S>(lanes[tid], cfg, job.t_out, T, emit, ckpt);
       }
     } else {
       // ================================ rk4 (3/8 rule) ====================================
-      if (owner && p.T <= 1 && lane_active(lanes[tid])) lanes[tid].status = LANE_DONE;
-      for (int gi = 0; gi + 1 < p.G; ++gi) {
-        const double g0 = p.grid[gi], g1 = p.grid[gi + 1];
+      if (owner && T <= 1 && lane_active(lanes[tid])) lanes[tid].status = LANE_DONE;
+      for (int gi = 0; gi + 1 < job.G; ++gi) {
+        const double g0 = job.grid[gi], g1 = job.grid[gi + 1];
         int act = owner && lane_active(lanes[tid]) ? 1 : 0;
         if (!__syncthreads_or(act)) break;
 #pragma unroll 1
@@ -204,25 +235,25 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
           if (owner) rk4_store_stage<S>(lanes[tid], cfg, s, (double)out);
         }
         if (owner) {
-          if (p.ckpt_t && lane_active(lanes[tid]))
+          if (job.ckpt_t && lane_active(lanes[tid]))
             ckpt(gi, g0, g1 - g0, lanes[tid].ya, lanes[tid].yr, lanes[tid].ka[0], lanes[tid].kr[0]);
-          rk4_finish_step<S>(lanes[tid], g0, g1, p.time_f32 != 0, p.t_out, p.T, emit);
+          rk4_finish_step<S>(lanes[tid], g0, g1, p.time_f32 != 0, job.t_out, T, emit);
         }
       }
     }
 
     if (valid) {
       const Lane<S>& L = lanes[tid];
-      p.stats_out[4 * b + 0] = L.n_acc;
-      p.stats_out[4 * b + 1] = L.n_rej;
-      p.stats_out[4 * b + 2] = L.nfe;
-      p.stats_out[4 * b + 3] = L.status == LANE_DONE ? 0 : L.status;
-      if (p.loss_out) {
-        p.loss_out[2 * b] = obs[2 * tid];
-        p.loss_out[2 * b + 1] = obs[2 * tid + 1];
+      job.stats_out[4 * b + 0] = L.n_acc;
+      job.stats_out[4 * b + 1] = L.n_rej;
+      job.stats_out[4 * b + 2] = L.nfe;
+      job.stats_out[4 * b + 3] = L.status == LANE_DONE ? 0 : L.status;
+      if (job.loss_out) {
+        job.loss_out[2 * b] = obs[2 * tid];
+        job.loss_out[2 * b + 1] = obs[2 * tid + 1];
       }
     }
-    __syncthreads();  // lanes[] is re-initialised by the next tile
+    __syncthreads();  // lanes[] / job slot are re-initialised by the next tile
   }
   mlp_pipe_drain<W>(p.mlp, sm, pp);
 }

@@ -131,8 +131,7 @@ def _uniform_hint(t):
 # =============================================================================================
 # device-side model: packed weights + protocol table
 # =============================================================================================
-def _make_desc(spec: ModelSpec, state_dtype, method, tab_len, uniform, rtol, atol, opts,
-               time_f32=False):
+def _make_desc(spec: ModelSpec, state_dtype, method, rtol, atol, opts, time_f32=False):
     d = _cabi.IkrDesc()
     d.n_layers, d.n_nodes, d.nn_d = spec.n_layers, spec.n_nodes, int(spec.nn_d)
     d.method = _cabi.DOPRI5 if method == 'dopri5' else _cabi.RK4
@@ -140,8 +139,6 @@ def _make_desc(spec: ModelSpec, state_dtype, method, tab_len, uniform, rtol, ato
     d.mlp_dtype = _cabi.F32 if spec.mlp_dtype == torch.float32 else _cabi.F64
     d.time_f32 = int(time_f32)
     d.rk4_perturb = int(bool(opts.get('perturb', False)))
-    d.table_len = tab_len
-    d.table_uniform, d.table_t0, d.table_inv_dt = uniform
     for i in range(8):
         d.p[i] = spec.p[i]
     d.vrange, d.netscale, d.negative_slope = spec.vrange, spec.netscale, spec.negative_slope
@@ -195,23 +192,53 @@ def unpack_grads(spec: ModelSpec, flat):
     return out
 
 
-class _DeviceModel:
-    """Packed weights + protocol table resident on one GPU (cached on the func object)."""
+class _DeviceTable:
+    """One protocol table resident on the GPU (compacted when that is bit-exact)."""
 
-    def __init__(self, func, device, use_compaction):
-        self.spec = describe(func)
-        t, v = _protocol_arrays(func)
-        self.table_key = (t.ctypes.data, v.ctypes.data, len(t), float(t[0]), float(t[-1]),
-                          float(v.sum()), use_compaction)
+    def __init__(self, t, v, device, use_compaction):
         if use_compaction:
             t, v = compact_table(t, v)
         self.uniform = _uniform_hint(t)
-        self.tab_len = len(t)
-        self.tab_t = torch.from_numpy(t).to(device)
-        self.tab_v = torch.from_numpy(v).to(device)
+        self.len = len(t)
+        self.t = torch.from_numpy(t).to(device)
+        self.v = torch.from_numpy(v).to(device)
+        self.duration = float(t[-1] - t[0])
+
+    def fill(self, io):
+        io.table_t, io.table_v, io.table_len = self.t.data_ptr(), self.v.data_ptr(), self.len
+        io.table_uniform, io.table_t0, io.table_inv_dt = self.uniform
+
+
+def _table_key(t, v, use_compaction):
+    return (t.ctypes.data, v.ctypes.data, len(t), float(t[0]), float(t[-1]), float(v.sum()),
+            bool(use_compaction))
+
+
+class _DeviceModel:
+    """Packed weights + protocol tables resident on one GPU (cached on the func object)."""
+
+    def __init__(self, func, device):
+        self.spec = describe(func)
         self.device = device
         self.weights = None
         self.weights_key = None
+        self.tables = {}
+
+    def table(self, t, v, use_compaction=True):
+        t = np.ascontiguousarray(np.asarray(t, dtype=np.float64).reshape(-1))
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+        if len(t) != len(v) or len(t) < 2:
+            raise TypeError('odeint: protocol table needs >= 2 samples of equal length')
+        key = _table_key(t, v, use_compaction)
+        tab = self.tables.get(key)
+        if tab is None:
+            if not np.all(np.diff(t) > 0):
+                raise TypeError('odeint: protocol table times must be strictly increasing')
+            if len(self.tables) > 256:
+                self.tables.clear()
+            tab = _DeviceTable(t, v, self.device, use_compaction)
+            self.tables[key] = tab
+        return tab
 
     def weights_for(self, desc):
         key = tuple((p.data_ptr(), p._version) for m in self.spec.linears
@@ -222,14 +249,11 @@ class _DeviceModel:
         return self.weights
 
 
-def _device_model(func, device, use_compaction):
+def _device_model(func, device):
     cache = func.__dict__.setdefault('_ikr_b200_cache', {})
     dm = cache.get(device)
-    t, v = _protocol_arrays(func)
-    key = (t.ctypes.data, v.ctypes.data, len(t), float(t[0]), float(t[-1]), float(v.sum()),
-           use_compaction)
-    if dm is None or dm.table_key != key:
-        dm = _DeviceModel(func, device, use_compaction)
+    if dm is None:
+        dm = _DeviceModel(func, device)
         cache[device] = dm
     else:
         dm.spec = describe(func)
@@ -303,19 +327,85 @@ def _raise_on_status(stats):
             '' if idx.numel() == 1 else ' and %d more' % (idx.numel() - 1)))
 
 
-def integrate(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, g=None, E=-86.0,
-              data=None, want_y=True, want_current=False, want_ckpt=False, device=None):
-    """Forward integration with the fused observation/loss epilogue.
+def _prepare_job(dm, desc, method, opts, dev, lib, sptr, job, state_dtype):
+    """Upload one job's inputs, allocate its outputs and fill its ``ikr_io``."""
+    y0, t = job['y0'], job['t_cpu']
+    B, T = y0.shape[0], t.numel()
+    proto = job.get('protocol')
+    if proto is None:
+        proto = _protocol_arrays(job['func'])
+    tab = dm.table(proto[0], proto[1], opts.get('compact_table', True))
+    io = _cabi.IkrIO()
+    io.B, io.T = B, T
+    tab.fill(io)
+    io.cost_hint = float(t[-1] - t[0]) if T > 1 else 1.0
+    y0_d = y0.detach().to(dev, non_blocking=True).contiguous()
+    t_d = t.to(torch.float64).to(dev, non_blocking=True)
+    io.y0, io.t_out = y0_d.data_ptr(), t_d.data_ptr()
+    keep = [y0_d, t_d, tab]
+    if method == 'rk4':
+        grid = _rk4_grid(t, opts.get('step_size')).to(dev)
+        io.grid, io.G = grid.data_ptr(), grid.numel()
+        keep.append(grid)
+    g, E, data = job.get('g'), job.get('E', -86.0), job.get('data')
+    want_current, want_y = job.get('want_current', False), job.get('want_y', True)
+    observe = want_current or data is not None
+    y_out = cur = loss = None
+    if observe:
+        v_out = torch.empty(T, dtype=torch.float64, device=dev)
+        _cabi.check(lib.ikr_interp_protocol(ctypes.byref(io), t_d.data_ptr(), T,
+                                            v_out.data_ptr(), sptr), 'ikr_interp_protocol')
+        io.v_out = v_out.data_ptr()
+        keep.append(v_out)
+        if g is not None:
+            g_d = torch.as_tensor(g).to(device=dev, dtype=state_dtype,
+                                        non_blocking=True).reshape(-1).contiguous()
+            if g_d.numel() == 1:
+                g_d = g_d.expand(B).contiguous()
+            if g_d.numel() != B:
+                raise ValueError('odeint: g must have B entries')
+            io.g = g_d.data_ptr()
+            keep.append(g_d)
+        if isinstance(E, torch.Tensor) and E.numel() > 1:
+            e_d = E.to(device=dev, dtype=state_dtype).reshape(-1).contiguous()
+            if e_d.numel() != B:
+                raise ValueError('odeint: E must be a scalar or have B entries')
+            io.e_rev = e_d.data_ptr()
+            keep.append(e_d)
+        else:
+            io.e_scalar = float(E)
+        if want_current:
+            cur = torch.empty((T, B), dtype=state_dtype, device=dev)
+            io.i_out = cur.data_ptr()
+        if data is not None:
+            d_d = torch.as_tensor(data).to(device=dev, dtype=state_dtype).contiguous()
+            if d_d.dim() == 1:
+                d_d = d_d.reshape(T, 1)
+            if d_d.shape[0] != T or d_d.shape[1] not in (1, B):
+                raise ValueError('odeint: data must be (T,) or (T, B)')
+            io.data, io.data_B = d_d.data_ptr(), d_d.shape[1]
+            loss = torch.empty((B, 2), dtype=torch.float64, device=dev)
+            io.loss_out = loss.data_ptr()
+            keep.append(d_d)
+    if want_y:
+        y_out = torch.empty((T, B, 2), dtype=state_dtype, device=dev)
+        io.y_out = y_out.data_ptr()
+    stats = torch.empty((B, 4), dtype=torch.int32, device=dev)
+    io.stats_out = stats.data_ptr()
+    ckpt = None
+    if job.get('want_ckpt', False):
+        cap = int(opts.get('ckpt_cap', 0)) or (io.G if method == 'rk4' else 4096)
+        ck_t = torch.empty((cap, B, 2), dtype=torch.float64, device=dev)
+        ck_y = torch.empty((cap, B, 4), dtype=state_dtype, device=dev)
+        io.ckpt_cap, io.ckpt_t, io.ckpt_y = cap, ck_t.data_ptr(), ck_y.data_ptr()
+        ckpt = (ck_t, ck_y)
+    res = IkrResult(y=y_out, current=cur, sse=None if loss is None else loss[:, 0],
+                    sae=None if loss is None else loss[:, 1], stats=stats, ckpt=ckpt)
+    res._keep = keep
+    return io, res
 
-    ``g`` (B,) conductances, ``E`` scalar or (B,) reversal potential, ``data`` (T,) or (T, B)
-    measured current: returns ``IkrResult`` with ``current = g a r (V(t) - E)`` and the
-    per-trajectory ``sse`` / ``sae`` reductions against ``data`` (``train-s1.py:328-329``,
-    ``train-d0.py:509``)."""
-    method = method or 'dopri5'
-    if method not in ('dopri5', 'rk4'):
-        raise ValueError('odeint: method must be dopri5 or rk4 (got %r); the B200 path '
-                         'implements the two solvers of the hot path only' % (method,))
-    opts = _split_options(method, options)
+
+def _check_job_inputs(y0, t):
     if not isinstance(y0, torch.Tensor) or y0.dim() != 2 or y0.shape[1] != 2:
         raise TypeError('odeint: y0 must be a (B, 2) tensor of (a, r) states')
     if y0.dtype not in (torch.float32, torch.float64):
@@ -326,94 +416,83 @@ def integrate(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, g
     t_cpu = t.detach().cpu()
     if t_cpu.numel() > 1 and not bool((t_cpu[1:] > t_cpu[:-1]).all()):
         raise ValueError('odeint: t must be strictly increasing')
+    return t_cpu
 
-    dev = _resolve_device(y0, device)
+
+def integrate_many(func, jobs, *, rtol=1e-7, atol=1e-9, method=None, options=None, device=None):
+    """Integrate several (protocol, batch) jobs that share ``func``'s MLP in ONE kernel launch.
+
+    ``jobs``: list of dicts with keys ``y0`` (B,2), ``t`` (T,), optional ``protocol=(t_ms, v_mV)``
+    (default: ``func``'s current protocol), ``g``, ``E``, ``data``, ``want_y``, ``want_current``,
+    ``want_ckpt``.  This is the batched form of the reference's protocol loops
+    (``train-s1.py:316-543``, ``table-1.py:401-599``): the tiles of all jobs are scheduled through
+    one longest-first queue so every SM stays busy.  Returns one ``IkrResult`` per job."""
+    method = method or 'dopri5'
+    if method not in ('dopri5', 'rk4'):
+        raise ValueError('odeint: method must be dopri5 or rk4 (got %r); the B200 path '
+                         'implements the two solvers of the hot path only' % (method,))
+    opts = _split_options(method, options)
+    if not jobs:
+        return []
+    prepared = []
+    for job in jobs:
+        job = dict(job)
+        job.setdefault('func', func)
+        job['t_cpu'] = _check_job_inputs(job['y0'], job['t'])
+        prepared.append(job)
+    state_dtype = prepared[0]['y0'].dtype
+    t_dtype = prepared[0]['t_cpu'].dtype
+    for job in prepared:
+        if job['y0'].dtype != state_dtype or job['t_cpu'].dtype != t_dtype:
+            raise TypeError('odeint: all jobs of one launch must share the state and time dtypes')
+
+    dev = _resolve_device(prepared[0]['y0'], device)
     with torch.cuda.device(dev):
-        dm = _device_model(func, dev, opts.get('compact_table', True))
+        dm = _device_model(func, dev)
         spec = dm.spec
-        if y0.dtype == torch.float32 and spec.mlp_dtype == torch.float64:
+        if state_dtype == torch.float32 and spec.mlp_dtype == torch.float64:
             raise TypeError('odeint: float32 state with a float64 MLP is not supported')
-        B, T = y0.shape[0], t_cpu.numel()
-        desc = _make_desc(spec, y0.dtype, method, dm.tab_len, dm.uniform, rtol, atol, opts,
-                          time_f32=(t_cpu.dtype == torch.float32))
+        desc = _make_desc(spec, state_dtype, method, rtol, atol, opts,
+                          time_f32=(t_dtype == torch.float32))
         weights = dm.weights_for(desc)
         lib = _cabi.lib()
         stream = torch.cuda.current_stream(dev)
         sptr = ctypes.c_void_p(stream.cuda_stream)
-
-        y0_d = y0.detach().to(dev, non_blocking=True).contiguous()
-        t_d = t_cpu.to(torch.float64).to(dev, non_blocking=True)
-        io = _cabi.IkrIO()
-        io.B, io.T = B, T
-        io.weights = weights.data_ptr()
-        io.table_t, io.table_v = dm.tab_t.data_ptr(), dm.tab_v.data_ptr()
-        io.y0, io.t_out = y0_d.data_ptr(), t_d.data_ptr()
-        keep = [y0_d, t_d, weights]
-        if method == 'rk4':
-            grid = _rk4_grid(t_cpu, opts.get('step_size')).to(dev)
-            io.grid, io.G = grid.data_ptr(), grid.numel()
-            keep.append(grid)
-        observe = want_current or data is not None
-        y_out = cur = loss = v_out = None
-        if observe:
-            v_out = torch.empty(T, dtype=torch.float64, device=dev)
-            _cabi.check(lib.ikr_interp_protocol(ctypes.byref(desc), dm.tab_t.data_ptr(),
-                                                dm.tab_v.data_ptr(), t_d.data_ptr(), T,
-                                                v_out.data_ptr(), sptr), 'ikr_interp_protocol')
-            io.v_out = v_out.data_ptr()
-            if g is not None:
-                g_d = torch.as_tensor(g).to(device=dev, dtype=y0.dtype).reshape(-1).contiguous()
-                if g_d.numel() == 1:
-                    g_d = g_d.expand(B).contiguous()
-                if g_d.numel() != B:
-                    raise ValueError('odeint: g must have B entries')
-                io.g = g_d.data_ptr()
-                keep.append(g_d)
-            if isinstance(E, torch.Tensor) and E.numel() > 1:
-                e_d = E.to(device=dev, dtype=y0.dtype).reshape(-1).contiguous()
-                if e_d.numel() != B:
-                    raise ValueError('odeint: E must be a scalar or have B entries')
-                io.e_rev = e_d.data_ptr()
-                keep.append(e_d)
-            else:
-                io.e_scalar = float(E)
-            if want_current:
-                cur = torch.empty((T, B), dtype=y0.dtype, device=dev)
-                io.i_out = cur.data_ptr()
-            if data is not None:
-                d_d = torch.as_tensor(data).to(device=dev, dtype=y0.dtype).contiguous()
-                if d_d.dim() == 1:
-                    d_d = d_d.reshape(T, 1)
-                if d_d.shape[0] != T or d_d.shape[1] not in (1, B):
-                    raise ValueError('odeint: data must be (T,) or (T, B)')
-                io.data, io.data_B = d_d.data_ptr(), d_d.shape[1]
-                loss = torch.empty((B, 2), dtype=torch.float64, device=dev)
-                io.loss_out = loss.data_ptr()
-                keep.append(d_d)
-        if want_y:
-            y_out = torch.empty((T, B, 2), dtype=y0.dtype, device=dev)
-            io.y_out = y_out.data_ptr()
-        stats = torch.empty((B, 4), dtype=torch.int32, device=dev)
-        io.stats_out = stats.data_ptr()
-        ckpt = None
-        if want_ckpt:
-            cap = int(opts.get('ckpt_cap', 0)) or (io.G if method == 'rk4' else 4096)
-            ck_t = torch.empty((cap, B, 2), dtype=torch.float64, device=dev)
-            ck_y = torch.empty((cap, B, 4), dtype=y0.dtype, device=dev)
-            io.ckpt_cap, io.ckpt_t, io.ckpt_y = cap, ck_t.data_ptr(), ck_y.data_ptr()
-            ckpt = (ck_t, ck_y)
-        _cabi.check(lib.ikr_forward(ctypes.byref(desc), ctypes.byref(io), None, 0, sptr),
-                    'ikr_forward')
+        ios = (_cabi.IkrIO * len(prepared))()
+        results = []
+        for k, job in enumerate(prepared):
+            io, res = _prepare_job(dm, desc, method, opts, dev, lib, sptr, job, state_dtype)
+            io.weights = weights.data_ptr()
+            ios[k] = io
+            results.append(res)
+        Bs = [int(j['y0'].shape[0]) for j in prepared]
+        ws_bytes = lib.ikr_workspace_bytes(ctypes.byref(desc), len(prepared), sum(Bs), 0)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _cabi.check(lib.ikr_forward(ctypes.byref(desc), ios, len(prepared), ws.data_ptr(),
+                                    ws_bytes, sptr), 'ikr_forward')
+        geo = _cabi.launch_geometry(desc, Bs)
+        for k, res in enumerate(results):
+            res.geometry = geo
+            res._keep += [weights, ws]
+            res._desc, res._io = desc, ios[k]
         if opts.get('check_status', True):
-            _raise_on_status(stats)
-        res = IkrResult(y=y_out, current=cur,
-                        sse=None if loss is None else loss[:, 0],
-                        sae=None if loss is None else loss[:, 1],
-                        stats=stats, ckpt=ckpt,
-                        geometry=_cabi.launch_geometry(desc, B))
-        res._keep = keep
-        res._desc, res._io = desc, io
-        return res
+            for res in results:
+                _raise_on_status(res.stats)
+        return results
+
+
+def integrate(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, g=None, E=-86.0,
+              data=None, want_y=True, want_current=False, want_ckpt=False, device=None):
+    """Forward integration with the fused observation/loss epilogue.
+
+    ``g`` (B,) conductances, ``E`` scalar or (B,) reversal potential, ``data`` (T,) or (T, B)
+    measured current: returns ``IkrResult`` with ``current = g a r (V(t) - E)`` and the
+    per-trajectory ``sse`` / ``sae`` reductions against ``data`` (``train-s1.py:328-329``,
+    ``train-d0.py:509``)."""
+    job = dict(y0=y0, t=t, g=g, E=E, data=data, want_y=want_y, want_current=want_current,
+               want_ckpt=want_ckpt)
+    return integrate_many(func, [job], rtol=rtol, atol=atol, method=method, options=options,
+                          device=device)[0]
 
 
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):

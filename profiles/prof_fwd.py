@@ -21,7 +21,8 @@ name, t_tab, v_tab, t_out = protocols.protocol_set(fam)[10 if fam == 'pr4' else 
 f.set_fixed_form_voltage_protocol(t_tab, v_tab)
 rng = np.random.RandomState(0)
 y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1), dtype=dtype).cuda()
-t = torch.tensor(t_out, dtype=dtype)
+n_out = int(sys.argv[4]) if len(sys.argv) > 4 else len(t_out)
+t = torch.tensor(t_out[:n_out], dtype=dtype)
 with torch.no_grad():
     for _ in range(2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

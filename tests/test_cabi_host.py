@@ -54,20 +54,22 @@ def test_struct_sizes_match_header(lib):
 
 def _desc(func=None, state=torch.float32, method='dopri5', **opts):
     func = func or ikr.ODEFunc()
-    return solver._make_desc(ikr.describe(func), state, method, 100, (0, 0., 0.), 1e-7, 1e-9, opts)
+    return solver._make_desc(ikr.describe(func), state, method, 1e-7, 1e-9, opts)
 
 
 def test_argument_validation_without_gpu(lib):
     d = _desc()
     io = _cabi.IkrIO()
-    assert lib.ikr_forward(None, ctypes.byref(io), None, 0, None) == -1
-    assert lib.ikr_forward(ctypes.byref(d), ctypes.byref(io), None, 0, None) == -1   # B = 0
+    assert lib.ikr_forward(None, ctypes.byref(io), 1, None, 0, None) == -1
+    assert lib.ikr_forward(ctypes.byref(d), ctypes.byref(io), 1, None, 0, None) == -1   # B = 0
+    assert lib.ikr_forward(ctypes.byref(d), ctypes.byref(io), 0, None, 0, None) == -1   # no jobs
     bad = _desc()
     bad.n_layers = 0
     assert lib.ikr_packed_weight_elems(ctypes.byref(bad)) == -1
     bad = _desc()
     bad.state_dtype, bad.mlp_dtype = _cabi.F32, _cabi.F64
-    assert lib.ikr_tile_m(ctypes.byref(bad), 10) == -1
+    one = (ctypes.c_int64 * 1)(10)
+    assert lib.ikr_tile_m(ctypes.byref(bad), 1, one) == -1
 
 
 def test_packed_layout_and_param_count(lib):
@@ -82,6 +84,11 @@ def test_packed_layout_and_param_count(lib):
         geo = _cabi.launch_geometry(d, 65536)
         assert geo['smem'] <= 227 * 1024 and geo['threads'] <= 512 and geo['tile_m'] % 8 == 0
         assert geo['n_tiles'] * geo['tile_m'] >= 65536
+        multi = _cabi.launch_geometry(d, [13107] * 4 + [13108])
+        assert multi['n_tiles'] >= sum(-(-b // multi['tile_m']) for b in [13107] * 4 + [13108])
+    # the default network at the bench batch gets the 16-warp, 160-trajectory tile
+    geo = _cabi.launch_geometry(_desc(), [13107] * 4 + [13108])
+    assert (geo['tile_m'], geo['threads']) == (160, 512)
 
 
 def test_pack_weights_roundtrip(lib):

@@ -373,20 +373,41 @@ def test_interp_kernel_matches_scipy():
     t_tab, v_tab = protocols.ap2hz()
     rng = np.random.RandomState(0)
     tq = np.concatenate([rng.uniform(0, 3499.9, 5000), t_tab[::700], [3499.9, 3500.0, -1.0]])
-    func, _ = _nn('s1')
     for compact in (False, True):
-        tt, vv = protocols.compact_table(t_tab, v_tab) if compact else (t_tab, v_tab)
-        spec = ikr.describe(func)
-        d = solver._make_desc(spec, torch.float32, 'dopri5', len(tt), solver._uniform_hint(tt),
-                              1e-7, 1e-9, {})
-        dt, dv = torch.from_numpy(tt).cuda(), torch.from_numpy(vv).cuda()
+        tab = solver._DeviceTable(t_tab, v_tab, 'cuda', compact)
+        io = _cabi.IkrIO()
+        tab.fill(io)
         q = torch.from_numpy(tq).cuda()
         out = torch.empty_like(q)
-        rc = _cabi.lib().ikr_interp_protocol(ctypes.byref(d), dt.data_ptr(), dv.data_ptr(),
-                                             q.data_ptr(), q.numel(), out.data_ptr(), None)
+        rc = _cabi.lib().ikr_interp_protocol(ctypes.byref(io), q.data_ptr(), q.numel(),
+                                             out.data_ptr(), None)
         assert rc == 0
         torch.cuda.synchronize()
         want = np.full(len(tq), -80.0)
         inside = (tq >= t_tab[0]) & (tq <= t_tab[-1])
         want[inside] = interp1d(t_tab, v_tab)(tq[inside])
         assert np.array_equal(out.cpu().numpy(), want)      # bit-exact, compacted or not
+
+
+def test_integrate_many_equals_separate_calls():
+    """One launch over several (protocol, batch) jobs == the reference's protocol loop of separate
+    odeint calls (train-s1.py:316-543)."""
+    func, _ = _nn('d1')
+    rng = np.random.RandomState(11)
+    jobs, singles = [], []
+    for fam, nb in (('pr3', 37), ('pr4', 200), ('aps', 5)):
+        name, t_tab, v_tab, t_out = protocols.protocol_set(fam)[1 if fam != 'aps' else 0]
+        t = torch.tensor(t_out[:121], dtype=torch.float32)
+        y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, nb), rng.uniform(0.95, 1, nb)], 1),
+                          dtype=torch.float32).cuda()
+        g = torch.tensor(rng.lognormal(0, 0.2, nb), dtype=torch.float32).cuda()
+        data = torch.tensor(rng.normal(0, 0.1, 121), dtype=torch.float32).cuda()
+        jobs.append(dict(protocol=(t_tab, v_tab), y0=y0, t=t, g=g, data=data, want_current=True))
+        func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        singles.append(ikr.integrate(func, y0, t, g=g, data=data, want_current=True,
+                                     options={'tile_m': 32}))
+    many = ikr.integrate_many(func, jobs)
+    assert len(many) == 3
+    for a, b in zip(many, singles):
+        assert torch.equal(a.y, b.y) and torch.equal(a.current, b.current)
+        assert torch.equal(a.stats, b.stats) and torch.equal(a.sae, b.sae)
