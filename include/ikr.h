@@ -103,17 +103,22 @@ typedef struct ikr_io {
   /* step checkpoints for ikr_backward (all nullable when no backward is wanted) */
   int64_t ckpt_cap;       /* capacity in accepted steps per trajectory                           */
   double* ckpt_t;         /* [ckpt_cap, B, 2] (t0, dt)                                           */
-  void* ckpt_y;           /* [ckpt_cap, B, 4] state dtype (a0, r0, f0_a, f0_r)                   */
+  void* ckpt_y;           /* [ckpt_cap, B, 16] state dtype (a0, r0, k_a[0..6], k_r[0..6])        */
 } ikr_io;
 
-/* Inputs/outputs of the backward sweep (discrete adjoint of the accepted-step sequence).        */
+/* Inputs/outputs of the backward sweep (discrete adjoint of the accepted-step sequence: step
+ * sizes, stage times and dense-output abscissae are constants, exactly what PyTorch autograd sees
+ * through torchdiffeq's non-adjoint odeint).  The forward job passed alongside must have been run
+ * with step checkpoints (ckpt_t / ckpt_y) and, for a fused loss, with y_out, v_out and data.     */
 typedef struct ikr_bwd_io {
-  const void* grad_y;     /* [T,B,2] state dtype dL/dy_out (nullable if fused loss is used)      */
+  const void* grad_y;     /* [T,B,2] state dtype dL/dy_out (used when fused_loss == 0)           */
   int32_t fused_loss;     /* 0: use grad_y; 1: L = sum (I - data)^2 ; 2: L = sum |I - data|      */
-  const void* weights_bwd;/* packed parameters in backward layout (same buffer as `weights`)     */
-  void* grad_weights;     /* [n_params] fp32/fp64 (mlp dtype... accumulated in >= state dtype)   */
-  void* grad_y0;          /* [B,2] (nullable)                                                    */
-  void* grad_g;           /* [B]   (nullable)                                                    */
+  int32_t reserved;
+  int64_t max_accepted_steps; /* max over trajectories of stats[:,0]; <= 0: assume ckpt_cap      */
+  double* grad_weights;   /* [ikr_param_count] fp64, state_dict order (net.0.weight, net.0.bias,
+                             net.2.weight, ...): OVERWRITTEN with dL/dtheta summed over B         */
+  void* grad_y0;          /* [B,2] state dtype (nullable)                                        */
+  void* grad_g;           /* [B]   state dtype dL/dg (nullable; fused loss only)                 */
 } ikr_bwd_io;
 
 int ikr_abi_version(void);
@@ -144,7 +149,10 @@ size_t ikr_workspace_bytes(const ikr_desc* d, int32_t n_jobs, int64_t B_total,
 int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* workspace,
                 size_t workspace_bytes, void* cuda_stream);
 
-/* Backward sweep: gradients of a scalar loss w.r.t. the MLP parameters (and optionally y0, g). */
+/* Backward sweep: gradients of a scalar loss w.r.t. the MLP parameters (and optionally y0, g)
+ * for ONE forward job (dopri5).  Runs in rounds sized by the workspace: ikr_workspace_bytes(...,
+ * with_backward=1) returns a size that holds the fixed buffers plus a stash for a few reversed
+ * steps per round; any larger workspace is used for longer rounds.                              */
 int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, void* workspace,
                  size_t workspace_bytes, void* cuda_stream);
 

@@ -4,6 +4,7 @@ Public surface (mirrors what the reference scripts use on this path):
 
 * ``odeint(func, y0, t, *, rtol, atol, method, options)`` -- torchdiffeq-compatible entry point
 * ``integrate(...)``                                   -- same, plus fused current / loss epilogue
+* ``loss_and_grad(...)``                               -- fused loss + gradient through the solver
 * ``ODEFunc`` / ``ODEFuncNNf`` / ``ODEFuncNNd``         -- the reference's ODE-func modules
 * ``ARCHITECTURES`` / ``build_net``                    -- architectures/s00..s11
 * ``protocols``                                        -- voltage-clamp protocol tables
@@ -12,6 +13,7 @@ from . import protocols  # noqa: F401
 from .models import (ARCHITECTURES, PARAMETER_SETS, ODEFunc, ODEFuncNNd, ODEFuncNNf,  # noqa: F401
                      build_net, load_weights)
 from .solver import IkrResult, describe, integrate, integrate_many, odeint  # noqa: F401
+from .adjoint import loss_and_grad  # noqa: F401
 
-__all__ = ['odeint', 'integrate', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
+__all__ = ['odeint', 'integrate', 'loss_and_grad', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
            'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols']

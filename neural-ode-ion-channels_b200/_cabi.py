@@ -50,8 +50,8 @@ class IkrIO(ctypes.Structure):
 
 class IkrBwdIO(ctypes.Structure):
     _fields_ = [
-        ('grad_y', c_vp), ('fused_loss', c_i32), ('weights_bwd', c_vp),
-        ('grad_weights', c_vp), ('grad_y0', c_vp), ('grad_g', c_vp),
+        ('grad_y', c_vp), ('fused_loss', c_i32), ('reserved', c_i32),
+        ('max_accepted_steps', c_i64), ('grad_weights', c_vp), ('grad_y0', c_vp), ('grad_g', c_vp),
     ]
 
 

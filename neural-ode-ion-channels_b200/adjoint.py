@@ -1,16 +1,61 @@
 """Gradient through ``odeint``: discrete adjoint of the accepted-step sequence (the semantics of
-torchdiffeq's non-adjoint autograd -- step sizes are constants of the backward pass).
+torchdiffeq's non-adjoint autograd -- step sizes, stage times and dense-output abscissae are
+constants of the backward pass; rejected steps contribute nothing).
 
 The reference never differentiates through ``odeint`` (SURVEY.md finding 3); this is the new
 capability the north star asks for, offered behind the same ``odeint`` call: when any MLP
 parameter requires grad (and grad mode is on) the forward records per-step checkpoints and
-``loss.backward()`` runs the fused backward kernel (``ikr_backward``)."""
+``loss.backward()`` runs the backward kernels (``ikr_backward``: adjoint sweep + weight-gradient
+GEMM).  ``loss_and_grad`` is the fused training entry point: the loss against a data trace and its
+gradient without materialising ``dL/dy`` on the host side.
+
+One deliberate difference from torchdiffeq: the *initial* step size chosen by the Hairer heuristic
+is treated as a constant as well (torchdiffeq lets it carry a graph until the first controller
+update).  With ``options={'first_step': h}`` the two agree exactly.
+"""
 import ctypes
 
 import torch
 
 from . import _cabi
-from .solver import _resolve_device, integrate, unpack_grads
+from .solver import _device_model, _resolve_device, describe, integrate, unpack_grads
+
+_LOSSES = {'sse': 1, 'sae': 2}
+
+
+def _run_backward(func, res, *, grad_y=None, fused_loss=0, want_y0=True, want_g=False,
+                  workspace_bytes=None):
+    """Call ``ikr_backward`` for the forward result ``res`` (needs ``want_ckpt=True``).
+    Returns (flat fp64 parameter gradient, grad_y0 or None, grad_g or None)."""
+    desc, io = res._desc, res._io
+    dev = res.stats.device
+    B = res.stats.shape[0]
+    state_dtype = torch.float32 if desc.state_dtype == _cabi.F32 else torch.float64
+    with torch.cuda.device(dev):
+        lib = _cabi.lib()
+        n_par = lib.ikr_param_count(ctypes.byref(desc))
+        grad_flat = torch.empty(n_par, dtype=torch.float64, device=dev)
+        grad_y0 = torch.zeros((B, 2), dtype=state_dtype, device=dev) if want_y0 else None
+        grad_g = torch.zeros(B, dtype=state_dtype, device=dev) if want_g else None
+        bio = _cabi.IkrBwdIO()
+        keep = []
+        if fused_loss == 0:
+            gy = grad_y.to(device=dev, dtype=state_dtype).contiguous()
+            bio.grad_y = gy.data_ptr()
+            keep.append(gy)
+        bio.fused_loss = fused_loss
+        bio.max_accepted_steps = int(res.stats[:, 0].max().item())
+        bio.grad_weights = grad_flat.data_ptr()
+        bio.grad_y0 = grad_y0.data_ptr() if want_y0 else None
+        bio.grad_g = grad_g.data_ptr() if want_g else None
+        ws_bytes = workspace_bytes or lib.ikr_workspace_bytes(ctypes.byref(desc), 1, B, 1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        _cabi.check(lib.ikr_backward(ctypes.byref(desc), ctypes.byref(io), ctypes.byref(bio),
+                                     ws.data_ptr(), ws_bytes,
+                                     ctypes.c_void_p(stream.cuda_stream)), 'ikr_backward')
+        ws.record_stream(stream)
+    return grad_flat, grad_y0, grad_g
 
 
 class _OdeintFn(torch.autograd.Function):
@@ -19,48 +64,54 @@ class _OdeintFn(torch.autograd.Function):
         res = integrate(func, y0, t, want_ckpt=True, **kwargs)
         ctx.res = res
         ctx.func = func
-        ctx.n_params = len(params)
         ctx.y0_requires_grad = y0.requires_grad
         return res.y
 
     @staticmethod
     def backward(ctx, grad_y):
-        from .solver import _device_model
         res = ctx.res
-        desc, io = res._desc, res._io
-        dev = res.y.device
-        with torch.cuda.device(dev):
-            dm = _device_model(ctx.func, dev)
-            spec = dm.spec
-            lib = _cabi.lib()
-            n_par = lib.ikr_param_count(ctypes.byref(desc))
-            acc_dtype = torch.float64 if res.y.dtype == torch.float64 else torch.float32
-            grad_flat = torch.zeros(n_par, dtype=acc_dtype, device=dev)
-            gy = grad_y.contiguous().to(res.y.dtype)
-            B = res.y.shape[1]
-            grad_y0 = torch.zeros((B, 2), dtype=res.y.dtype, device=dev)
-            bio = _cabi.IkrBwdIO()
-            bio.grad_y = gy.data_ptr()
-            bio.fused_loss = 0
-            bio.weights_bwd = io.weights
-            bio.grad_weights = grad_flat.data_ptr()
-            bio.grad_y0 = grad_y0.data_ptr()
-            ws_bytes = lib.ikr_workspace_bytes(ctypes.byref(desc), 1, B, 1)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            stream = torch.cuda.current_stream(dev)
-            _cabi.check(lib.ikr_backward(ctypes.byref(desc), ctypes.byref(io), ctypes.byref(bio),
-                                         ws.data_ptr(), ws_bytes,
-                                         ctypes.c_void_p(stream.cuda_stream)), 'ikr_backward')
-            grads = [g.to(p.dtype) for g, p in
-                     zip(unpack_grads(spec, grad_flat),
-                         [q for m in spec.linears for q in (m.weight, m.bias)])]
+        spec = describe(ctx.func)
+        flat, grad_y0, _ = _run_backward(ctx.func, res, grad_y=grad_y, fused_loss=0,
+                                         want_y0=ctx.y0_requires_grad)
+        plist = [q for m in spec.linears for q in (m.weight, m.bias)]
+        grads = [g.to(device=q.device, dtype=q.dtype) for g, q in zip(unpack_grads(spec, flat), plist)]
         return (None, grad_y0 if ctx.y0_requires_grad else None, None, None) + tuple(grads)
 
 
 def odeint_with_grad(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None):
+    if (method or 'dopri5') != 'dopri5':
+        raise NotImplementedError('odeint: gradients are implemented for method="dopri5"')
     dev = _resolve_device(y0, None)
     kwargs = dict(rtol=rtol, atol=atol, method=method, options=options, device=dev)
-    from .solver import describe
     spec = describe(func)
     params = [q for m in spec.linears for q in (m.weight, m.bias)]
     return _OdeintFn.apply(func, y0.to(dev), t, kwargs, *params)
+
+
+def loss_and_grad(func, y0, t, data, *, g=None, E=-86.0, loss='sse', rtol=1e-7, atol=1e-9,
+                  options=None, want_y0=False, want_g=False, accumulate=False, device=None,
+                  workspace_bytes=None):
+    """Fused training step of the hot path: integrate B trajectories with dopri5, form
+    ``I = g a r (V - E)``, reduce ``loss`` ('sse': sum (I - data)^2, the
+    ``pints.SumOfSquaresError`` form of ``train-d0.py:509``; 'sae': sum |I - data|, T times the
+    reporting MAE of ``train-s1.py:329``) over all trajectories and samples, and back-propagate
+    through the solver.
+
+    Returns ``(loss_total, per_trajectory_loss (B,), grads, result)`` where ``grads`` is a list
+    shaped like ``func.net.parameters()`` (fp64, on the GPU).  With ``accumulate=True`` the
+    gradients are also added into ``p.grad`` of the module's parameters."""
+    if loss not in _LOSSES:
+        raise ValueError("loss must be 'sse' or 'sae'")
+    res = integrate(func, y0, t, rtol=rtol, atol=atol, method='dopri5', options=options, g=g, E=E,
+                    data=data, want_y=True, want_current=False, want_ckpt=True, device=device)
+    per_traj = res.sse if loss == 'sse' else res.sae
+    flat, grad_y0, grad_g = _run_backward(func, res, fused_loss=_LOSSES[loss], want_y0=want_y0,
+                                          want_g=want_g, workspace_bytes=workspace_bytes)
+    spec = describe(func)
+    grads = unpack_grads(spec, flat)
+    if accumulate:
+        for gr, m in zip(grads, [q for m in spec.linears for q in (m.weight, m.bias)]):
+            gr = gr.to(device=m.device, dtype=m.dtype)
+            m.grad = gr if m.grad is None else m.grad + gr
+    res.grad_y0, res.grad_g = grad_y0, grad_g
+    return per_traj.sum(), per_traj, grads, res

@@ -9,7 +9,6 @@
 
 #include "../../include/ikr.h"
 #include "ikr_backward.cuh"
-#include "ikr_forward.cuh"
 
 using namespace ikr;
 
@@ -133,6 +132,7 @@ MlpView make_view(const ikr_desc* d, const void* weights) {
   v.n = d->n_nodes;
   v.off_w0 = off[0]; v.off_wt = off[1]; v.off_bh = off[2]; v.off_wl = off[3]; v.off_wn = off[4];
   v.slope = d->negative_slope;
+  v.bwd_seq = 0;
   return v;
 }
 
@@ -166,6 +166,247 @@ int launch_forward(const FwdParams& p, const Geometry& g, cudaStream_t st) {
     return IKR_ERR_LAUNCH;
   }
   kern<<<g.grid, g.threads, g.smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// backward: geometry, workspace plan, round loop
+// ---------------------------------------------------------------------------------------------
+template <typename S, typename W>
+size_t adj_smem(int M, int npad, int kc, int L) { return AdjSmemLayout<S, W>(M, npad, kc, L).total; }
+
+size_t adj_smem_dyn(const ikr_desc* d, int M, int npad, int kc) {
+  if (d->state_dtype == IKR_F32) return adj_smem<float, float>(M, npad, kc, d->n_layers);
+  if (d->mlp_dtype == IKR_F32) return adj_smem<double, float>(M, npad, kc, d->n_layers);
+  return adj_smem<double, double>(M, npad, kc, d->n_layers);
+}
+
+Geometry make_geometry_bwd(const ikr_desc* d, long long B) {
+  Geometry g;
+  long long off[5], total;
+  mlp_layout(d, &g.npad, &g.kc, &g.cpl, off, &total);
+  g.TN = d->mlp_dtype == IKR_F32 ? 8 : 4;
+  g.NG = g.npad / g.TN;
+  g.sms = device_sms();
+  double best_score = -1.0;
+  int best_mg = 1;
+  const int forced = d->tile_m > 0 ? round_up(d->tile_m, 8) / 8 : 0;
+  for (int mg : kMgCandidates) {
+    const int M = 8 * mg;
+    const int workers = tile_worker_threads(mg, g.NG);
+    const int threads = round_up(workers > M ? workers : M, 32);
+    if (threads > kMaxThreads) continue;
+    if (adj_smem_dyn(d, M, g.npad, g.kc) > kSmemLimit) continue;
+    if (forced) {
+      if (mg <= forced) best_mg = mg;
+      continue;
+    }
+    const long long tiles = (B + M - 1) / M;
+    const double waves = (double)tiles / g.sms;
+    const double wave_eff = waves / (double)((tiles + g.sms - 1) / g.sms);
+    const double fill = (double)B / ((double)tiles * M);
+    const int warps = (workers + 31) / 32;
+    const double balance = (workers / 32.0) / (4.0 * ((warps + 3) / 4));
+    const double amort = (double)M / (M + 6.0);
+    const double score = wave_eff * fill * balance * amort;
+    if (score > best_score) { best_score = score; best_mg = mg; }
+  }
+  g.MG = best_mg;
+  g.M = 8 * best_mg;
+  const int workers = tile_worker_threads(g.MG, g.NG);
+  g.n_worker_warps = (workers + 31) / 32;
+  g.threads = round_up(workers > g.M ? workers : g.M, 32);
+  g.n_tiles = (B + g.M - 1) / g.M;
+  g.grid = (int)(g.n_tiles < g.sms ? g.n_tiles : g.sms);
+  if (g.grid < 1) g.grid = 1;
+  g.smem = adj_smem_dyn(d, g.M, g.npad, g.kc);
+  return g;
+}
+
+int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
+
+struct BwdPlan {
+  Geometry g;
+  // weight-gradient GEMM
+  int KC, n_ot, n_it, BO, BI, S, IG, OG, wg_threads, wg_stages, wg_grid;
+  size_t wg_smem;
+  // workspace carve-up (byte offsets)
+  size_t off_counters, off_lanes, off_small, off_pw, off_pb, off_stash_h, off_stash_d, fixed_bytes;
+  size_t slot_bytes;   // one stash slot, ONE of the two stashes
+  int small_stride;
+  size_t zero_begin, zero_bytes;  // accumulators that must start at zero
+};
+
+BwdPlan make_bwd_plan(const ikr_desc* d, long long B) {
+  BwdPlan pl;
+  pl.g = make_geometry_bwd(d, B);
+  const Geometry& g = pl.g;
+  const int wsz = d->mlp_dtype == IKR_F32 ? 4 : 8;
+  const int ssz = d->state_dtype == IKR_F32 ? 4 : 8;
+  const int L = d->n_layers;
+  const int RI = wsz == 4 ? 8 : 4;
+  // K-chunk of the GEMM: a divisor of M (chunks never straddle stash slots)
+  pl.KC = 8 * gcd_int(g.MG, 4);
+  while (pl.KC > 8 && 2ULL * pl.KC * g.npad * wsz * 2 > 200 * 1024) pl.KC /= 2;
+  pl.n_ot = (g.npad + 199) / 200;
+  pl.BO = round_up((g.npad + pl.n_ot - 1) / pl.n_ot, 8);
+  pl.OG = pl.BO / 8;
+  const int ig_max = kWgMaxThreads / pl.OG;
+  pl.n_it = (g.npad + ig_max * RI - 1) / (ig_max * RI);
+  pl.BI = round_up((g.npad + pl.n_it - 1) / pl.n_it, 8);
+  pl.IG = (pl.BI + RI - 1) / RI;
+  pl.wg_threads = round_up(pl.OG * pl.IG, 32);
+  if (pl.wg_threads > kWgMaxThreads) pl.wg_threads = kWgMaxThreads;
+  pl.S = g.sms / (L * pl.n_ot * pl.n_it);
+  if (pl.S < 1) pl.S = 1;
+  pl.wg_grid = L * pl.n_ot * pl.n_it * pl.S;
+  const size_t stage = 2ULL * pl.KC * g.npad * wsz;
+  pl.wg_stages = (int)((200 * 1024) / stage);
+  if (pl.wg_stages > 6) pl.wg_stages = 6;
+  if (pl.wg_stages < 2) pl.wg_stages = 2;
+  pl.wg_smem = 128 + (size_t)pl.wg_stages * stage;
+
+  pl.small_stride = 4 * g.npad + 8;
+  const size_t lane_save = ssz == 4 ? sizeof(BLaneSave<float>) : sizeof(BLaneSave<double>);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
+  pl.off_counters = take(256);
+  pl.off_lanes = take((size_t)g.n_tiles * g.M * lane_save);
+  pl.off_small = take((size_t)g.sms * pl.small_stride * sizeof(double));
+  pl.off_pw = take((size_t)L * pl.S * g.npad * g.npad * sizeof(double));
+  pl.off_pb = take((size_t)L * pl.S * g.npad * sizeof(double));
+  pl.zero_begin = pl.off_small;
+  pl.zero_bytes = o - pl.off_small;
+  pl.fixed_bytes = o;
+  pl.slot_bytes = (size_t)L * g.M * g.npad * wsz;
+  return pl;
+}
+
+// steps per round a workspace of `bytes` can hold (0: too small)
+int bwd_steps_per_round(const BwdPlan& pl, size_t bytes) {
+  if (bytes <= pl.fixed_bytes + 512) return 0;
+  const size_t avail = (bytes - pl.fixed_bytes - 512) / 2;       // per stash
+  const long long slots = (long long)(avail / pl.slot_bytes);
+  const long long per_tile = slots / pl.g.n_tiles;               // 6 R + 1 slots per tile
+  if (per_tile < 7) return 0;
+  long long R = (per_tile - 1) / 6;
+  return (int)(R > 4096 ? 4096 : R);
+}
+
+size_t bwd_workspace_bytes(const ikr_desc* d, long long B) {
+  const BwdPlan pl = make_bwd_plan(d, B);
+  // default: a stash of about 4 GiB (both halves), at least one step per round
+  const double target = 4.0 * 1024 * 1024 * 1024;
+  long long R = (long long)((target / 2 / (double)pl.slot_bytes / (double)pl.g.n_tiles - 1) / 6);
+  if (R < 1) R = 1;
+  if (R > 64) R = 64;
+  return pl.fixed_bytes + 512 + 2 * (size_t)pl.g.n_tiles * (6 * R + 1) * pl.slot_bytes;
+}
+
+template <typename S, typename W>
+int launch_adjoint(const BwdParams& p, const Geometry& g, cudaStream_t st) {
+  auto kern = ikr_adjoint_kernel<S, W>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return IKR_ERR_LAUNCH;
+  }
+  kern<<<g.grid, g.threads, g.smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
+template <typename W>
+int launch_wgrad(const WgradParams& p, const BwdPlan& pl, cudaStream_t st) {
+  auto kern = ikr_wgrad_kernel<W>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.wg_smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return IKR_ERR_LAUNCH;
+  }
+  kern<<<pl.wg_grid, pl.wg_threads, pl.wg_smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
+int bwd_dispatch(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, void* workspace,
+                 size_t workspace_bytes, cudaStream_t st) {
+  if (d->method != IKR_DOPRI5) return IKR_ERR_UNSUPPORTED;
+  if (io->B < 1 || io->T < 1 || !io->weights || !io->table_t || !io->table_v || !io->y0 ||
+      !io->t_out || !io->stats_out || !io->ckpt_t || !io->ckpt_y || io->ckpt_cap < 1 ||
+      !bio->grad_weights)
+    return IKR_ERR_ARG;
+  if (bio->fused_loss == 0 && !bio->grad_y) return IKR_ERR_ARG;
+  if (bio->fused_loss != 0 && (!io->y_out || !io->v_out || !io->data)) return IKR_ERR_ARG;
+  if (bio->fused_loss < 0 || bio->fused_loss > 2) return IKR_ERR_ARG;
+  if (!workspace) return IKR_ERR_WORKSPACE;
+  const BwdPlan pl = make_bwd_plan(d, io->B);
+  const Geometry& g = pl.g;
+  if (g.smem > kSmemLimit || g.threads > kMaxThreads || pl.wg_smem > kSmemLimit)
+    return IKR_ERR_UNSUPPORTED;
+  const int R = bwd_steps_per_round(pl, workspace_bytes);
+  if (R < 1) return IKR_ERR_WORKSPACE;
+  unsigned char* ws = (unsigned char*)workspace;
+  const size_t stash_each = (size_t)g.n_tiles * (6 * (size_t)R + 1) * pl.slot_bytes;
+  const size_t off_sh = (pl.fixed_bytes + 255) & ~(size_t)255;
+  const size_t off_sd = (off_sh + stash_each + 255) & ~(size_t)255;
+  if (off_sd + stash_each > workspace_bytes) return IKR_ERR_WORKSPACE;
+
+  if (cudaMemsetAsync(ws + pl.zero_begin, 0, pl.zero_bytes, st) != cudaSuccess)
+    return IKR_ERR_DEVICE;
+
+  BwdParams p;
+  p.mlp = make_view(d, io->weights);
+  p.mlp.bwd_seq = 1;
+  p.cfg = make_cfg(d);
+  p.cfg.tab = make_table(io);
+  p.M = g.M; p.MG = g.MG; p.NG = g.NG; p.n_worker_warps = g.n_worker_warps;
+  p.B = io->B; p.T = (int)io->T; p.n_tiles = g.n_tiles;
+  p.y0 = io->y0; p.t_out = io->t_out; p.stats = io->stats_out;
+  p.ckpt_t = io->ckpt_t; p.ckpt_y = io->ckpt_y;
+  p.grad_y = bio->grad_y; p.fused_loss = bio->fused_loss;
+  p.y_out = io->y_out; p.v_out = io->v_out; p.g = io->g; p.e_rev = io->e_rev;
+  p.e_scalar = io->e_scalar; p.data = io->data; p.data_B = io->data_B;
+  p.lane_state = ws + pl.off_lanes;
+  p.steps_per_round = R;
+  p.stash_h = ws + off_sh; p.stash_d = ws + off_sd;
+  p.counters = reinterpret_cast<unsigned long long*>(ws + pl.off_counters);
+  p.small_grad = reinterpret_cast<double*>(ws + pl.off_small);
+  p.small_stride = pl.small_stride;
+  p.grad_y0 = bio->grad_y0; p.grad_g = bio->grad_g;
+
+  WgradParams wp;
+  wp.L = d->n_layers; wp.n = d->n_nodes; wp.npad = g.npad; wp.M = g.M; wp.KC = pl.KC;
+  wp.n_ot = pl.n_ot; wp.n_it = pl.n_it; wp.BO = pl.BO; wp.BI = pl.BI; wp.S = pl.S; wp.IG = pl.IG;
+  wp.stages = pl.wg_stages;
+  wp.stash_h = p.stash_h; wp.stash_d = p.stash_d; wp.counters = p.counters;
+  wp.partial_w = reinterpret_cast<double*>(ws + pl.off_pw);
+  wp.partial_b = reinterpret_cast<double*>(ws + pl.off_pb);
+
+  long long max_steps = bio->max_accepted_steps > 0 ? bio->max_accepted_steps : io->ckpt_cap;
+  if (max_steps > io->ckpt_cap) max_steps = io->ckpt_cap;
+  const long long rounds = max_steps > 0 ? (max_steps + R - 1) / R : 1;
+  for (long long r = 0; r < rounds; ++r) {
+    if (cudaMemsetAsync(ws + pl.off_counters, 0, 256, st) != cudaSuccess) return IKR_ERR_DEVICE;
+    p.first_round = r == 0 ? 1 : 0;
+    int rc;
+    if (d->state_dtype == IKR_F32) rc = launch_adjoint<float, float>(p, g, st);
+    else if (d->mlp_dtype == IKR_F32) rc = launch_adjoint<double, float>(p, g, st);
+    else rc = launch_adjoint<double, double>(p, g, st);
+    if (rc != 0) return rc;
+    rc = d->mlp_dtype == IKR_F32 ? launch_wgrad<float>(wp, pl, st) : launch_wgrad<double>(wp, pl, st);
+    if (rc != 0) return rc;
+  }
+
+  ReduceParams rp;
+  rp.L = d->n_layers; rp.n = d->n_nodes; rp.npad = g.npad; rp.S = pl.S; rp.n_cta = g.sms;
+  rp.small_stride = pl.small_stride;
+  rp.partial_w = wp.partial_w; rp.partial_b = wp.partial_b; rp.small_grad = p.small_grad;
+  rp.out = bio->grad_weights;
+  const long long n = d->n_nodes, Ln = d->n_layers;
+  rp.n_params = 3 * n + Ln * (n * n + n) + n + 1;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((rp.n_params + threads - 1) / threads);
+  ikr_grad_reduce_kernel<<<blocks, threads, 0, st>>>(rp);
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
 }
 

@@ -75,6 +75,8 @@ struct MlpView {
   long long off_wl;  // [npad] + b_last
   long long off_wn;  // [L][n][npad] backward operand (rows = out features)
   double slope;
+  int bwd_seq;       // 0: chunk sequence = forward layers only; 1: forward layers then backward
+                     //    layers (adjoint kernel: Wt of layers 0..L-1, then Wn of layers L-1..0)
 };
 
 template <typename W>
@@ -112,11 +114,24 @@ __device__ __forceinline__ void mlp_issue_chunk(const MlpView& mv, const MlpSmem
                                                 unsigned q) {
   const unsigned stage = q % kStages;
   const unsigned c = q % (unsigned)mv.cpl;
-  const unsigned layer = (q / (unsigned)mv.cpl) % (unsigned)mv.L;
+  unsigned lq = q / (unsigned)mv.cpl;
+  long long off = mv.off_wt;
+  unsigned layer;
+  if (mv.bwd_seq) {
+    lq %= 2u * (unsigned)mv.L;
+    if (lq < (unsigned)mv.L) {
+      layer = lq;
+    } else {
+      layer = 2u * (unsigned)mv.L - 1u - lq;
+      off = mv.off_wn;
+    }
+  } else {
+    layer = lq % (unsigned)mv.L;
+  }
   const int k0 = (int)c * mv.kc;
   const int rows = min(mv.kc, mv.n - k0);
   const unsigned bytes = (unsigned)(rows * mv.npad * (int)sizeof(W));
-  const W* src = (const W*)mv.base + mv.off_wt + ((long long)layer * mv.n + k0) * mv.npad;
+  const W* src = (const W*)mv.base + off + ((long long)layer * mv.n + k0) * mv.npad;
   mbar_expect_tx(&sm.full[stage], bytes);
   bulk_g2s(sm.Wr + (size_t)stage * mv.kc * mv.npad, src, bytes, &sm.full[stage]);
 }
@@ -210,6 +225,70 @@ __device__ __forceinline__ int tile_row(int i, int gm, int MG) {
   return (i / V) * (MG * V) + gm * V + (i % V);
 }
 
+// K-loop of one n x n layer over the weight-chunk ring: acc[i][j] += sum_k Hs[k][row_i] * Wr[k][col_j]
+// for the thread's 8 x TN register tile.  No CTA barrier inside (full/empty mbarriers only).
+template <typename W>
+__device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem<W>& sm,
+                                                MlpPipe& pp, int M, int MG, const TileCoord& tc,
+                                                bool warp_works,
+                                                W (&acc)[kTM][MlpTileCfg<W>::TN]) {
+  constexpr int TN = MlpTileCfg<W>::TN;
+  constexpr int V = MlpTileCfg<W>::V;
+  const int tid = threadIdx.x;
+  const int gm = tc.gm, gn = tc.gn;
+  const bool worker = tc.worker;
+  for (int c = 0; c < mv.cpl; ++c) {
+    const unsigned q = pp.q;
+    const unsigned stage = q % kStages;
+    const int k0 = c * mv.kc;
+    const int rows = min(mv.kc, mv.n - k0);
+    if (warp_works) {
+      mbar_wait(&sm.full[stage], (q / kStages) & 1);
+      if (worker) {
+        const W* Hk = sm.Hs + (size_t)k0 * M + gm * V;
+        const W* Wk = sm.Wr + (size_t)stage * mv.kc * mv.npad + gn * TN;
+#pragma unroll 2
+        for (int kk = 0; kk < rows; ++kk) {
+          W a[kTM], b[TN];
+          if (sizeof(W) == 4) {
+            float4 a0 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M);
+            float4 a1 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M + MG * V);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            float4 b0 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad);
+            float4 b1 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad + 4);
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+            b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              double2 av = *reinterpret_cast<const double2*>(Hk + (size_t)kk * M + g * MG * V);
+              a[2 * g] = av.x; a[2 * g + 1] = av.y;
+            }
+            double2 b0 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad);
+            double2 b1 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad + 2);
+            b[0] = b0.x; b[1] = b0.y; b[TN - 2] = b1.x; b[TN - 1] = b1.y;
+          }
+#pragma unroll
+          for (int i = 0; i < kTM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = ikr_fma(a[i], b[j], acc[i][j]);
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&sm.empty[stage]);
+      if (tid == 0 && q >= 1) {
+        // refill the slot of the previous chunk once every worker warp has released it
+        const unsigned qp = q - 1;
+        mbar_wait(&sm.empty[qp % kStages], (qp / kStages) & 1);
+        mlp_issue_chunk<W>(mv, sm, qp + kStages);
+        pp.issued = qp + kStages + 1;
+      }
+    }
+    pp.q = q + 1;
+  }
+}
+
 // Hidden layers of the tile MLP: activations in sm.Hs (feature-major) are replaced layer by
 // layer; weights arrive through the full/empty mbarrier ring (no CTA-wide barrier per chunk:
 // warps drift up to kStages-1 chunks apart; thread 0 refills a ring slot one chunk late so that
@@ -234,56 +313,7 @@ __device__ __forceinline__ void mlp_tile_hidden(const MlpView& mv, const MlpSmem
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = (W)0;
 
-    for (int c = 0; c < mv.cpl; ++c) {
-      const unsigned q = pp.q;
-      const unsigned stage = q % kStages;
-      const int k0 = c * mv.kc;
-      const int rows = min(mv.kc, mv.n - k0);
-      if (warp_works) {
-        mbar_wait(&sm.full[stage], (q / kStages) & 1);
-        if (worker) {
-          const W* Hk = sm.Hs + (size_t)k0 * M + gm * V;
-          const W* Wk = sm.Wr + (size_t)stage * mv.kc * mv.npad + gn * TN;
-#pragma unroll 2
-          for (int kk = 0; kk < rows; ++kk) {
-            W a[kTM], b[TN];
-            if (sizeof(W) == 4) {
-              float4 a0 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M);
-              float4 a1 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M + MG * V);
-              a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-              a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-              float4 b0 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad);
-              float4 b1 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad + 4);
-              b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
-              b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
-            } else {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                double2 av = *reinterpret_cast<const double2*>(Hk + (size_t)kk * M + g * MG * V);
-                a[2 * g] = av.x; a[2 * g + 1] = av.y;
-              }
-              double2 b0 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad);
-              double2 b1 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad + 2);
-              b[0] = b0.x; b[1] = b0.y; b[TN - 2] = b1.x; b[TN - 1] = b1.y;
-            }
-#pragma unroll
-            for (int i = 0; i < kTM; ++i)
-#pragma unroll
-              for (int j = 0; j < TN; ++j) acc[i][j] = ikr_fma(a[i], b[j], acc[i][j]);
-          }
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&sm.empty[stage]);
-        if (tid == 0 && q >= 1) {
-          // refill the slot of the previous chunk once every worker warp has released it
-          const unsigned qp = q - 1;
-          mbar_wait(&sm.empty[qp % kStages], (qp / kStages) & 1);
-          mlp_issue_chunk<W>(mv, sm, qp + kStages);
-          pp.issued = qp + kStages + 1;
-        }
-      }
-      pp.q = q + 1;
-    }
+    mlp_layer_kloop<W>(mv, sm, pp, M, MG, tc, warp_works, acc);
     __syncthreads();  // all reads of this layer's input activations are done
 
     if (worker) {

@@ -152,13 +152,23 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
         }
       }
     };
-    auto ckpt = [&](int step, double t0, double dt, S ya, S yr, S fa, S fr) -> bool {
+    auto ckpt = [&](int step, const Lane<S>& lane) -> bool {
       if (!job.ckpt_t) return true;
       if (step >= job.ckpt_cap) return false;
       size_t o = (size_t)step * jB + b;
-      job.ckpt_t[2 * o] = t0;
-      job.ckpt_t[2 * o + 1] = dt;
-      ckpt_y[4 * o] = ya; ckpt_y[4 * o + 1] = yr; ckpt_y[4 * o + 2] = fa; ckpt_y[4 * o + 3] = fr;
+      double2 tt;
+      tt.x = lane.t0; tt.y = lane.dt;
+      *reinterpret_cast<double2*>(job.ckpt_t + 2 * o) = tt;
+      S buf[kCkptVals];
+      ckpt_pack<S>(lane, buf);
+      typedef typename Vec2<S>::type V2;
+      V2* dst = reinterpret_cast<V2*>(ckpt_y + (size_t)kCkptVals * o);
+#pragma unroll
+      for (int i = 0; i < kCkptVals / 2; ++i) {
+        V2 v;
+        v.x = buf[2 * i]; v.y = buf[2 * i + 1];
+        dst[i] = v;
+      }
       return true;
     };
 
@@ -235,8 +245,6 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
           if (owner) rk4_store_stage<S>(lanes[tid], cfg, s, (double)out);
         }
         if (owner) {
-          if (job.ckpt_t && lane_active(lanes[tid]))
-            ckpt(gi, g0, g1 - g0, lanes[tid].ya, lanes[tid].yr, lanes[tid].ka[0], lanes[tid].kr[0]);
           rk4_finish_step<S>(lanes[tid], g0, g1, p.time_f32 != 0, job.t_out, T, emit);
         }
       }

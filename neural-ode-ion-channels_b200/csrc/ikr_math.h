@@ -521,7 +521,7 @@ IKR_HD void dp_check_before_step(Lane<S>& L, const SolverCfg& c) {
 
 // After the six stages: error ratio, accept/reject, dense outputs, controller.
 //   emit(idx, a, r)            : write output sample idx
-//   checkpoint(step, t0, dt, y0a, y0r, f0a, f0r) -> bool : record an accepted step
+//   checkpoint(step, lane) -> bool : record an accepted step (t0, dt, y0, k_0..k_6)
 template <typename S, typename Emit, typename Ckpt>
 IKR_HD void dp_finish_step(Lane<S>& L, const SolverCfg& c, const double* t_out, int T, Emit emit,
                            Ckpt checkpoint) {
@@ -533,7 +533,7 @@ IKR_HD void dp_finish_step(Lane<S>& L, const SolverCfg& c, const double* t_out, 
   bool accept = ratio_s <= (S)1;
   L.n_int += 1;
   if (accept) {
-    if (!checkpoint(L.n_acc, L.t0, L.dt, L.ya, L.yr, L.ka[0], L.kr[0])) {
+    if (!checkpoint(L.n_acc, L)) {
       L.status = LANE_CKPT_OVERFLOW;
       return;
     }
@@ -641,6 +641,194 @@ IKR_HD void rk4_finish_step(Lane<S>& L, double g0, double g1, bool tf32, const d
   L.n_acc += 1;
   if (!(isfinite((double)L.ya) && isfinite((double)L.yr))) L.status = LANE_NONFINITE;
   else if (L.out_idx >= T) L.status = LANE_DONE;
+}
+
+
+// ==========================================================================================
+// Discrete adjoint of one accepted step (backward sweep).  Semantics = PyTorch autograd through
+// torchdiffeq's non-adjoint `odeint`: every accepted step's tensor ops are differentiated, step
+// sizes, stage times and dense-output abscissae are constants, rejected steps contribute nothing.
+//
+// The forward pass checkpoints, per accepted step, (t0, dt, y0, k_0..k_6) -- see StepCkpt -- so
+// the sweep never re-integrates: stage states are re-formed from the checkpoint (same arithmetic
+// as the forward), every stage costs exactly one MLP forward (activations kept) + one MLP
+// backward.  The sweep walks the steps last-to-first and, inside a step, the stages 5..0.
+// ==========================================================================================
+constexpr int kCkptVals = 16;   // per accepted step, state dtype: ya, yr, ka[0..6], kr[0..6]
+
+template <typename S>
+IKR_HD void ckpt_pack(const Lane<S>& L, S* dst) {
+  dst[0] = L.ya; dst[1] = L.yr;
+  for (int j = 0; j < 7; ++j) { dst[2 + j] = L.ka[j]; dst[9 + j] = L.kr[j]; }
+}
+
+template <typename S>
+struct BLane {
+  double t0, dt;         // the step being reversed
+  S ya, yr;              // y0 of that step
+  S ka[7], kr[7];        // k_0 .. k_6 of that step (checkpoint)
+  S lka[7], lkr[7];      // adjoints of k_0 .. k_6
+  S lya, lyr;            // in: adjoint of y1 (from the later steps); out: adjoint of y0
+  S lfa, lfr;            // in: adjoint of f1 = k_6 (FSAL: it is k_0 of the next step)
+  S la, lr;              // adjoint of y1 = Y_5 seeded by bdp_seed_step
+  S ja, jr;              // HH Jacobian terms d(fa_hh)/da, d(fr)/dr of the stage in flight
+  S gsum;                // accumulated dL/dg (fused-loss mode)
+  int n_left;            // accepted steps still to reverse (step index = n_left - 1)
+  int out_idx;           // largest output index not yet consumed
+  int phase;             // 0: reversing steps, 1: f(t[0], y0) pending, 2: finished
+};
+
+template <typename S>
+IKR_HD void blane_reset(BLane<S>& B, int n_acc, int T, bool valid) {
+  B.t0 = 0; B.dt = 0; B.ya = (S)0; B.yr = (S)1;
+  for (int j = 0; j < 7; ++j) { B.ka[j] = B.kr[j] = B.lka[j] = B.lkr[j] = (S)0; }
+  B.lya = B.lyr = B.lfa = B.lfr = B.la = B.lr = B.ja = B.jr = B.gsum = (S)0;
+  B.n_left = valid ? n_acc : 0;
+  B.out_idx = T - 1;
+  B.phase = valid ? (n_acc > 0 ? 0 : 1) : 2;
+}
+
+template <typename S>
+IKR_HD void blane_load_step(BLane<S>& B, double t0, double dt, const S* ck) {
+  B.t0 = t0; B.dt = dt; B.ya = ck[0]; B.yr = ck[1];
+  for (int j = 0; j < 7; ++j) { B.ka[j] = ck[2 + j]; B.kr[j] = ck[9 + j]; }
+}
+
+template <typename S>
+struct DenseAdj {
+  S a, b, c, d, e;
+};
+
+// adjoint of  y(x) = e + x d + x^2 c + x^3 b + x^4 a   w.r.t. the coefficients
+template <typename S>
+IKR_HD void adj_dense_accumulate(DenseAdj<S>& q, S x, S g) {
+  q.e = q.e + g;
+  q.d = q.d + x * g;
+  S xp = x * x;
+  q.c = q.c + xp * g;
+  xp = xp * x;
+  q.b = q.b + xp * g;
+  xp = xp * x;
+  q.a = q.a + xp * g;
+}
+
+// coefficients -> (y0, y1, y_mid, f0, f1); see dp_dense_fit
+template <typename S>
+IKR_HD void adj_dense_to_inputs(const DenseAdj<S>& q, double dt, S* ly0, S* ly1, S* lymid, S* lf0,
+                                S* lf1) {
+  S dts = (S)dt;
+  *ly0 = q.e - (S)8 * q.a + (S)18 * q.b - (S)11 * q.c;
+  *ly1 = -(S)8 * q.a + (S)14 * q.b - (S)5 * q.c;
+  *lymid = (S)16 * q.a - (S)32 * q.b + (S)16 * q.c;
+  *lf0 = dts * (-(S)2 * q.a + (S)5 * q.b - (S)4 * q.c + q.d);
+  *lf1 = dts * ((S)2 * q.a - (S)3 * q.b + q.c);
+}
+
+// Seed the adjoints of the loaded step from
+//   - the incoming adjoints of y1 (B.lya/lyr) and f1 (B.lfa/lfr),
+//   - the gradients of the outputs that fall in (t0, t0 + dt]   (grad(idx, &ga, &gr)).
+// Leaves lka/lkr[0..6] seeded, B.la/lr = adjoint of Y_5 (= y1), and B.lya/lyr = the part of the
+// adjoint of y0 that is already known.
+template <typename S, typename Grad>
+IKR_HD void bdp_seed_step(BLane<S>& B, const double* t_out, Grad grad) {
+  DenseAdj<S> qa = {(S)0, (S)0, (S)0, (S)0, (S)0}, qr = {(S)0, (S)0, (S)0, (S)0, (S)0};
+  const double t_lo = B.t0, t_hi = B.t0 + B.dt;
+  bool any = false;
+  while (B.out_idx >= 1 && t_out[B.out_idx] > t_lo) {
+    S ga, gr;
+    grad(B.out_idx, &ga, &gr);
+    S x = dp_dense_x<S>(t_lo, t_hi, t_out[B.out_idx]);
+    adj_dense_accumulate(qa, x, ga);
+    adj_dense_accumulate(qr, x, gr);
+    B.out_idx -= 1;
+    any = true;
+  }
+  for (int j = 0; j < 7; ++j) { B.lka[j] = (S)0; B.lkr[j] = (S)0; }
+  S ly1a = B.lya, ly1r = B.lyr;       // adjoint of y1 from the later steps
+  S ly0a = (S)0, ly0r = (S)0;
+  B.lka[6] = B.lfa; B.lkr[6] = B.lfr;  // f1 = k_6 is k_0 of the next step
+  if (any) {
+    S dts = (S)B.dt;
+    S a0, a1, am, f0, f1;
+    adj_dense_to_inputs(qa, B.dt, &a0, &a1, &am, &f0, &f1);
+    ly0a = ly0a + a0 + am; ly1a = ly1a + a1;
+    B.lka[0] = B.lka[0] + f0; B.lka[6] = B.lka[6] + f1;
+    for (int j = 0; j < 7; ++j) B.lka[j] = B.lka[j] + (dts * dp_cmid<S>(j)) * am;
+    adj_dense_to_inputs(qr, B.dt, &a0, &a1, &am, &f0, &f1);
+    ly0r = ly0r + a0 + am; ly1r = ly1r + a1;
+    B.lkr[0] = B.lkr[0] + f0; B.lkr[6] = B.lkr[6] + f1;
+    for (int j = 0; j < 7; ++j) B.lkr[j] = B.lkr[j] + (dts * dp_cmid<S>(j)) * am;
+  }
+  B.la = ly1a; B.lr = ly1r;            // y1 = Y_5
+  B.lya = ly0a; B.lyr = ly0r;
+}
+
+// d(fa)/d(net_out) = 1 / netscale applied to an adjoint of fa
+IKR_HD double adj_mlp_upstream(double lk, const SolverCfg& c) {
+  return c.mlp_is_f64 ? lk / c.netscale : (double)((float)lk / (float)c.netscale);
+}
+
+// Stage s (5..0) of the loaded step: MLP inputs (nv, a_in), the upstream gradient of the MLP
+// output `up` = lambda_{k_{s+1}} / netscale, and the HH Jacobian terms (kept in B.ja/jr).
+template <typename S>
+IKR_HD void bdp_stage_inputs(BLane<S>& B, const SolverCfg& c, int s, double* nv, double* a_in,
+                             double* up) {
+  S ti = dp_stage_time<S>(s, B.t0, B.dt);
+  S Ya = dp_stage_state<S>(s, B.ya, B.ka, B.dt);
+  double v;
+  bool in_table = table_voltage(c.tab, (double)ti, &v);
+  B.jr = (S)hh_drdt_dr(c.hp, v, in_table);
+  B.ja = c.nn_d ? (S)hh_dadt_da(c.hp, v, in_table) : (S)0;
+  *nv = mlp_input_nv(v, in_table, c.vrange, c.mlp_is_f64 != 0);
+  *a_in = (double)Ya;
+  *up = adj_mlp_upstream((double)B.lka[s + 1], c);
+}
+
+// Reverse stage s.  Before: B.lka/lkr[s+1] complete.  `mlp_grad_a` = up * d(net)/d(a_in) (the
+// MLP backward result for this lane).
+//   lambda_Y_s = J^T lambda_k_{s+1} (+ lambda_y1 for s = 5, carried in B.la/lr)
+//   lambda_y0 += lambda_Y_s ; lambda_k_j += (beta_sj dt) lambda_Y_s  (j <= s)
+template <typename S>
+IKR_HD void bdp_reverse_stage(BLane<S>& B, int s, S mlp_grad_a) {
+  S lYa = mlp_grad_a + B.lka[s + 1] * B.ja;
+  S lYr = B.lkr[s + 1] * B.jr;
+  if (s == 5) { lYa = lYa + B.la; lYr = lYr + B.lr; }
+  S dts = (S)B.dt;
+  B.lya = B.lya + lYa; B.lyr = B.lyr + lYr;
+  for (int j = 0; j <= s; ++j) {
+    S w = dp_beta<S>(s, j) * dts;
+    B.lka[j] = B.lka[j] + w * lYa;
+    B.lkr[j] = B.lkr[j] + w * lYr;
+  }
+}
+
+// End of the step: the adjoints of y0 / k_0 become the incoming adjoints of the previous step.
+template <typename S>
+IKR_HD void bdp_finish_step(BLane<S>& B) {
+  B.lfa = B.lka[0]; B.lfr = B.lkr[0];
+  B.n_left -= 1;
+  if (B.n_left <= 0) B.phase = 1;
+}
+
+// The first evaluation f0 = f(t[0], y0) (phase 1): its output adjoint is what the first step left
+// in lfa/lfr.
+template <typename S>
+IKR_HD void bdp_f0_inputs(BLane<S>& B, const SolverCfg& c, double t_start, S y0a, double* nv,
+                          double* a_in, double* up) {
+  double v;
+  bool in_table = table_voltage(c.tab, (double)(S)t_start, &v);
+  B.jr = (S)hh_drdt_dr(c.hp, v, in_table);
+  B.ja = c.nn_d ? (S)hh_dadt_da(c.hp, v, in_table) : (S)0;
+  *nv = mlp_input_nv(v, in_table, c.vrange, c.mlp_is_f64 != 0);
+  *a_in = (double)y0a;
+  *up = adj_mlp_upstream((double)B.lfa, c);
+}
+// `g0a, g0r` = dL/dy_out[0] (the first output sample is y0 itself)
+template <typename S>
+IKR_HD void bdp_f0_finish(BLane<S>& B, S mlp_grad_a, S g0a, S g0r) {
+  B.lya = B.lya + mlp_grad_a + B.lfa * B.ja + g0a;
+  B.lyr = B.lyr + B.lfr * B.jr + g0r;
+  B.phase = 2;
 }
 
 }  // namespace ikr

@@ -396,7 +396,7 @@ def _prepare_job(dm, desc, method, opts, dev, lib, sptr, job, state_dtype):
     if job.get('want_ckpt', False):
         cap = int(opts.get('ckpt_cap', 0)) or (io.G if method == 'rk4' else 4096)
         ck_t = torch.empty((cap, B, 2), dtype=torch.float64, device=dev)
-        ck_y = torch.empty((cap, B, 4), dtype=state_dtype, device=dev)
+        ck_y = torch.empty((cap, B, 16), dtype=state_dtype, device=dev)
         io.ckpt_cap, io.ckpt_t, io.ckpt_y = cap, ck_t.data_ptr(), ck_y.data_ptr()
         ckpt = (ck_t, ck_y)
     res = IkrResult(y=y_out, current=cur, sse=None if loss is None else loss[:, 0],

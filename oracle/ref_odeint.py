@@ -134,7 +134,8 @@ class Dopri5:
     order = 5
 
     def __init__(self, func, y0, rtol, atol, first_step=None, safety=0.9, ifactor=10.0,
-                 dfactor=0.2, max_num_steps=2 ** 31 - 1, detach_first_step=False, record=None):
+                 dfactor=0.2, max_num_steps=2 ** 31 - 1, detach_first_step=False, record=None,
+                 replay=None):
         self.f = _TimeCast(func)
         self.y0 = y0
         tdt = torch.promote_types(torch.float64, y0.dtype)
@@ -155,6 +156,11 @@ class Dopri5:
         self.n_accept = 0
         self.n_reject = 0
         self.record = record          # optional list receiving (t0, dt, accepted) per attempt
+        # TEST HOOK (not torchdiffeq): `replay` = [(t0, dt), ...] of the accepted steps of another
+        # run.  The controller is bypassed and exactly these steps are taken, so that gradients
+        # can be compared step-for-step (the step-size sequence is ill-conditioned w.r.t. rounding:
+        # two correct implementations drift apart by ~1e-7 relative in dt after a stiff phase).
+        self.replay = None if replay is None else list(replay)
 
     # one Runge-Kutta attempt ---------------------------------------------------------------
     def _rk_step(self, y0, f0, t0, dt, t1):
@@ -210,10 +216,15 @@ class Dopri5:
                 t1 = ts + dt
                 assert ts + dt > ts, 'underflow in dt {}'.format(dt.item())
                 assert torch.isfinite(y).all(), 'non-finite values in state `y`: {}'.format(y)
+                if self.replay is not None:
+                    r_t0, r_dt = self.replay[self.n_accept]
+                    ts = torch.as_tensor(r_t0, dtype=self.tdtype)
+                    dt = torch.as_tensor(r_dt, dtype=self.tdtype)
+                    t1 = ts + dt
                 y1, f1, err, k = self._rk_step(y, f, ts, dt, t1)
                 tol = self.atol + self.rtol * torch.max(y.abs(), y1.abs())
                 ratio = _rms(err / tol)
-                accept = bool(ratio <= 1)
+                accept = bool(ratio <= 1) or self.replay is not None
                 if self.record is not None:
                     self.record.append((float(ts), float(dt), accept))
                 if accept:
@@ -286,7 +297,7 @@ class RK4:
 
 
 _KNOWN_ADAPTIVE = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps',
-                   'detach_first_step', 'record'}
+                   'detach_first_step', 'record', 'replay'}
 _KNOWN_FIXED = {'step_size', 'perturb'}
 
 

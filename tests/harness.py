@@ -96,3 +96,35 @@ def table_voltage(tab_t, tab_v, x):
                                   ctypes.c_double(t0), ctypes.c_double(inv), ctypes.c_double(x),
                                   ctypes.byref(flag))
     return v, bool(flag.value)
+
+
+class GradArgs(ctypes.Structure):
+    _fields_ = [('grad_y', ctypes.c_void_p), ('grad_params', ctypes.c_void_p),
+                ('grad_y0', ctypes.c_void_p), ('steps_cap', ctypes.c_int)]
+
+
+def gradient(net, L, n, nn_d, p8, tab_t, tab_v, y0, t_out, grad_y, state_f64, mlp_f64, rtol=1e-7,
+             atol=1e-9, first_step=0.0):
+    """Host build of the lane adjoint (ikr_math.h) + scalar MLP backward: dL/dparams (flat,
+    state_dict order) and dL/dy0 for L = sum(grad_y * y_out)."""
+    import torch
+    lib = build()
+    params = flat_params(net, torch.float64 if mlp_f64 else torch.float32)
+    tab_t = np.ascontiguousarray(tab_t, dtype=np.float64)
+    tab_v = np.ascontiguousarray(tab_v, dtype=np.float64)
+    t_out = np.ascontiguousarray(t_out, dtype=np.float64)
+    p = np.ascontiguousarray(p8, dtype=np.float64)
+    y_out = np.zeros((len(t_out), 2))
+    stats = np.zeros(4, dtype=np.int32)
+    uni, t0, inv = uniform_hint(tab_t)
+    a = Args(L, n, int(nn_d), 0, 0, 0, params.ctypes.data, tab_t.ctypes.data, tab_v.ctypes.data,
+             len(tab_t), uni, t0, inv, p.ctypes.data, rtol, atol, first_step, t_out.ctypes.data,
+             len(t_out), t_out.ctypes.data, len(t_out), float(y0[0]), float(y0[1]),
+             y_out.ctypes.data, stats.ctypes.data, None, 0)
+    gy = np.ascontiguousarray(grad_y, dtype=np.float64)
+    gp = np.zeros(len(params))
+    g0 = np.zeros(2)
+    g = GradArgs(gy.ctypes.data, gp.ctypes.data, g0.ctypes.data, 0)
+    rc = lib.harness_grad(int(state_f64), int(mlp_f64), ctypes.byref(a), ctypes.byref(g))
+    assert rc == 0
+    return gp, g0, y_out, stats

@@ -1,0 +1,205 @@
+"""GPU parity tests of the backward path (adjoint sweep + weight-gradient GEMM, through the C ABI)
+against PyTorch autograd through the CPU oracle (restated torchdiffeq dopri5 + reference RHS).
+
+The oracle replays the accepted steps the CUDA run took (``options={'replay': ...}``, see
+oracle/ref_odeint.py): the step-size controller is ill-conditioned with respect to rounding, so two
+correct implementations drift apart in dt by ~1e-7 relative after a stiff phase; with the steps
+pinned, the gradients must agree to rounding.
+
+Tolerances: fp64 state + fp64 MLP: 1e-8 relative to the largest gradient entry (north star: equal
+loss / gradients to 1e-8 relative); fp32 "as shipped": 2e-3 (fp32 accumulation noise).
+"""
+import numpy as np
+import pytest
+import torch
+
+import neural_ode_ion_channels_b200 as ikr
+from neural_ode_ion_channels_b200 import protocols
+from oracle import ref_odeint as ro
+from tests import kat
+from tests.test_gpu_forward import _nn
+
+pytestmark = pytest.mark.gpu
+
+
+def _flat(grads):
+    return torch.cat([g.reshape(-1).double().cpu() for g in grads]).numpy()
+
+
+def _oracle_grads(ofunc, y0, t, steps_per_lane, first_step, loss_fn):
+    """sum over lanes of d loss_fn(b, y_b)/d theta by autograd through the oracle, replaying the
+    accepted steps of each lane; returns (flat param grad, grad_y0 (B,2), losses)."""
+    params = list(ofunc.net.parameters())
+    for p in params:
+        p.requires_grad_(True)
+        p.grad = None
+    gy0, losses = [], []
+    for b in range(y0.shape[0]):
+        yb = y0[b:b + 1].clone().requires_grad_(True)
+        y = ro.odeint(ofunc, yb, t, options={'first_step': first_step,
+                                             'replay': steps_per_lane[b]})
+        lb = loss_fn(b, y[:, 0, :])
+        lb.backward()
+        gy0.append(yb.grad.reshape(-1).double())
+        losses.append(float(lb.detach()))
+    g = torch.cat([p.grad.reshape(-1).double() for p in params]).numpy()
+    for p in params:
+        p.requires_grad_(False)
+        p.grad = None
+    return g, torch.stack(gy0).numpy(), np.array(losses)
+
+
+def _steps(res):
+    ck_t = res.ckpt[0].cpu().numpy()
+    st = res.stats.cpu().numpy()
+    return [[(float(ck_t[j, b, 0]), float(ck_t[j, b, 1])) for j in range(st[b, 0])]
+            for b in range(st.shape[0])]
+
+
+def _setup(study, double, t_end=60., n_out=31):
+    torch.set_num_threads(1)
+    func, ofunc = _nn(study, double=double)
+    t_tab, v_tab = protocols.ap2hz()
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    ofunc.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    dt = torch.float64 if double else torch.float32
+    t = torch.linspace(0., t_end, n_out, dtype=dt)
+    return func, ofunc, t
+
+
+@pytest.mark.parametrize('study', ['s1', 'd2'])
+def test_autograd_through_odeint_fp64_matches_oracle(study):
+    func, ofunc, t = _setup(study, True)
+    y0 = torch.tensor([[0.02, 0.97], [0.0, 1.0], [0.3, 0.6]], dtype=torch.float64)
+    rng = np.random.RandomState(4)
+    w = torch.from_numpy(rng.randn(len(t), 3, 2))
+    func.cuda()
+    for p in func.net.parameters():
+        p.requires_grad_(True)
+    y0g = y0.cuda().requires_grad_(True)
+    y = ikr.odeint(func, y0g, t, options={'first_step': 0.05})
+    (y * w.cuda()).sum().backward()
+    got = _flat([p.grad for p in func.net.parameters()])
+    got_y0 = y0g.grad.cpu().numpy()
+    # replay the accepted steps on the oracle
+    with torch.no_grad():
+        res = ikr.integrate(func, y0.cuda(), t, options={'first_step': 0.05}, want_ckpt=True)
+    want, want_y0, _ = _oracle_grads(ofunc, y0, t, _steps(res), 0.05,
+                                     lambda b, yb: (yb * w[:, b, :]).sum())
+    assert np.abs(got - want).max() <= 1e-8 * np.abs(want).max()
+    assert np.abs(got_y0 - want_y0).max() <= 1e-8 * np.abs(want_y0).max()
+
+
+def test_fused_sse_loss_and_grad_fp64_matches_oracle():
+    func, ofunc, t = _setup('d2', True)
+    B = 5
+    rng = np.random.RandomState(5)
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.9, 1, B)], 1))
+    g = torch.tensor(rng.lognormal(0, 0.2, B))
+    data = torch.from_numpy(rng.randn(len(t), B) * 0.1)
+    func.cuda()
+    total, per, grads, res = ikr.loss_and_grad(func, y0.cuda(), t, data, g=g, E=-86.0,
+                                               options={'first_step': 0.05}, want_y0=True,
+                                               want_g=True)
+    v = torch.from_numpy(np.interp(t.numpy(), *protocols.ap2hz()))
+
+    def loss_fn(b, yb):
+        cur = g[b] * yb[:, 0] * yb[:, 1] * (v + 86.0)
+        return ((cur - data[:, b]) ** 2).sum()
+
+    want, want_y0, want_l = _oracle_grads(ofunc, y0, t, _steps(res), 0.05, loss_fn)
+    assert np.abs(per.cpu().numpy() - want_l).max() <= 1e-8 * np.abs(want_l).max()
+    assert abs(float(total) - want_l.sum()) <= 1e-8 * want_l.sum()
+    assert np.abs(_flat(grads) - want).max() <= 1e-8 * np.abs(want).max()
+    assert np.abs(res.grad_y0.cpu().numpy() - want_y0).max() <= 1e-8 * np.abs(want_y0).max()
+    # dL/dg by finite differences of the fused loss itself (g enters the loss linearly per sample)
+    eps = 1e-6
+    with torch.no_grad():
+        lp = ikr.integrate(func, y0.cuda(), t, g=g + eps, data=data, want_y=False,
+                           options={'first_step': 0.05}).sse.cpu().numpy()
+        lm = ikr.integrate(func, y0.cuda(), t, g=g - eps, data=data, want_y=False,
+                           options={'first_step': 0.05}).sse.cpu().numpy()
+    fd = (lp - lm) / (2 * eps)
+    assert np.abs(res.grad_g.cpu().numpy() - fd).max() <= 1e-5 * np.abs(fd).max()
+
+
+def test_fp32_as_shipped_gradient_envelope():
+    func, ofunc, t = _setup('d1', False, t_end=40., n_out=21)
+    y0 = torch.tensor([[0.02, 0.97], [0.0, 1.0]])
+    rng = np.random.RandomState(6)
+    data = torch.from_numpy((rng.randn(len(t), 1) * 0.1).astype(np.float32))
+    func.cuda()
+    total, per, grads, res = ikr.loss_and_grad(func, y0.cuda(), t, data, loss='sae',
+                                               options={'first_step': 0.05}, want_y0=True)
+    v = torch.from_numpy(np.interp(t.double().numpy(), *protocols.ap2hz()))
+
+    def loss_fn(b, yb):
+        cur = (yb[:, 0] * yb[:, 1]).double() * (v + 86.0)
+        return (cur - data[:, 0].double()).abs().sum()
+
+    want, want_y0, want_l = _oracle_grads(ofunc, y0, t, _steps(res), 0.05, loss_fn)
+    assert np.abs(per.cpu().numpy() - want_l).max() <= 1e-4 * np.abs(want_l).max()
+    assert np.abs(_flat(grads) - want).max() <= 2e-3 * np.abs(want).max()
+    assert np.abs(res.grad_y0.cpu().numpy() - want_y0).max() <= 2e-3 * np.abs(want_y0).max()
+
+
+def test_gradient_is_round_and_tile_invariant():
+    """Many trajectories (several tiles, ragged last tile); one reversed step per round versus
+    the default round size; two tile sizes: same gradient up to summation order."""
+    func, _, t = _setup('s1', True, t_end=30., n_out=16)
+    B = 77
+    rng = np.random.RandomState(7)
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.9, 1, B)], 1))
+    data = torch.from_numpy(rng.randn(len(t), B) * 0.1)
+    func.cuda()
+    ref = None
+    for opts, ws in (({}, None), ({'tile_m': 16}, None), ({'tile_m': 32}, 'small')):
+        o = dict(opts, first_step=0.05)
+        kw = {}
+        if ws == 'small':
+            # room for exactly one reversed step per round
+            import ctypes
+            from neural_ode_ion_channels_b200 import _cabi
+            res0 = ikr.integrate(func, y0.cuda(), t, options=o, data=data, want_ckpt=True)
+            full = _cabi.lib().ikr_workspace_bytes(ctypes.byref(res0._desc), 1, B, 1)
+            kw['workspace_bytes'] = full // 3
+        total, per, grads, res = ikr.loss_and_grad(func, y0.cuda(), t, data, options=o, **kw)
+        flat = _flat(grads)
+        if ref is None:
+            ref = (flat, per.cpu().numpy())
+            assert np.isfinite(flat).all() and np.abs(flat).max() > 0
+        else:
+            assert np.abs(flat - ref[0]).max() <= 1e-10 * np.abs(ref[0]).max()
+            assert np.abs(per.cpu().numpy() - ref[1]).max() <= 1e-12 * np.abs(ref[1]).max()
+
+
+@pytest.mark.parametrize('arch', ['s03', 's10', 's01'])
+def test_gradient_fp64_architectures(arch):
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    func = ikr.ODEFuncNNf(arch=arch, params='r').double()
+    from oracle import ref_models as rm
+    L, n = ikr.ARCHITECTURES[arch]
+    ofunc = rm.NNfRhs(net=rm.build_mlp(L, n),
+                      inact=tuple(func.__dict__['p%d' % i] for i in (5, 6, 7, 8)),
+                      mlp_follows_state=True).double()
+    ofunc.net.load_state_dict(func.net.state_dict())
+    ofunc.vrange = ofunc.vrange.double()
+    ofunc.netscale = ofunc.netscale.double()
+    t_tab, v_tab = protocols.pr3_activation(20)
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    ofunc.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 1200., 25, dtype=torch.float64)
+    y0 = torch.tensor([[0.01, 0.9], [0.1, 0.5]], dtype=torch.float64)
+    w = torch.from_numpy(np.random.RandomState(8).randn(len(t), 2, 2))
+    func.cuda()
+    for p in func.net.parameters():
+        p.requires_grad_(True)
+    y = ikr.odeint(func, y0.cuda(), t, options={'first_step': 0.05})
+    (y * w.cuda()).sum().backward()
+    got = _flat([p.grad for p in func.net.parameters()])
+    with torch.no_grad():
+        res = ikr.integrate(func, y0.cuda(), t, options={'first_step': 0.05}, want_ckpt=True)
+    want, _, _ = _oracle_grads(ofunc, y0, t, _steps(res), 0.05,
+                               lambda b, yb: (yb * w[:, b, :]).sum())
+    assert np.abs(got - want).max() <= 1e-8 * np.abs(want).max()

@@ -84,3 +84,80 @@ def test_dopri5_fp32_host_logic_ap2hz():
                                       t.double().numpy(), False, False)
     assert stats[3] == 0 and abs(int(stats[0]) - st['n_accept']) < 0.05 * st['n_accept']
     assert np.abs(got - want).max() < 1e-4          # fp32-state noise envelope
+
+
+# ---------------------------------------------------------------------------------------------
+# discrete adjoint (the lane functions the backward kernel runs) vs autograd through the oracle
+# ---------------------------------------------------------------------------------------------
+def _oracle_grad(nn, y0, t, grad_y, first_step, replay=None):
+    """d/dtheta, d/dy0 of sum(grad_y * odeint(...)) by PyTorch autograd through the restated
+    torchdiffeq dopri5 (step sizes are constants of the backward pass: `first_step` is given so
+    that the initial-step heuristic -- the only place torchdiffeq lets dt carry a graph -- is
+    not in play)."""
+    for p in nn.net.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    y0 = y0.clone().requires_grad_(True)
+    st = {}
+    opts = {'first_step': first_step}
+    if replay is not None:
+        opts['replay'] = replay
+    y = ro.odeint(nn, y0, t, options=opts, stats=st)
+    (y[:, 0, :] * grad_y).sum().backward()
+    g = torch.cat([p.grad.reshape(-1) for p in nn.net.parameters()]).double().numpy()
+    for p in nn.net.parameters():
+        p.requires_grad_(False)
+    return g, y0.grad.reshape(-1).double().numpy(), y.detach().numpy()[:, 0, :], st
+
+
+@pytest.mark.parametrize('study', ['s1', 'd2'])
+def test_adjoint_fp64_host_logic_matches_oracle_autograd(study):
+    """31 outputs over the first AP upstroke (37 accepted / 17 rejected steps).  With the
+    oracle's own controller the two step-size sequences drift apart by ~1e-7 relative after the
+    stiff phase (ill-conditioned error estimate), so that comparison is loose; with the accepted
+    steps replayed into the oracle the gradients agree to rounding."""
+    torch.set_num_threads(1)
+    nn = _double(kat.make_nn(study, mlp_follows_state=True))
+    t_tab, v_tab = protocols.ap2hz()
+    nn.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    y0 = torch.tensor([[0.02, 0.97]], dtype=torch.float64)
+    t = torch.linspace(0., 60., 31, dtype=torch.float64)
+    rng = np.random.RandomState(1)
+    gy = rng.randn(len(t), 2)
+    args = (nn.net, 5, 200, study == 'd2', _p8(nn), t_tab, v_tab, [0.02, 0.97], t.numpy())
+    got_g, got_y0, got_y, stats = harness.gradient(*args, gy, True, True, first_step=0.05)
+    _, _, steps = harness.integrate(*args, True, True, first_step=0.05, steps_cap=4096)
+
+    want_g, want_y0, want_y, st = _oracle_grad(nn, y0, t, torch.from_numpy(gy), 0.05)
+    if (stats[0], stats[1]) == (st['n_accept'], st['n_reject']):   # same accept/reject decisions
+        assert np.abs(got_y - want_y).max() <= 1e-10
+        assert np.abs(got_g - want_g).max() <= 1e-5 * np.abs(want_g).max()
+        assert np.abs(got_y0 - want_y0).max() <= 1e-5 * np.abs(want_y0).max()
+    else:                                                          # controller took another path
+        assert study != 's1'
+        assert np.abs(got_y - want_y).max() <= 5e-6   # global-error envelope at rtol 1e-7
+
+    want_g, want_y0, want_y, st = _oracle_grad(nn, y0, t, torch.from_numpy(gy), 0.05,
+                                               replay=[tuple(r) for r in steps])
+    assert np.abs(got_y - want_y).max() <= 1e-13
+    assert np.abs(got_g - want_g).max() <= 1e-11 * np.abs(want_g).max()
+    assert np.abs(got_y0 - want_y0).max() <= 1e-11 * np.abs(want_y0).max()
+
+
+def test_adjoint_fp32_as_shipped_host_logic():
+    """fp32 state + fp32 MLP (the reference's shipped precision): gradient vs the oracle's
+    autograd on the replayed step sequence, fp32 noise envelope."""
+    torch.set_num_threads(1)
+    nn = kat.make_nn('d2')
+    t_tab, v_tab = protocols.ap2hz()
+    nn.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    y0 = torch.tensor([[0.02, 0.97]])
+    t = torch.linspace(0., 40., 21)
+    gy = np.random.RandomState(3).randn(len(t), 2).astype(np.float32)
+    args = (nn.net, 5, 200, True, _p8(nn), t_tab, v_tab, [0.02, 0.97], t.double().numpy())
+    got_g, got_y0, _, stats = harness.gradient(*args, gy, False, False, first_step=0.05)
+    _, _, steps = harness.integrate(*args, False, False, first_step=0.05, steps_cap=4096)
+    want_g, want_y0, _, _ = _oracle_grad(nn, y0, t, torch.from_numpy(gy), 0.05,
+                                         replay=[tuple(r) for r in steps])
+    assert np.abs(got_g - want_g).max() <= 2e-4 * np.abs(want_g).max()
+    assert np.abs(got_y0 - want_y0).max() <= 2e-4 * np.abs(want_y0).max()
