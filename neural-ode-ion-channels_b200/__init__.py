@@ -9,11 +9,11 @@ Public surface (mirrors what the reference scripts use on this path):
 * ``ARCHITECTURES`` / ``build_net``                    -- architectures/s00..s11
 * ``protocols``                                        -- voltage-clamp protocol tables
 """
-from . import protocols  # noqa: F401
+from . import parallel, protocols  # noqa: F401
 from .models import (ARCHITECTURES, PARAMETER_SETS, ODEFunc, ODEFuncNNd, ODEFuncNNf,  # noqa: F401
                      build_net, load_weights)
 from .solver import IkrResult, describe, integrate, integrate_many, odeint  # noqa: F401
 from .adjoint import loss_and_grad  # noqa: F401
 
 __all__ = ['odeint', 'integrate', 'loss_and_grad', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
-           'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols']
+           'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols', 'parallel']
