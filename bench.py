@@ -33,6 +33,7 @@ FAMILY_SWEEP = {'pr3': 4, 'pr4': 10, 'pr5': 4, 'sinewave': 0, 'aps': 0}   # swee
 WEIGHTS = os.path.join(ROOT, 'neural-ode-ion-channels_b200', 'data', 'weights',
                        'd1-model-state-dict.pt')
 FLOP_PER_EVAL = 2 * 200600          # BASELINE.md section 3 (s00 architecture, forward)
+METRIC = 'NN-ODE RHS evals/sec (batched dopri5; headline = configs[1] forward, fwd+backward in "train")'
 
 
 def parse_args():
@@ -45,6 +46,10 @@ def parse_args():
     ap.add_argument('--families', default='pr3,pr4,pr5,sinewave,aps')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--train-batch', type=int, default=4096,
+                    help='datasets per GPU of the fwd+bwd leg (configs[2]); 0 disables the leg')
+    ap.add_argument('--train-outputs', type=int, default=7501,
+                    help='output samples of the staircase stand-in used by the fwd+bwd leg')
     return ap.parse_args()
 
 
@@ -132,7 +137,7 @@ def run_reference(args):
     sample = ('%d worker processes x 1 trajectory (B=1 per odeint call) cycling the %s sweeps, '
               '~%.0f s of each trajectory per step' % (cores, '/'.join(families), per_step))
     line = {
-        'impl': 'reference', 'metric': 'NN-ODE RHS evals/sec (batched dopri5 fwd)',
+        'impl': 'reference', 'metric': METRIC,
         'value': value, 'unit': 'evals/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * wall_tot / max(1, args.steps),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -187,6 +192,81 @@ class ClockSampler(threading.Thread):
         s = sorted(self.samples)
         return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz,
                 'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+def run_train_leg(args, ikr, dev, world, rank):
+    """configs[2]: NN-d (d2 weights) fitted to noisy staircase datasets -- ONE training step =
+    batched dopri5 forward with step checkpoints + fused SSE loss + backward through the solver
+    (adjoint sweep + weight-gradient GEMM) + (N > 1) one flat all-reduce of the gradient.
+    Returns a dict for the JSON line (device-timed, max over ranks)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from neural_ode_ion_channels_b200 import parallel, protocols
+    B = args.train_batch
+    wpath = os.path.join(ROOT, 'neural-ode-ion-channels_b200', 'data', 'weights',
+                         'd2-model-state-dict.pt')
+    func = ikr.load_weights(ikr.ODEFuncNNd(params='d'), wpath).to(dev)
+    name, t_tab, v_tab, t_out = protocols.protocol_set('staircase')[0]
+    t_out = t_out[:args.train_outputs]
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.tensor(t_out, dtype=torch.float32)
+    rng = np.random.RandomState(2000 + rank)
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1.0, B)], 1),
+                      dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        nominal = ikr.integrate(func, torch.tensor([[0., 1.]], device=dev), t, want_current=True,
+                                want_y=False, E=-86.0).current[:, 0]
+    # 4,096 noisy datasets: nominal trace + N(0, 0.1^2) per dataset (train-d2.py:40 noise_sigma)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3000 + rank)
+    data = nominal[:, None] + 0.1 * torch.randn(len(t), B, generator=gen, device=dev)
+    opts = {'check_status': False, 'ckpt_cap': args.train_outputs // 2 + 512}
+
+    def step():
+        total, per, grads, res = ikr.loss_and_grad(func, y0, t, data, E=-86.0, options=opts)
+        if world > 1:
+            grads, total = parallel.allreduce_gradients(grads, total)
+        return total, grads, res
+
+    total, grads, res = step()          # warm-up (also sizes the caching allocator)
+    st = res.stats
+    assert int((st[:, 3] != 0).sum()) == 0, 'solver status != ok in the training leg'
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    total, grads, res = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = res.stats
+    nfe_f = float(st[:, 2].sum())
+    nfe_b = float((6 * st[:, 0] + 1).sum())
+    vec = torch.tensor([ms, nfe_f, nfe_b], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = vec.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vec.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_all, nfe_f_all, nfe_b_all = float(mx[0]), float(sm[1]), float(sm[2])
+    else:
+        ms_all, nfe_f_all, nfe_b_all = ms, nfe_f, nfe_b
+    gmax = max(float(g.abs().max()) for g in grads)
+    return {
+        'workload': 'configs[2]: NN-d (d2 weights, s00 MLP) one training step through dopri5 on %d '
+                    'noisy %s datasets per GPU (%d output samples): forward + fused SSE + adjoint '
+                    'sweep + weight-gradient GEMM%s' % (B, name, len(t), '' if world == 1 else
+                                                      ' + one flat NCCL all-reduce'),
+        'value': (nfe_f_all + nfe_b_all) / (ms_all * 1e-3), 'unit': 'evals/s (fwd + adjoint)',
+        'ms_per_step': ms_all, 'forward_evals': nfe_f_all, 'adjoint_evals': nfe_b_all,
+        'accepted_steps_mean': float(st[:, 0].float().mean()),
+        'algorithmic_tflops': (nfe_f * FLOP_PER_EVAL + nfe_b * 3 * FLOP_PER_EVAL) / (ms * 1e-3) / 1e12,
+        'loss': float(total), 'grad_abs_max': gmax,
+    }
 
 
 def run_b200(args):
@@ -293,6 +373,7 @@ def run_b200(args):
     nfe_total = int(nfe_dev.item())
     assert int(bad_dev.item()) == 0, 'solver status != ok in the timed region'
     steps_per_lane = [float((r.stats[:, 0] + r.stats[:, 1]).float().mean()) for r in outs]
+    geo = outs[0].geometry
 
     # e2e: host inputs, H2D + D2H inside the timed region
     for _ in range(min(2, args.warmup)):
@@ -320,18 +401,22 @@ def run_b200(args):
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, e2e_ms = float(mx[0]), float(mx[1])
         nfe_total, nfe_e2e = float(sm[2]), float(sm[3])
+    h2d = sum(j['y0'].numel() * 4 + j['g'].numel() * 4 for j in jobs_host) + \
+        sum(t.numel() * 8 for t in tgrids)
+    d2h = sum(nb * 8 + nb * 16 for nb in sizes)
+    train = None
+    if args.train_batch > 0:
+        del jobs_dev, jobs_host, outs
+        torch.cuda.empty_cache()
+        train = run_train_leg(args, ikr, dev, world, rank)
     if rank == 0:
         value = nfe_total / (ms * 1e-3)
         e2e_value = nfe_e2e / (e2e_ms * 1e-3)
         # the forward kernel is >99.9 % of the timed region (profiles/): its launch duration is the
         # event-timed step
         achieved = (nfe_rank0 * FLOP_PER_EVAL) / (ms_rank0 * 1e-3) / 1e12
-        h2d = sum(j['y0'].numel() * 4 + j['g'].numel() * 4 for j in jobs_host) + \
-            sum(t.numel() * 8 for t in tgrids)
-        d2h = sum(nb * 8 + nb * 16 for nb in sizes)
-        geo = outs[0].geometry
         line = {
-            'metric': 'NN-ODE RHS evals/sec (batched dopri5 fwd)',
+            'metric': METRIC,
             'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -365,6 +450,9 @@ def run_b200(args):
             },
             'cpu_baseline': cpu_base,
         }
+        if train is not None:
+            train['roofline_frac'] = train['algorithmic_tflops'] / fma_peak_tflops
+            line['train'] = train
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -164,6 +164,7 @@ int ikr_interp_protocol(const ikr_io* table, const double* t_query, int64_t T, d
 /* FMA-pipe micro-benchmark used by bench.py for the roofline denominator: runs `iters`
  * dependent-free FFMA (dtype F32) or DFMA (F64) per thread on every SM and returns the elapsed
  * milliseconds through *ms_out (this one entry point synchronises the stream).                  */
+/* dtype: IKR_F32 (scalar FFMA), IKR_F64 (DFMA) or 2 (packed FFMA2, fma.rn.f32x2).            */
 int ikr_fma_peak(int32_t dtype, int64_t iters, double* tflops_out, void* cuda_stream);
 
 #ifdef __cplusplus

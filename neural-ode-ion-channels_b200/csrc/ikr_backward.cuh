@@ -77,7 +77,7 @@ struct AdjSmemLayout {
     off_sg = o; o += (size_t)(4 * npad + 8) * sizeof(double);
     off_mask = o; o += (size_t)L * npad * (M / 8); o = (o + 127) & ~(size_t)127;
     off_hs = o; o += (size_t)npad * M * sizeof(W); o = (o + 127) & ~(size_t)127;
-    off_wr = o; o += (size_t)kStages * kc * npad * sizeof(W);
+    off_wr = o; o += ((size_t)kStages * kc + 1) * npad * sizeof(W);   // +1 row: prefetch pad
     total = o;
   }
 };
@@ -564,6 +564,13 @@ __global__ void __launch_bounds__(kWgMaxThreads, 1) ikr_wgrad_kernel(const Wgrad
     for (int c = 0; c < RI; ++c) acc[r][c] = (W)0;
   }
 
+  f32x2 c2[RO][4];
+  if (sizeof(W) == 4) {
+#pragma unroll
+    for (int r = 0; r < RO; ++r)
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) c2[r][pc] = f2_pack(0.f, 0.f);
+  }
   for (long long j = 0; j < my_chunks; ++j) {
     const int st = (int)(j % p.stages);
     const unsigned par = (unsigned)((j / p.stages) & 1);
@@ -571,19 +578,28 @@ __global__ void __launch_bounds__(kWgMaxThreads, 1) ikr_wgrad_kernel(const Wgrad
     if (worker) {
       const W* Dp = ring + (size_t)st * stage_elems + o0 + og * RO;
       const W* Hp = ring + (size_t)st * stage_elems + op_elems + i0 + ig * V;
+      if (sizeof(W) == 4) {
 #pragma unroll 2
-      for (int m = 0; m < p.KC; ++m) {
-        W d[RO], h[RI];
-        if (sizeof(W) == 4) {
+        for (int m = 0; m < p.KC; ++m) {
           const float4 d0 = *reinterpret_cast<const float4*>(Dp + (size_t)m * npad);
           const float4 d1 = *reinterpret_cast<const float4*>(Dp + (size_t)m * npad + 4);
-          d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w;
-          d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
           const float4 h0 = *reinterpret_cast<const float4*>(Hp + (size_t)m * npad);
           const float4 h1 = *reinterpret_cast<const float4*>(Hp + (size_t)m * npad + half);
-          h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w;
-          h[RI - 4] = h1.x; h[RI - 3] = h1.y; h[RI - 2] = h1.z; h[RI - 1] = h1.w;
-        } else {
+          const float d[RO] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          const f32x2 h[4] = {f2_pack(h0.x, h0.y), f2_pack(h0.z, h0.w), f2_pack(h1.x, h1.y),
+                              f2_pack(h1.z, h1.w)};
+#pragma unroll
+          for (int r = 0; r < RO; ++r) {
+            const f32x2 dd = f2_pack(d[r], d[r]);
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) f2_fma(c2[r][pc], dd, h[pc]);
+            bacc[r] += (W)d[r];
+          }
+        }
+      } else {
+#pragma unroll 2
+        for (int m = 0; m < p.KC; ++m) {
+          W d[RO], h[RI];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const double2 dv = *reinterpret_cast<const double2*>(Dp + (size_t)m * npad + 2 * g);
@@ -592,12 +608,12 @@ __global__ void __launch_bounds__(kWgMaxThreads, 1) ikr_wgrad_kernel(const Wgrad
           const double2 h0 = *reinterpret_cast<const double2*>(Hp + (size_t)m * npad);
           const double2 h1 = *reinterpret_cast<const double2*>(Hp + (size_t)m * npad + half);
           h[0] = h0.x; h[1] = h0.y; h[RI - 2] = h1.x; h[RI - 1] = h1.y;
-        }
 #pragma unroll
-        for (int r = 0; r < RO; ++r) {
+          for (int r = 0; r < RO; ++r) {
 #pragma unroll
-          for (int c = 0; c < RI; ++c) acc[r][c] = ikr_fma(d[r], h[c], acc[r][c]);
-          bacc[r] += d[r];
+            for (int c = 0; c < RI; ++c) acc[r][c] = ikr_fma(d[r], h[c], acc[r][c]);
+            bacc[r] += d[r];
+          }
         }
       }
     }
@@ -609,6 +625,16 @@ __global__ void __launch_bounds__(kWgMaxThreads, 1) ikr_wgrad_kernel(const Wgrad
       mbar_wait(&empty[jp % p.stages], (unsigned)((jp / p.stages) & 1));
       issue(jp + p.stages);
     }
+  }
+  if (sizeof(W) == 4) {
+#pragma unroll
+    for (int r = 0; r < RO; ++r)
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) {
+        float lo, hi;
+        f2_unpack(c2[r][pc], lo, hi);
+        acc[r][(2 * pc) % RI] = (W)lo; acc[r][(2 * pc + 1) % RI] = (W)hi;
+      }
   }
 
   if (worker) {

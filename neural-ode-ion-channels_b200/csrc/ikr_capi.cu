@@ -588,6 +588,8 @@ int ikr_fma_peak(int32_t dtype, int64_t iters, double* tflops_out, void* cuda_st
     cudaEventRecord(e0, st);
     if (dtype == IKR_F32)
       ikr_fma_peak_kernel<float><<<blocks, threads, 0, st>>>((float*)sink, iters);
+    else if (dtype == 2)
+      ikr_fma2_peak_kernel<<<blocks, threads, 0, st>>>((float*)sink, iters);
     else
       ikr_fma_peak_kernel<double><<<blocks, threads, 0, st>>>((double*)sink, iters);
     cudaEventRecord(e1, st);
@@ -599,7 +601,7 @@ int ikr_fma_peak(int32_t dtype, int64_t iters, double* tflops_out, void* cuda_st
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  double flops = 2.0 * 16.0 * (double)iters * threads * (double)blocks;
+  double flops = 2.0 * 16.0 * (double)iters * threads * (double)blocks * (dtype == 2 ? 2.0 : 1.0);
   *tflops_out = flops / (ms * 1e-3) / 1e12;
   return 0;
 }

@@ -59,6 +59,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 __device__ __forceinline__ float ikr_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// Packed FP32 pair FMA (sm_100 FFMA2): c.{lo,hi} = a.{lo,hi} * b.{lo,hi} + c.{lo,hi}, each half
+// rounded exactly like a scalar fma.rn.  ptxas folds a {x, x} pack into a scalar-broadcast
+// operand, so an outer-product update costs half the issue slots of scalar FFMA.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void f2_fma(f32x2& c, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ double ikr_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
 
 // ---------------------------------------------------------------------------------------------
@@ -237,6 +252,14 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
   const int tid = threadIdx.x;
   const int gm = tc.gm, gn = tc.gn;
   const bool worker = tc.worker;
+  // fp32: accumulate in packed pairs (acc[i][2p], acc[i][2p+1]) with FFMA2
+  f32x2 c2[kTM][4];
+  if (sizeof(W) == 4) {
+#pragma unroll
+    for (int i = 0; i < kTM; ++i)
+#pragma unroll
+      for (int pj = 0; pj < 4; ++pj) c2[i][pj] = f2_pack((float)acc[i][2 * pj], (float)acc[i][2 * pj + 1]);
+  }
   for (int c = 0; c < mv.cpl; ++c) {
     const unsigned q = pp.q;
     const unsigned stage = q % kStages;
@@ -247,19 +270,39 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
       if (worker) {
         const W* Hk = sm.Hs + (size_t)k0 * M + gm * V;
         const W* Wk = sm.Wr + (size_t)stage * mv.kc * mv.npad + gn * TN;
+        if (sizeof(W) == 4) {
+          // software-pipelined: the fragments of row kk+1 are loaded before row kk is consumed
+          // (the ring is padded by one row so the last prefetch stays inside shared memory)
+          const float* hp = reinterpret_cast<const float*>(Hk);
+          const float* wp = reinterpret_cast<const float*>(Wk);
+          const int a1_off = MG * V;
+          float4 a0 = *reinterpret_cast<const float4*>(hp);
+          float4 a1 = *reinterpret_cast<const float4*>(hp + a1_off);
+          float4 b0 = *reinterpret_cast<const float4*>(wp);
+          float4 b1 = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll 2
-        for (int kk = 0; kk < rows; ++kk) {
-          W a[kTM], b[TN];
-          if (sizeof(W) == 4) {
-            float4 a0 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M);
-            float4 a1 = *reinterpret_cast<const float4*>(Hk + (size_t)kk * M + MG * V);
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-            float4 b0 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad);
-            float4 b1 = *reinterpret_cast<const float4*>(Wk + (size_t)kk * mv.npad + 4);
-            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
-            b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
-          } else {
+          for (int kk = 0; kk < rows; ++kk) {
+            hp += M;
+            wp += mv.npad;
+            const float4 na0 = *reinterpret_cast<const float4*>(hp);
+            const float4 na1 = *reinterpret_cast<const float4*>(hp + a1_off);
+            const float4 nb0 = *reinterpret_cast<const float4*>(wp);
+            const float4 nb1 = *reinterpret_cast<const float4*>(wp + 4);
+            const float a[kTM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const f32x2 b[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y),
+                                f2_pack(b1.z, b1.w)};
+#pragma unroll
+            for (int i = 0; i < kTM; ++i) {
+              const f32x2 aa = f2_pack(a[i], a[i]);
+#pragma unroll
+              for (int pj = 0; pj < 4; ++pj) f2_fma(c2[i][pj], aa, b[pj]);
+            }
+            a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+          }
+        } else {
+#pragma unroll 2
+          for (int kk = 0; kk < rows; ++kk) {
+            W a[kTM], b[TN];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               double2 av = *reinterpret_cast<const double2*>(Hk + (size_t)kk * M + g * MG * V);
@@ -268,11 +311,11 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
             double2 b0 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad);
             double2 b1 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad + 2);
             b[0] = b0.x; b[1] = b0.y; b[TN - 2] = b1.x; b[TN - 1] = b1.y;
+#pragma unroll
+            for (int i = 0; i < kTM; ++i)
+#pragma unroll
+              for (int j = 0; j < TN; ++j) acc[i][j] = ikr_fma(a[i], b[j], acc[i][j]);
           }
-#pragma unroll
-          for (int i = 0; i < kTM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = ikr_fma(a[i], b[j], acc[i][j]);
         }
       }
       __syncwarp();
@@ -286,6 +329,16 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
       }
     }
     pp.q = q + 1;
+  }
+  if (sizeof(W) == 4) {
+#pragma unroll
+    for (int i = 0; i < kTM; ++i)
+#pragma unroll
+      for (int pj = 0; pj < 4; ++pj) {
+        float lo, hi;
+        f2_unpack(c2[i][pj], lo, hi);
+        acc[i][2 * pj] = (W)lo; acc[i][2 * pj + 1] = (W)hi;
+      }
   }
 }
 

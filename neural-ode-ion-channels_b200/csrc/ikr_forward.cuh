@@ -74,7 +74,7 @@ struct FwdSmemLayout {
     off_obs = o; o += (size_t)M * 2 * sizeof(double); o = (o + 15) & ~(size_t)15;
     off_xin = o; o += (size_t)2 * M * sizeof(W); o = (o + 127) & ~(size_t)127;
     off_hs = o; o += (size_t)npad * M * sizeof(W); o = (o + 127) & ~(size_t)127;
-    off_wr = o; o += (size_t)kStages * kc * npad * sizeof(W);
+    off_wr = o; o += ((size_t)kStages * kc + 1) * npad * sizeof(W);   // +1 row: prefetch pad
     total = o;
   }
 };
@@ -293,6 +293,23 @@ __global__ void ikr_fma_peak_kernel(W* sink, long long iters) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += a[i];
   if (s == (W)123.456) sink[0] = s;
+}
+
+// FFMA2 (packed fp32 pair) variant: counts 2 FMA per instruction
+__global__ void ikr_fma2_peak_kernel(float* sink, long long iters) {
+  f32x2 a[16];
+  const f32x2 x = f2_pack(1.0f + 1e-7f * threadIdx.x, 1.0f - 1e-7f * threadIdx.x);
+  const f32x2 y = f2_pack(1e-9f * blockIdx.x, 2e-9f * blockIdx.x);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = f2_pack((float)i, (float)-i);
+  for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(x), "l"(y));
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { float lo, hi; f2_unpack(a[i], lo, hi); s += lo + hi; }
+  if (s == 123.456f) sink[0] = s;
 }
 
 }  // namespace ikr
