@@ -404,6 +404,7 @@ def run_b200(args):
     h2d = sum(j['y0'].numel() * 4 + j['g'].numel() * 4 for j in jobs_host) + \
         sum(t.numel() * 8 for t in tgrids)
     d2h = sum(nb * 8 + nb * 16 for nb in sizes)
+    n_launch_fwd = (len(jobs_dev) + 1) * args.steps   # forward kernel + one V(t_out) kernel per job
     train = None
     if args.train_batch > 0:
         del jobs_dev, jobs_host, outs
@@ -435,7 +436,7 @@ def run_b200(args):
             },
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps},
-            'gpu_launches': (len(jobs_dev) + 1) * args.steps,
+            'gpu_launches': n_launch_fwd,
             'clocks': clocks,
             'roofline': {
                 'bound': 'fma', 'achieved': achieved, 'peak': fma_peak_tflops,

@@ -579,12 +579,21 @@ __global__ void __launch_bounds__(kWgMaxThreads, 1) ikr_wgrad_kernel(const Wgrad
       const W* Dp = ring + (size_t)st * stage_elems + o0 + og * RO;
       const W* Hp = ring + (size_t)st * stage_elems + op_elems + i0 + ig * V;
       if (sizeof(W) == 4) {
+        // software-pipelined fragment loads (the ring has one pad row behind the last stage)
+        const float* dp = reinterpret_cast<const float*>(Dp);
+        const float* hp = reinterpret_cast<const float*>(Hp);
+        float4 d0 = *reinterpret_cast<const float4*>(dp);
+        float4 d1 = *reinterpret_cast<const float4*>(dp + 4);
+        float4 h0 = *reinterpret_cast<const float4*>(hp);
+        float4 h1 = *reinterpret_cast<const float4*>(hp + half);
 #pragma unroll 2
         for (int m = 0; m < p.KC; ++m) {
-          const float4 d0 = *reinterpret_cast<const float4*>(Dp + (size_t)m * npad);
-          const float4 d1 = *reinterpret_cast<const float4*>(Dp + (size_t)m * npad + 4);
-          const float4 h0 = *reinterpret_cast<const float4*>(Hp + (size_t)m * npad);
-          const float4 h1 = *reinterpret_cast<const float4*>(Hp + (size_t)m * npad + half);
+          dp += npad;
+          hp += npad;
+          const float4 nd0 = *reinterpret_cast<const float4*>(dp);
+          const float4 nd1 = *reinterpret_cast<const float4*>(dp + 4);
+          const float4 nh0 = *reinterpret_cast<const float4*>(hp);
+          const float4 nh1 = *reinterpret_cast<const float4*>(hp + half);
           const float d[RO] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
           const f32x2 h[4] = {f2_pack(h0.x, h0.y), f2_pack(h0.z, h0.w), f2_pack(h1.x, h1.y),
                               f2_pack(h1.z, h1.w)};
@@ -595,6 +604,7 @@ __global__ void __launch_bounds__(kWgMaxThreads, 1) ikr_wgrad_kernel(const Wgrad
             for (int pc = 0; pc < 4; ++pc) f2_fma(c2[r][pc], dd, h[pc]);
             bacc[r] += (W)d[r];
           }
+          d0 = nd0; d1 = nd1; h0 = nh0; h1 = nh1;
         }
       } else {
 #pragma unroll 2

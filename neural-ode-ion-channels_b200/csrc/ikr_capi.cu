@@ -73,6 +73,17 @@ void mlp_layout(const ikr_desc* d, int* npad, int* kc, int* cpl, long long off[5
   *total = o;
 }
 
+// Relative SM throughput of the tile GEMM as a function of the worker warps per CTA (measured on
+// B200: 4 warps = 1 per scheduler reach ~43 % of the 16-warp rate; latency hiding needs >= 3 per
+// scheduler), times the balance of the warps over the four schedulers.
+double warp_throughput(int workers) {
+  const int warps = (workers + 31) / 32;
+  const int per_sched = (warps + 3) / 4;
+  static const double kRate[5] = {0.0, 0.43, 0.70, 0.88, 1.0};
+  const double rate = kRate[per_sched > 4 ? 4 : per_sched];
+  return rate * (workers / 32.0) / (4.0 * per_sched);
+}
+
 // candidate trajectory-group counts MG (tile M = 8 MG): multiples of 4 keep the quarter-warp
 // mapping bank-conflict free; 1..3 only serve tiny batches.
 const int kMgCandidates[] = {1, 2, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64};
@@ -104,10 +115,8 @@ Geometry make_geometry(const ikr_desc* d, int n_jobs, const long long* B) {
     const double waves = (double)tiles / g.sms;
     const double wave_eff = waves / (double)((tiles + g.sms - 1) / g.sms);
     const double fill = (double)b_total / ((double)tiles * M);
-    const int warps = (workers + 31) / 32;
-    const double balance = (workers / 32.0) / (4.0 * ((warps + 3) / 4));
     const double amort = (double)M / (M + 6.0);   // per-evaluation owner-phase overhead
-    const double score = wave_eff * fill * balance * amort;
+    const double score = wave_eff * fill * warp_throughput(workers) * amort;
     if (score > best_score) { best_score = score; best_mg = mg; }
   }
   g.MG = best_mg;
@@ -206,10 +215,8 @@ Geometry make_geometry_bwd(const ikr_desc* d, long long B) {
     const double waves = (double)tiles / g.sms;
     const double wave_eff = waves / (double)((tiles + g.sms - 1) / g.sms);
     const double fill = (double)B / ((double)tiles * M);
-    const int warps = (workers + 31) / 32;
-    const double balance = (workers / 32.0) / (4.0 * ((warps + 3) / 4));
     const double amort = (double)M / (M + 6.0);
-    const double score = wave_eff * fill * balance * amort;
+    const double score = wave_eff * fill * warp_throughput(workers) * amort;
     if (score > best_score) { best_score = score; best_mg = mg; }
   }
   g.MG = best_mg;
@@ -265,7 +272,7 @@ BwdPlan make_bwd_plan(const ikr_desc* d, long long B) {
   pl.wg_stages = (int)((200 * 1024) / stage);
   if (pl.wg_stages > 6) pl.wg_stages = 6;
   if (pl.wg_stages < 2) pl.wg_stages = 2;
-  pl.wg_smem = 128 + (size_t)pl.wg_stages * stage;
+  pl.wg_smem = 128 + (size_t)pl.wg_stages * stage + (size_t)g.npad * wsz;   // + prefetch pad row
 
   pl.small_stride = 4 * g.npad + 8;
   const size_t lane_save = ssz == 4 ? sizeof(BLaneSave<float>) : sizeof(BLaneSave<double>);
