@@ -329,7 +329,7 @@ def run_b200(args):
     _cabi.check(_cabi.lib().ikr_fma_peak(_cabi.F32, 200000, ctypes.byref(peak), None), 'fma_peak')
     fma_peak_tflops = peak.value
 
-    opts = {'check_status': False}
+    opts = {'check_status': False, 'lane_pool': bool(os.environ.get('IKR_LANE_POOL'))}
 
     def step_device():
         return ikr.integrate_many(func, jobs_dev, options=opts)

@@ -68,7 +68,7 @@ typedef struct ikr_desc {
   double safety, ifactor, dfactor; /* 0.9, 10, 0.2                                               */
   int64_t max_num_steps;  /* per output interval, torchdiffeq semantics                          */
   int32_t tile_m;         /* 0: library picks the trajectories-per-CTA tile                      */
-  int32_t reserved;
+  int32_t reserved;       /* bit 0: dopri5 on the lane-pool kernel (slots refill from a queue)     */
 } ikr_desc;
 
 /* One JOB = one protocol table + one batch of trajectories, i.e. the shape of one reference

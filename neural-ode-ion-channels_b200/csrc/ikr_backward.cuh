@@ -66,7 +66,7 @@ struct BwdParams {
 
 template <typename S, typename W>
 struct AdjSmemLayout {
-  size_t off_bar, off_misc, off_lanes, off_xin, off_up, off_sg, off_mask, off_hs, off_wr, total;
+  size_t off_bar, off_misc, off_lanes, off_xin, off_up, off_sg, off_sp, off_mask, off_hs, off_wr, total;
   __host__ __device__ AdjSmemLayout(int M, int npad, int kc, int L) {
     size_t o = 0;
     off_bar = o; o += 64;
@@ -75,6 +75,7 @@ struct AdjSmemLayout {
     off_xin = o; o += (size_t)2 * M * sizeof(W); o = (o + 15) & ~(size_t)15;
     off_up = o; o += (size_t)M * sizeof(W); o = (o + 15) & ~(size_t)15;
     off_sg = o; o += (size_t)(4 * npad + 8) * sizeof(double);
+    off_sp = o; o += mlp_small_elems(L, npad) * sizeof(W); o = (o + 15) & ~(size_t)15;
     off_mask = o; o += (size_t)L * npad * (M / 8); o = (o + 127) & ~(size_t)127;
     off_hs = o; o += (size_t)npad * M * sizeof(W); o = (o + 127) & ~(size_t)127;
     off_wr = o; o += ((size_t)kStages * kc + 1) * npad * sizeof(W);   // +1 row: prefetch pad
@@ -197,7 +198,7 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
 
   // ---- layer 0 forward: H_0 = leaky(w0 [nv, a] + b0) -------------------------------------------
   if (tc.worker) {
-    const W* w0 = P + mv.off_w0;
+    const W* w0 = sp_w0<W>(mv, sm);
     W nv[kTM], aa[kTM];
 #pragma unroll
     for (int i = 0; i < kTM; ++i) {
@@ -209,7 +210,7 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int col = tc.gn * TN + j;
-      W wa = __ldg(w0 + col), wb = __ldg(w0 + npad + col), bb = __ldg(w0 + 2 * npad + col);
+      W wa = w0[col], wb = w0[npad + col], bb = w0[2 * npad + col];
 #pragma unroll
       for (int i = 0; i < kTM; ++i) h[i][j] = leaky(ikr_fma(wb, aa[i], ikr_fma(wa, nv[i], bb)), slope);
     }
@@ -221,12 +222,12 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
 
   // ---- hidden layers forward -------------------------------------------------------------------
   for (int l = 1; l <= L; ++l) {
-    const W* bh = P + mv.off_bh + (long long)(l - 1) * npad + tc.gn * TN;
+    const W* bh = sp_bh<W>(mv, sm, l - 1) + tc.gn * TN;
     if (l < L) {
       mlp_layer<W>(mv, sm, pp, M, MG, tc, warp_works, [&](W (&acc)[kTM][TN]) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-          W bb = __ldg(bh + j);
+          W bb = bh[j];
 #pragma unroll
           for (int i = 0; i < kTM; ++i) acc[i][j] = leaky(acc[i][j] + bb, slope);
         }
@@ -242,10 +243,10 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
         W upv[kTM];
 #pragma unroll
         for (int i = 0; i < kTM; ++i) upv[i] = as.up[tile_row<V>(i, tc.gm, MG)];
-        const W* wl = P + mv.off_wl + tc.gn * TN;
+        const W* wl = sp_wl<W>(mv, sm) + tc.gn * TN;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-          W bb = __ldg(bh + j), wj = __ldg(wl + j);
+          W bb = bh[j], wj = wl[j];
           W s = (W)0;
 #pragma unroll
           for (int i = 0; i < kTM; ++i) {
@@ -279,16 +280,16 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
   // ---- layer 0 backward (rank-2): Hs = dz_0 ------------------------------------------------------
   W da = (W)0;
   if (tid < M) {
-    const W* w0b = P + mv.off_w0 + npad;
+    const W* w0b = sp_w0<W>(mv, sm) + npad;
     W s0 = (W)0, s1 = (W)0, s2 = (W)0, s3 = (W)0;
     int k = 0;
     for (; k + 3 < mv.n; k += 4) {
-      s0 = ikr_fma(sm.Hs[(size_t)(k + 0) * M + tid], __ldg(w0b + k + 0), s0);
-      s1 = ikr_fma(sm.Hs[(size_t)(k + 1) * M + tid], __ldg(w0b + k + 1), s1);
-      s2 = ikr_fma(sm.Hs[(size_t)(k + 2) * M + tid], __ldg(w0b + k + 2), s2);
-      s3 = ikr_fma(sm.Hs[(size_t)(k + 3) * M + tid], __ldg(w0b + k + 3), s3);
+      s0 = ikr_fma(sm.Hs[(size_t)(k + 0) * M + tid], w0b[k + 0], s0);
+      s1 = ikr_fma(sm.Hs[(size_t)(k + 1) * M + tid], w0b[k + 1], s1);
+      s2 = ikr_fma(sm.Hs[(size_t)(k + 2) * M + tid], w0b[k + 2], s2);
+      s3 = ikr_fma(sm.Hs[(size_t)(k + 3) * M + tid], w0b[k + 3], s3);
     }
-    for (; k < mv.n; ++k) s0 = ikr_fma(sm.Hs[(size_t)k * M + tid], __ldg(w0b + k), s0);
+    for (; k < mv.n; ++k) s0 = ikr_fma(sm.Hs[(size_t)k * M + tid], w0b[k], s0);
     da = (s0 + s1) + (s2 + s3);
     // d b_last = sum_m up[m]
     W u = as.up[tid];
@@ -329,12 +330,14 @@ __global__ void __launch_bounds__(512, 1) ikr_adjoint_kernel(const BwdParams p) 
   as.mlp.xin = reinterpret_cast<W*>(smem_raw + lay.off_xin);
   as.mlp.Hs = reinterpret_cast<W*>(smem_raw + lay.off_hs);
   as.mlp.Wr = reinterpret_cast<W*>(smem_raw + lay.off_wr);
+  as.mlp.sp = reinterpret_cast<W*>(smem_raw + lay.off_sp);
   as.up = reinterpret_cast<W*>(smem_raw + lay.off_up);
   as.sg = reinterpret_cast<double*>(smem_raw + lay.off_sg);
   as.mask = smem_raw + lay.off_mask;
 
   mlp_pipe_init<W>(as.mlp, p.n_worker_warps);
   for (int k = tid; k < 4 * p.mlp.npad + 8; k += blockDim.x) as.sg[k] = 0.0;
+  mlp_stage_small<W>(p.mlp, as.mlp);
   __syncthreads();
   MlpPipe pp;
   mlp_pipe_start<W>(p.mlp, as.mlp, pp);

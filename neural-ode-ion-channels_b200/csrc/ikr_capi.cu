@@ -29,12 +29,12 @@ struct Geometry {
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 template <typename S, typename W>
-size_t fwd_smem(int M, int npad, int kc) { return FwdSmemLayout<S, W>(M, npad, kc).total; }
+size_t fwd_smem(int M, int npad, int kc, int L) { return FwdSmemLayout<S, W>(M, npad, kc, L).total; }
 
 size_t fwd_smem_dyn(const ikr_desc* d, int M, int npad, int kc) {
-  if (d->state_dtype == IKR_F32) return fwd_smem<float, float>(M, npad, kc);
-  if (d->mlp_dtype == IKR_F32) return fwd_smem<double, float>(M, npad, kc);
-  return fwd_smem<double, double>(M, npad, kc);
+  if (d->state_dtype == IKR_F32) return fwd_smem<float, float>(M, npad, kc, d->n_layers);
+  if (d->mlp_dtype == IKR_F32) return fwd_smem<double, float>(M, npad, kc, d->n_layers);
+  return fwd_smem<double, double>(M, npad, kc, d->n_layers);
 }
 
 int device_sms() {
@@ -88,7 +88,7 @@ double warp_throughput(int workers) {
 // mapping bank-conflict free; 1..3 only serve tiny batches.
 const int kMgCandidates[] = {1, 2, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64};
 
-Geometry make_geometry(const ikr_desc* d, int n_jobs, const long long* B) {
+Geometry make_geometry(const ikr_desc* d, int n_jobs, const long long* B, bool pool = false) {
   Geometry g;
   long long off[5], total;
   mlp_layout(d, &g.npad, &g.kc, &g.cpl, off, &total);
@@ -112,9 +112,18 @@ Geometry make_geometry(const ikr_desc* d, int n_jobs, const long long* B) {
     }
     long long tiles = 0;
     for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + M - 1) / M;
-    const double waves = (double)tiles / g.sms;
-    const double wave_eff = waves / (double)((tiles + g.sms - 1) / g.sms);
-    const double fill = (double)b_total / ((double)tiles * M);
+    double wave_eff, fill;
+    if (pool) {
+      // lane-pool kernel: slots refill from one queue, so only an under-filled GPU costs
+      tiles = (b_total + M - 1) / M;
+      const long long ctas = tiles < g.sms ? tiles : g.sms;
+      wave_eff = (double)ctas / g.sms;
+      fill = b_total >= ctas * (long long)M ? 1.0 : (double)b_total / ((double)ctas * M);
+    } else {
+      const double waves = (double)tiles / g.sms;
+      wave_eff = waves / (double)((tiles + g.sms - 1) / g.sms);
+      fill = (double)b_total / ((double)tiles * M);
+    }
     const double amort = (double)M / (M + 6.0);   // per-evaluation owner-phase overhead
     const double score = wave_eff * fill * warp_throughput(workers) * amort;
     if (score > best_score) { best_score = score; best_mg = mg; }
@@ -125,7 +134,8 @@ Geometry make_geometry(const ikr_desc* d, int n_jobs, const long long* B) {
   g.n_worker_warps = (workers + 31) / 32;
   g.threads = round_up(workers > g.M ? workers : g.M, 32);
   g.n_tiles = 0;
-  for (int j = 0; j < n_jobs; ++j) g.n_tiles += (B[j] + g.M - 1) / g.M;
+  if (pool) g.n_tiles = (b_total + g.M - 1) / g.M;
+  else for (int j = 0; j < n_jobs; ++j) g.n_tiles += (B[j] + g.M - 1) / g.M;
   g.grid = (int)(g.n_tiles < g.sms ? g.n_tiles : g.sms);
   if (g.grid < 1) g.grid = 1;
   g.smem = fwd_smem_dyn(d, g.M, g.npad, g.kc);
@@ -166,9 +176,15 @@ SolverCfg make_cfg(const ikr_desc* d) {
   return c;
 }
 
+// dopri5 runs tile-scheduled by default; desc.reserved bit 0 selects the lane-pool kernel (slots
+// refill from one trajectory queue).  Measured on B200 (profiles/r1_forward_v3_summary.md): the
+// pool wins when one long job has many more trajectories than lane slots (+3.5 % at 65,536 x pr4)
+// and loses ~3 % on the five-protocol bench mix, so it is opt-in.  rk4 is always tile-scheduled.
+bool use_pool(const ikr_desc* d) { return d->method == IKR_DOPRI5 && (d->reserved & 1); }
+
 template <typename S, typename W>
-int launch_forward(const FwdParams& p, const Geometry& g, cudaStream_t st) {
-  auto kern = ikr_forward_kernel<S, W>;
+int launch_forward(const FwdParams& p, const Geometry& g, cudaStream_t st, bool pool) {
+  auto kern = pool ? ikr_forward_pool_kernel<S, W> : ikr_forward_kernel<S, W>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) !=
       cudaSuccess) {
     cudaGetLastError();
@@ -464,13 +480,13 @@ int64_t ikr_param_count(const ikr_desc* d) {
 int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B) {
   if (!valid_desc(d) || n_jobs < 1 || !B) return IKR_ERR_ARG;
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
-  return make_geometry(d, n_jobs, (const long long*)B).M;
+  return make_geometry(d, n_jobs, (const long long*)B, use_pool(d)).M;
 }
 
 int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[8]) {
   if (!valid_desc(d) || n_jobs < 1 || !B || !out) return IKR_ERR_ARG;
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
-  Geometry g = make_geometry(d, n_jobs, (const long long*)B);
+  Geometry g = make_geometry(d, n_jobs, (const long long*)B, use_pool(d));
   out[0] = g.M; out[1] = g.threads; out[2] = g.grid; out[3] = (int64_t)g.smem;
   out[4] = g.n_tiles; out[5] = g.kc; out[6] = g.cpl; out[7] = g.sms;
   return 0;
@@ -513,14 +529,17 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
   });
   std::vector<long long> Bs(n_jobs);
   for (int j = 0; j < n_jobs; ++j) Bs[j] = jobs[order[j]].B;
-  Geometry g = make_geometry(d, n_jobs, Bs.data());
+  const bool pool = use_pool(d);
+  Geometry g = make_geometry(d, n_jobs, Bs.data(), pool);
   if (g.smem > kSmemLimit || g.threads > kMaxThreads) return IKR_ERR_UNSUPPORTED;
 
   std::vector<FwdJob> table(n_jobs);
-  long long tile = 0;
+  long long tile = 0, traj = 0;
   for (int j = 0; j < n_jobs; ++j) {
     const ikr_io* io = &jobs[order[j]];
     FwdJob& fj = table[j];
+    fj.traj_begin = traj;
+    traj += io->B;
     fj.tab = make_table(io);
     fj.B = io->B; fj.T = (int)io->T; fj.G = (int)io->G;
     fj.tile_begin = tile;
@@ -551,12 +570,15 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
   p.n_worker_warps = g.n_worker_warps;
   p.n_jobs = n_jobs;
   p.n_tiles = g.n_tiles;
+  p.n_traj = traj;
+  p.jobs_are_inline = n_jobs <= kInlineJobs ? 1 : 0;
+  for (int j = 0; j < kInlineJobs; ++j) p.jobs_inline[j] = table[j < n_jobs ? j : 0];
   p.jobs = reinterpret_cast<const FwdJob*>(ws + 256);
   p.queue = reinterpret_cast<unsigned long long*>(ws);
 
-  if (d->state_dtype == IKR_F32) return launch_forward<float, float>(p, g, st);
-  if (d->mlp_dtype == IKR_F32) return launch_forward<double, float>(p, g, st);
-  return launch_forward<double, double>(p, g, st);
+  if (d->state_dtype == IKR_F32) return launch_forward<float, float>(p, g, st, pool);
+  if (d->mlp_dtype == IKR_F32) return launch_forward<double, float>(p, g, st, pool);
+  return launch_forward<double, double>(p, g, st, pool);
 }
 
 int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, void* workspace,

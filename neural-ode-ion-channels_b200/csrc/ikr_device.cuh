@@ -115,6 +115,7 @@ struct MlpSmem {
   W* xin;          // [2][M]   MLP inputs (nv, a)
   W* Hs;           // [npad][M] activations, feature-major
   W* Wr;           // [kStages][kc][npad] weight-chunk ring
+  W* sp;           // small parameters staged once per CTA: w0a | w0b | b0 | L x b_hidden | w_last | b_last
   uint64_t* full;   // [kStages] chunk landed (TMA complete_tx)
   uint64_t* empty;  // [kStages] every worker warp is done reading the chunk
 };
@@ -179,6 +180,27 @@ __device__ __forceinline__ void mlp_pipe_drain(const MlpView& mv, const MlpSmem<
   if (threadIdx.x == 0) {
     for (unsigned q = pp.q; q < pp.issued; ++q) mbar_wait(&sm.full[q % kStages], (q / kStages) & 1);
   }
+}
+
+// number of elements of the small-parameter block ((3 + L + 1) npad + 8)
+__host__ __device__ inline size_t mlp_small_elems(int L, int npad) { return (size_t)(4 + L) * npad + 8; }
+// cooperative copy global -> shared (call once, follow with __syncthreads())
+template <typename W>
+__device__ __forceinline__ void mlp_stage_small(const MlpView& mv, const MlpSmem<W>& sm) {
+  const W* P = (const W*)mv.base;
+  const int n0 = 3 * mv.npad, n1 = (mv.L + 1) * mv.npad + 8;
+  for (int i = threadIdx.x; i < n0; i += blockDim.x) sm.sp[i] = P[mv.off_w0 + i];
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) sm.sp[n0 + i] = P[mv.off_bh + i];
+}
+template <typename W>
+__device__ __forceinline__ const W* sp_w0(const MlpView& mv, const MlpSmem<W>& sm) { return sm.sp; }
+template <typename W>
+__device__ __forceinline__ const W* sp_bh(const MlpView& mv, const MlpSmem<W>& sm, int layer) {
+  return sm.sp + (size_t)(3 + layer) * mv.npad;
+}
+template <typename W>
+__device__ __forceinline__ const W* sp_wl(const MlpView& mv, const MlpSmem<W>& sm) {
+  return sm.sp + (size_t)(3 + mv.L) * mv.npad;
 }
 
 template <typename W>
@@ -370,10 +392,10 @@ __device__ __forceinline__ void mlp_tile_hidden(const MlpView& mv, const MlpSmem
     __syncthreads();  // all reads of this layer's input activations are done
 
     if (worker) {
-      const W* bh = P + mv.off_bh + (long long)layer * mv.npad + gn * TN;
+      const W* bh = sp_bh<W>(mv, sm, layer) + gn * TN;
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
-        W bb = __ldg(bh + j);
+        W bb = bh[j];
         W* dst = sm.Hs + (size_t)(gn * TN + j) * M + gm * V;
         if (sizeof(W) == 4) {
           float4 o0, o1;
@@ -415,7 +437,7 @@ __device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W
 
   // ---- layer 0: Linear(2, n) + LeakyReLU ----------------------------------------------------
   if (tc.worker) {
-    const W* w0 = P + mv.off_w0;
+    const W* w0 = sp_w0<W>(mv, sm);
     W nv[kTM], aa[kTM];
 #pragma unroll
     for (int i = 0; i < kTM; ++i) {
@@ -426,7 +448,7 @@ __device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int col = tc.gn * TN + j;
-      W wa = __ldg(w0 + col), wb = __ldg(w0 + mv.npad + col), bb = __ldg(w0 + 2 * mv.npad + col);
+      W wa = w0[col], wb = w0[mv.npad + col], bb = w0[2 * mv.npad + col];
 #pragma unroll
       for (int i = 0; i < kTM; ++i) {
         W z = ikr_fma(wb, aa[i], ikr_fma(wa, nv[i], bb));
@@ -441,17 +463,17 @@ __device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W
   // ---- output layer: Linear(n, 1), one owner thread per trajectory ---------------------------
   W out = (W)0;
   if (tid < M) {
-    const W* wl = P + mv.off_wl;
+    const W* wl = sp_wl<W>(mv, sm);
     W s0 = (W)0, s1 = (W)0, s2 = (W)0, s3 = (W)0;
     int k = 0;
     for (; k + 3 < mv.n; k += 4) {
-      s0 = ikr_fma(sm.Hs[(size_t)(k + 0) * M + tid], __ldg(wl + k + 0), s0);
-      s1 = ikr_fma(sm.Hs[(size_t)(k + 1) * M + tid], __ldg(wl + k + 1), s1);
-      s2 = ikr_fma(sm.Hs[(size_t)(k + 2) * M + tid], __ldg(wl + k + 2), s2);
-      s3 = ikr_fma(sm.Hs[(size_t)(k + 3) * M + tid], __ldg(wl + k + 3), s3);
+      s0 = ikr_fma(sm.Hs[(size_t)(k + 0) * M + tid], wl[k + 0], s0);
+      s1 = ikr_fma(sm.Hs[(size_t)(k + 1) * M + tid], wl[k + 1], s1);
+      s2 = ikr_fma(sm.Hs[(size_t)(k + 2) * M + tid], wl[k + 2], s2);
+      s3 = ikr_fma(sm.Hs[(size_t)(k + 3) * M + tid], wl[k + 3], s3);
     }
-    for (; k < mv.n; ++k) s0 = ikr_fma(sm.Hs[(size_t)k * M + tid], __ldg(wl + k), s0);
-    out = ((s0 + s1) + (s2 + s3)) + __ldg(wl + mv.npad);
+    for (; k < mv.n; ++k) s0 = ikr_fma(sm.Hs[(size_t)k * M + tid], wl[k], s0);
+    out = ((s0 + s1) + (s2 + s3)) + wl[mv.npad];
   }
   return out;
 }

@@ -21,7 +21,8 @@ struct FwdJob {
   long long B;
   int T;
   int G;
-  long long tile_begin;  // first global tile index of this job
+  long long tile_begin;  // first global tile index of this job (tile-scheduled kernel)
+  long long traj_begin;  // first global trajectory index of this job (lane-pool kernel)
   const void* y0;
   const double* t_out;
   const double* grid;
@@ -40,6 +41,8 @@ struct FwdJob {
   void* ckpt_y;
 };
 
+constexpr int kInlineJobs = 8;   // job descriptors carried in the kernel parameters (constant bank)
+
 struct FwdParams {
   MlpView mlp;
   SolverCfg cfg;     // cfg.tab is overwritten per job
@@ -50,7 +53,10 @@ struct FwdParams {
   int n_worker_warps;
   int n_jobs;
   long long n_tiles;
+  long long n_traj;          // trajectories of all jobs (lane-pool kernel)
   const FwdJob* jobs;        // device array [n_jobs]
+  int jobs_are_inline;       // n_jobs <= kInlineJobs: read jobs_inline (no L2 hot spot)
+  FwdJob jobs_inline[kInlineJobs];
   unsigned long long* queue; // device tile counter (zeroed by the host before launch)
 };
 
@@ -64,15 +70,17 @@ struct Vec2<double> { typedef double2 type; };
 // shared memory carve-up (host and device agree through this one function)
 template <typename S, typename W>
 struct FwdSmemLayout {
-  size_t off_lanes, off_obs, off_xin, off_hs, off_wr, off_bar, off_job, off_tile, total;
-  __host__ __device__ FwdSmemLayout(int M, int npad, int kc) {
+  size_t off_lanes, off_obs, off_aux, off_xin, off_sp, off_hs, off_wr, off_bar, off_job, off_tile, total;
+  __host__ __device__ FwdSmemLayout(int M, int npad, int kc, int L) {
     size_t o = 0;
     off_bar = o; o += 64;
     off_job = o; o += (sizeof(FwdJob) + 15) & ~(size_t)15;
     off_tile = o; o += 16;
     off_lanes = o; o += (size_t)M * sizeof(Lane<S>); o = (o + 15) & ~(size_t)15;
     off_obs = o; o += (size_t)M * 2 * sizeof(double); o = (o + 15) & ~(size_t)15;
-    off_xin = o; o += (size_t)2 * M * sizeof(W); o = (o + 127) & ~(size_t)127;
+    off_aux = o; o += (size_t)M * 32; o = (o + 15) & ~(size_t)15;   // LaneAux (lane-pool kernel)
+    off_xin = o; o += (size_t)2 * M * sizeof(W); o = (o + 15) & ~(size_t)15;
+    off_sp = o; o += mlp_small_elems(L, npad) * sizeof(W); o = (o + 127) & ~(size_t)127;
     off_hs = o; o += (size_t)npad * M * sizeof(W); o = (o + 127) & ~(size_t)127;
     off_wr = o; o += ((size_t)kStages * kc + 1) * npad * sizeof(W);   // +1 row: prefetch pad
     total = o;
@@ -84,7 +92,7 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int M = p.M;
-  const FwdSmemLayout<S, W> lay(M, p.mlp.npad, p.mlp.kc);
+  const FwdSmemLayout<S, W> lay(M, p.mlp.npad, p.mlp.kc, p.mlp.L);
   Lane<S>* lanes = reinterpret_cast<Lane<S>*>(smem_raw + lay.off_lanes);
   double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);  // [M][2] sse, sae
   FwdJob* jobp = reinterpret_cast<FwdJob*>(smem_raw + lay.off_job);
@@ -95,8 +103,10 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
   sm.xin = reinterpret_cast<W*>(smem_raw + lay.off_xin);
   sm.Hs = reinterpret_cast<W*>(smem_raw + lay.off_hs);
   sm.Wr = reinterpret_cast<W*>(smem_raw + lay.off_wr);
+  sm.sp = reinterpret_cast<W*>(smem_raw + lay.off_sp);
 
   mlp_pipe_init<W>(sm, p.n_worker_warps);
+  mlp_stage_small<W>(p.mlp, sm);
   __syncthreads();
   MlpPipe pp;
   mlp_pipe_start<W>(p.mlp, sm, pp);
@@ -262,6 +272,220 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
       }
     }
     __syncthreads();  // lanes[] / job slot are re-initialised by the next tile
+  }
+  mlp_pipe_drain<W>(p.mlp, sm, pp);
+}
+
+
+// =============================================================================================
+// Lane-pool forward kernel (dopri5).  Every CTA owns M lane SLOTS; a slot whose trajectory has
+// finished pulls the next trajectory -- of whatever job -- from one global queue (jobs longest
+// first), so no slot idles while its neighbours finish and there is no tile/wave quantisation:
+// the only tail is the very end of the launch.  Lanes stay in lock-step by ROUND of six RHS
+// evaluations: a lane either attempts one dopri5 step (6 stages) or, right after a refill, runs
+// its two start-up evaluations f(t0, y0) and the initial-step probe (then idles 4 slots of ~10^3).
+// Results are identical to the tile-scheduled kernel: every lane's arithmetic is independent of
+// its slot and of its neighbours.
+// =============================================================================================
+// Job descriptor j.  Every lane reads its job every evaluation: from the kernel parameters
+// (constant cache) when they fit, else from global memory (all SMs then hammer the same L2 lines).
+__device__ __forceinline__ FwdJob load_job(const FwdParams& p, int j) {
+  if (p.jobs_are_inline) return p.jobs_inline[j];
+  return p.jobs[j];
+}
+__device__ __forceinline__ long long job_traj_begin(const FwdParams& p, int j) {
+  return p.jobs_are_inline ? p.jobs_inline[j].traj_begin : p.jobs[j].traj_begin;
+}
+
+template <typename S>
+struct LaneAux {
+  long long b;    // trajectory index inside its job
+  int job;
+  int mode;       // 0 empty, 1 start-up pending, 2 stepping
+  S g, e;
+};
+enum { POOL_EMPTY = 0, POOL_INIT = 1, POOL_STEP = 2 };
+
+template <typename S, typename W>
+__global__ void __launch_bounds__(512, 1) ikr_forward_pool_kernel(const FwdParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int M = p.M;
+  const FwdSmemLayout<S, W> lay(M, p.mlp.npad, p.mlp.kc, p.mlp.L);
+  Lane<S>* lanes = reinterpret_cast<Lane<S>*>(smem_raw + lay.off_lanes);
+  double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);  // [M][2] sse, sae
+  LaneAux<S>* aux = reinterpret_cast<LaneAux<S>*>(smem_raw + lay.off_aux);
+  MlpSmem<W> sm;
+  sm.full = reinterpret_cast<uint64_t*>(smem_raw + lay.off_bar);
+  sm.empty = sm.full + kStages;
+  sm.xin = reinterpret_cast<W*>(smem_raw + lay.off_xin);
+  sm.Hs = reinterpret_cast<W*>(smem_raw + lay.off_hs);
+  sm.Wr = reinterpret_cast<W*>(smem_raw + lay.off_wr);
+  sm.sp = reinterpret_cast<W*>(smem_raw + lay.off_sp);
+
+  mlp_pipe_init<W>(sm, p.n_worker_warps);
+  mlp_stage_small<W>(p.mlp, sm);
+  __syncthreads();
+  MlpPipe pp;
+  mlp_pipe_start<W>(p.mlp, sm, pp);
+
+  const bool owner = tid < M;
+  const bool heuristic = !(p.cfg.first_step > 0);
+  if (owner) {
+    lane_reset<S>(lanes[tid], (S)0, (S)1, 0.0, false);
+    aux[tid].mode = POOL_EMPTY; aux[tid].job = 0; aux[tid].b = 0;
+    aux[tid].g = (S)1; aux[tid].e = (S)0;
+  }
+  bool queue_dry = false;
+
+  while (true) {
+    // ---- round boundary: retire finished trajectories, refill free slots -----------------------
+    int act = 0;
+    if (owner) {
+      Lane<S>& L = lanes[tid];
+      LaneAux<S>& A = aux[tid];
+      if (A.mode == POOL_STEP) {
+        SolverCfg c = p.cfg;
+        dp_check_before_step<S>(L, c);
+      }
+      if (A.mode != POOL_EMPTY && !lane_active(L)) {
+        const FwdJob job = load_job(p, A.job);
+        int* st = job.stats_out + 4 * A.b;
+        st[0] = L.n_acc; st[1] = L.n_rej; st[2] = L.nfe;
+        st[3] = L.status == LANE_DONE ? 0 : L.status;
+        if (job.loss_out) {
+          job.loss_out[2 * A.b] = obs[2 * tid];
+          job.loss_out[2 * A.b + 1] = obs[2 * tid + 1];
+        }
+        A.mode = POOL_EMPTY;
+      }
+      if (A.mode == POOL_EMPTY && !queue_dry) {
+        const long long gidx = (long long)atomicAdd(p.queue, 1ULL);
+        if (gidx < p.n_traj) {
+          int j = 0;
+          while (j + 1 < p.n_jobs && job_traj_begin(p, j + 1) <= gidx) ++j;
+          const FwdJob job = load_job(p, j);
+          const long long b = gidx - job.traj_begin;
+          const S* y0 = reinterpret_cast<const S*>(job.y0);
+          A.job = j; A.b = b; A.mode = POOL_INIT;
+          A.g = job.g ? reinterpret_cast<const S*>(job.g)[b] : (S)1;
+          A.e = job.e_rev ? reinterpret_cast<const S*>(job.e_rev)[b] : (S)job.e_scalar;
+          lane_reset<S>(L, y0[2 * b], y0[2 * b + 1], job.t_out[0], true);
+          obs[2 * tid] = 0.0; obs[2 * tid + 1] = 0.0;
+        } else {
+          queue_dry = true;
+        }
+      }
+      act = A.mode != POOL_EMPTY ? 1 : 0;
+    }
+    if (!__syncthreads_or(act)) break;
+
+    // ---- one round = six RHS evaluations --------------------------------------------------------
+#pragma unroll 1
+    for (int s = 0; s < 6; ++s) {
+      int what = 0;   // 0 masked, 1 dopri5 stage, 2 f0, 3 initial-step probe
+      if (owner) {
+        Lane<S>& L = lanes[tid];
+        const LaneAux<S>& A = aux[tid];
+        double nv = 0, ain = 0;
+        if (A.mode == POOL_STEP) what = 1;
+        else if (A.mode == POOL_INIT && s == 0) what = 2;
+        else if (A.mode == POOL_INIT && s == 1 && heuristic) what = 3;
+        if (what) {
+          SolverCfg c = p.cfg;
+          c.tab = load_job(p, A.job).tab;
+          if (what == 1) dp_prepare_stage<S>(L, c, s, &nv, &ain);
+          else if (what == 2) init_prepare_f0<S>(L, c, &nv, &ain);
+          else init_prepare_f1<S>(L, c, &nv, &ain);
+        }
+        sm.xin[tid] = (W)nv; sm.xin[M + tid] = (W)ain;
+      }
+      const W out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+      if (what) {
+        Lane<S>& L = lanes[tid];
+        SolverCfg c = p.cfg;
+        if (what == 1) dp_store_stage<S>(L, c, s, (double)out);
+        else if (what == 2) {
+          init_store_f0<S>(L, c, (double)out);
+          if (!heuristic) L.dt = c.first_step;
+        } else init_store_f1<S>(L, c, (double)out);
+      }
+    }
+
+    // ---- end of round: finish the attempted step / leave start-up ---------------------------------
+    if (owner) {
+      Lane<S>& L = lanes[tid];
+      LaneAux<S>& A = aux[tid];
+      if (A.mode == POOL_STEP) {
+        const FwdJob job = load_job(p, A.job);
+        const long long jB = job.B, b = A.b;
+        S* y_out = reinterpret_cast<S*>(job.y_out);
+        S* i_out = reinterpret_cast<S*>(job.i_out);
+        S* ckpt_y = reinterpret_cast<S*>(job.ckpt_y);
+        const S* dptr = reinterpret_cast<const S*>(job.data);
+        const bool observe = (job.v_out != nullptr) && (job.i_out != nullptr || job.loss_out != nullptr);
+        const S g_b = A.g, e_b = A.e;
+        auto emit = [&](int idx, S a, S r) {
+          if (y_out) {
+            typename Vec2<S>::type v;
+            v.x = a; v.y = r;
+            *reinterpret_cast<typename Vec2<S>::type*>(y_out + ((size_t)idx * jB + b) * 2) = v;
+          }
+          if (observe) {
+            double cur = (double)(g_b * a * r) * (job.v_out[idx] - (double)e_b);
+            if (i_out) i_out[(size_t)idx * jB + b] = (S)cur;
+            if (dptr) {
+              double d = (double)dptr[(size_t)idx * job.data_B + (job.data_B == 1 ? 0 : b)];
+              double diff = cur - d;
+              obs[2 * tid] += diff * diff;
+              obs[2 * tid + 1] += fabs(diff);
+            }
+          }
+        };
+        auto ckpt = [&](int step, const Lane<S>& lane) -> bool {
+          if (!job.ckpt_t) return true;
+          if (step >= job.ckpt_cap) return false;
+          size_t o = (size_t)step * jB + b;
+          double2 tt;
+          tt.x = lane.t0; tt.y = lane.dt;
+          *reinterpret_cast<double2*>(job.ckpt_t + 2 * o) = tt;
+          S buf[kCkptVals];
+          ckpt_pack<S>(lane, buf);
+          typedef typename Vec2<S>::type V2;
+          V2* dst = reinterpret_cast<V2*>(ckpt_y + (size_t)kCkptVals * o);
+#pragma unroll
+          for (int i = 0; i < kCkptVals / 2; ++i) {
+            V2 v;
+            v.x = buf[2 * i]; v.y = buf[2 * i + 1];
+            dst[i] = v;
+          }
+          return true;
+        };
+        SolverCfg c = p.cfg;
+        dp_finish_step<S>(L, c, job.t_out, job.T, emit, ckpt);
+      } else if (A.mode == POOL_INIT) {
+        // start-up done: emit y(t[0]) = y0 and start stepping (or finish if there is one output)
+        const FwdJob job = load_job(p, A.job);
+        const long long b = A.b;
+        if (job.y_out) {
+          typename Vec2<S>::type v;
+          v.x = L.ya; v.y = L.yr;
+          reinterpret_cast<typename Vec2<S>::type*>(job.y_out)[b] = v;
+        }
+        if (job.v_out && (job.i_out || job.loss_out)) {
+          double cur = (double)(A.g * L.ya * L.yr) * (job.v_out[0] - (double)A.e);
+          if (job.i_out) reinterpret_cast<S*>(job.i_out)[b] = (S)cur;
+          if (job.data) {
+            const S* dptr = reinterpret_cast<const S*>(job.data);
+            double diff = cur - (double)dptr[job.data_B == 1 ? 0 : b];
+            obs[2 * tid] += diff * diff;
+            obs[2 * tid + 1] += fabs(diff);
+          }
+        }
+        A.mode = POOL_STEP;
+        if (job.T <= 1 && lane_active(L)) L.status = LANE_DONE;
+      }
+    }
   }
   mlp_pipe_drain<W>(p.mlp, sm, pp);
 }

@@ -411,3 +411,33 @@ def test_integrate_many_equals_separate_calls():
     for a, b in zip(many, singles):
         assert torch.equal(a.y, b.y) and torch.equal(a.current, b.current)
         assert torch.equal(a.stats, b.stats) and torch.equal(a.sae, b.sae)
+
+
+def test_lane_pool_kernel_equals_tile_scheduled_kernel():
+    """The opt-in lane-pool kernel (slots refill from one trajectory queue, jobs mixed inside a
+    CTA) must reproduce the tile-scheduled kernel bit for bit: a lane's arithmetic does not depend
+    on its slot or its neighbours."""
+    func, _ = _nn('d1')
+    rng = np.random.RandomState(11)
+    jobs = []
+    for k, (tt, vv, T) in enumerate([(*protocols.ap2hz(), 101), (*protocols.pr3_activation(20), 81),
+                                     (*protocols.pr5_deactivation(-60), 41)]):
+        B = (37, 200, 5)[k]
+        y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1),
+                          dtype=torch.float32).cuda()
+        t = torch.linspace(0., 2. * (T - 1), T)
+        g = torch.tensor(rng.lognormal(0, 0.2, B), dtype=torch.float32)
+        jobs.append(dict(protocol=(tt, vv), y0=y0, t=t, g=g, data=torch.zeros(T),
+                         want_current=True, want_ckpt=True))
+    a = ikr.integrate_many(func, jobs, options={'tile_m': 32})
+    b = ikr.integrate_many(func, jobs, options={'tile_m': 32, 'lane_pool': True})
+    for ra, rb in zip(a, b):
+        assert torch.equal(ra.stats, rb.stats)
+        assert torch.equal(ra.y, rb.y) and torch.equal(ra.current, rb.current)
+        assert torch.equal(ra.sse, rb.sse) and torch.equal(ra.sae, rb.sae)
+        n = int(ra.stats[:, 0].max())
+        assert torch.equal(ra.ckpt[0][:1], rb.ckpt[0][:1])
+        for bb in range(ra.stats.shape[0]):
+            k = int(ra.stats[bb, 0])
+            assert torch.equal(ra.ckpt[1][:k, bb], rb.ckpt[1][:k, bb])
+        assert n > 0
