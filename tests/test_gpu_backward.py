@@ -203,3 +203,51 @@ def test_gradient_fp64_architectures(arch):
     want, _, _ = _oracle_grads(ofunc, y0, t, _steps(res), 0.05,
                                lambda b, yb: (yb * w[:, b, :]).sum())
     assert np.abs(got - want).max() <= 1e-8 * np.abs(want).max()
+
+
+def test_gradient_is_additive_over_batch_shards():
+    """Multi-GPU contract checked on one device: the gradient of the whole batch equals
+    the sum of the gradients of its shards (what the flat all-reduce adds up), and so does the
+    loss -- independent of how `parallel.shard_bounds` cuts the batch."""
+    from neural_ode_ion_channels_b200 import parallel
+    func, _, t = _setup('d2', True, t_end=30., n_out=16)
+    B = 13
+    rng = np.random.RandomState(9)
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.9, 1, B)], 1))
+    g = torch.tensor(rng.lognormal(0, 0.2, B))
+    data = torch.from_numpy(rng.randn(len(t), B) * 0.1)
+    func.cuda()
+    opts = {'first_step': 0.05}
+    total, _, grads, _ = ikr.loss_and_grad(func, y0.cuda(), t, data, g=g, options=opts)
+    whole = _flat(grads)
+    for world in (2, 4):
+        acc, loss = np.zeros_like(whole), 0.0
+        for rank in range(world):
+            lo, hi = parallel.shard_bounds(B, world, rank)
+            tl, _, gr, _ = ikr.loss_and_grad(func, y0[lo:hi].cuda(), t, data[:, lo:hi], g=g[lo:hi],
+                                             options=opts)
+            acc += _flat(gr)
+            loss += float(tl)
+        assert np.abs(acc - whole).max() <= 1e-10 * np.abs(whole).max()
+        assert abs(loss - float(total)) <= 1e-12 * abs(float(total))
+
+
+def test_full_size_training_batch_4096_properties():
+    """BASELINE configs[2] size (4,096 datasets) on a short window: statuses ok, gradient finite,
+    and equal to 16 x the gradient of the 256 distinct datasets it is made of (fp32 as shipped,
+    so equality up to fp32 / summation-order noise)."""
+    func, _, t = _setup('d2', False, t_end=40., n_out=21)
+    rng = np.random.RandomState(10)
+    y0s = np.stack([rng.uniform(0, 0.05, 256), rng.uniform(0.9, 1, 256)], 1).astype(np.float32)
+    ds = (rng.randn(len(t), 256) * 0.1).astype(np.float32)
+    idx = rng.permutation(np.arange(4096) % 256)
+    func.cuda()
+    tot_b, per_b, g_b, res_b = ikr.loss_and_grad(func, torch.from_numpy(y0s[idx]).cuda(), t,
+                                                 torch.from_numpy(ds[:, idx]))
+    tot_s, per_s, g_s, res_s = ikr.loss_and_grad(func, torch.from_numpy(y0s).cuda(), t,
+                                                 torch.from_numpy(ds))
+    assert int((res_b.stats[:, 3] != 0).sum()) == 0
+    assert torch.equal(per_b, per_s[torch.from_numpy(idx).cuda()])
+    fb, fs = _flat(g_b), _flat(g_s)
+    assert np.isfinite(fb).all()
+    assert np.abs(fb - 16 * fs).max() <= 1e-4 * np.abs(fb).max()

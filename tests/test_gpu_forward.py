@@ -441,3 +441,49 @@ def test_lane_pool_kernel_equals_tile_scheduled_kernel():
             k = int(ra.stats[bb, 0])
             assert torch.equal(ra.ckpt[1][:k, bb], rb.ckpt[1][:k, bb])
         assert n > 0
+
+
+@pytest.mark.parametrize('B', [65536, 1048576])
+def test_full_size_ensembles_duplicate_invariance(B):
+    """BASELINE configs[1] / configs[4] sizes (65,536 and 1M trajectories): 256 distinct (y0, g)
+    instances, each repeated B/256 times in shuffled positions.  Size-independent properties:
+    every copy of an instance gives bit-identical results wherever it sits (tile / CTA / slot
+    invariance), all statuses are ok, and the distinct instances match a separate B=256 launch."""
+    func, _ = _nn('d1')
+    t_tab, v_tab = protocols.pr3_activation(20)
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    rng = np.random.RandomState(12)
+    base_y0 = np.stack([rng.uniform(0, 0.05, 256), rng.uniform(0.95, 1, 256)], 1).astype(np.float32)
+    base_g = rng.lognormal(0, 0.2, 256).astype(np.float32)
+    idx = rng.permutation(np.arange(B) % 256)
+    t = torch.linspace(0., 120., 13)
+    data = torch.zeros(13)
+    big = ikr.integrate(func, torch.from_numpy(base_y0[idx]).cuda(), t, g=torch.from_numpy(base_g[idx]),
+                        data=data, want_y=False, want_current=False)
+    small = ikr.integrate(func, torch.from_numpy(base_y0).cuda(), t, g=torch.from_numpy(base_g),
+                          data=data, want_y=False, want_current=False, options={'tile_m': 32})
+    assert int((big.stats[:, 3] != 0).sum()) == 0
+    idx_d = torch.from_numpy(idx).cuda()
+    assert torch.equal(big.stats, small.stats[idx_d])
+    assert torch.equal(big.sse, small.sse[idx_d]) and torch.equal(big.sae, small.sae[idx_d])
+
+
+def test_architecture_sweep_s00_to_s11_fp32_and_fp64():
+    """BASELINE configs[3]: every architectures/sNN.py net integrates (dopri5) in fp32 and in fp64
+    with finite results and ok status; fp64 results agree with fp32 at the fp32 noise level."""
+    t_tab, v_tab = protocols.pr5_deactivation(-60)
+    y0 = torch.tensor([[0.02, 0.97], [0.4, 0.6], [0.0, 1.0]])
+    t = torch.linspace(0., 60., 16)
+    for arch in sorted(ikr.ARCHITECTURES):
+        torch.manual_seed(0)
+        f32 = ikr.ODEFuncNNf(arch=arch, params='r', std=0.05)
+        f32.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        r32 = ikr.integrate(f32, y0.cuda(), t)
+        f64 = ikr.ODEFuncNNf(arch=arch, params='r', std=0.05).double()
+        f64.net.load_state_dict({k: v.double() for k, v in f32.net.state_dict().items()})
+        f64.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        r64 = ikr.integrate(f64, y0.double().cuda(), t.double())
+        for r in (r32, r64):
+            assert int((r.stats[:, 3] != 0).sum()) == 0, arch
+            assert bool(torch.isfinite(r.y).all()), arch
+        assert (r32.y.double() - r64.y).abs().max().item() < 5e-4, arch
