@@ -92,10 +92,9 @@ struct AdjSmem {
 };
 
 // ---- register tile <-> memory ------------------------------------------------------------------
-template <typename W>
+template <typename W, int TN>
 __device__ __forceinline__ void tile_store_smem(W* Hs, int M, int MG, const TileCoord& tc,
-                                                const W (&v)[kTM][MlpTileCfg<W>::TN]) {
-  constexpr int TN = MlpTileCfg<W>::TN;
+                                                const W (&v)[kTM][TN]) {
   constexpr int V = MlpTileCfg<W>::V;
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
@@ -118,33 +117,31 @@ __device__ __forceinline__ void tile_store_smem(W* Hs, int M, int MG, const Tile
 }
 
 // stash block layout [M][npad] (lane-major, so that the weight-gradient GEMM streams K-major rows)
-template <typename W>
+template <typename W, int TN>
 __device__ __forceinline__ void tile_store_stash(W* dst, int npad, int MG, const TileCoord& tc,
-                                                 const W (&v)[kTM][MlpTileCfg<W>::TN]) {
-  constexpr int TN = MlpTileCfg<W>::TN;
+                                                 const W (&v)[kTM][TN]) {
   constexpr int V = MlpTileCfg<W>::V;
 #pragma unroll
   for (int i = 0; i < kTM; ++i) {
     W* p = dst + (size_t)tile_row<V>(i, tc.gm, MG) * npad + tc.gn * TN;
-    if (sizeof(W) == 4) {
-      float4 o0, o1;
-      o0.x = v[i][0]; o0.y = v[i][1]; o0.z = v[i][2]; o0.w = v[i][3];
-      o1.x = v[i][TN - 4]; o1.y = v[i][TN - 3]; o1.z = v[i][TN - 2]; o1.w = v[i][TN - 1];
-      *reinterpret_cast<float4*>(p) = o0;
-      *reinterpret_cast<float4*>(p + 4) = o1;
-    } else {
-      double2 o0, o1;
-      o0.x = v[i][0]; o0.y = v[i][1]; o1.x = v[i][TN - 2]; o1.y = v[i][TN - 1];
-      *reinterpret_cast<double2*>(p) = o0;
-      *reinterpret_cast<double2*>(p + 2) = o1;
+#pragma unroll
+    for (int g = 0; g < TN / V; ++g) {
+      if (sizeof(W) == 4) {
+        float4 o;
+        o.x = v[i][4 * g]; o.y = v[i][4 * g + 1]; o.z = v[i][4 * g + 2]; o.w = v[i][4 * g + 3];
+        *reinterpret_cast<float4*>(p + 4 * g) = o;
+      } else {
+        double2 o;
+        o.x = v[i][2 * g]; o.y = v[i][2 * g + 1];
+        *reinterpret_cast<double2*>(p + 2 * g) = o;
+      }
     }
   }
 }
 
-template <typename W>
+template <typename W, int TN>
 __device__ __forceinline__ void tile_store_mask(unsigned char* mask_l, int MG, const TileCoord& tc,
-                                                const W (&v)[kTM][MlpTileCfg<W>::TN]) {
-  constexpr int TN = MlpTileCfg<W>::TN;
+                                                const W (&v)[kTM][TN]) {
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
     unsigned bits = 0;
@@ -156,17 +153,16 @@ __device__ __forceinline__ void tile_store_mask(unsigned char* mask_l, int MG, c
 
 // One n x n layer: K-loop over the ring, then `epi(acc)` by the worker threads between the two
 // CTA barriers (reads of the input activations done / writes of the outputs done).
-template <typename W, typename Epi>
+template <typename W, int TN, typename Epi>
 __device__ __forceinline__ void mlp_layer(const MlpView& mv, const MlpSmem<W>& sm, MlpPipe& pp,
                                           int M, int MG, const TileCoord& tc, bool warp_works,
                                           Epi epi) {
-  constexpr int TN = MlpTileCfg<W>::TN;
   W acc[kTM][TN];
 #pragma unroll
   for (int i = 0; i < kTM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = (W)0;
-  mlp_layer_kloop<W>(mv, sm, pp, M, MG, tc, warp_works, acc);
+  mlp_layer_kloop<W, TN>(mv, sm, pp, M, MG, tc, warp_works, acc);
   __syncthreads();
   if (tc.worker) epi(acc);
   __syncthreads();
@@ -175,12 +171,11 @@ __device__ __forceinline__ void mlp_layer(const MlpView& mv, const MlpSmem<W>& s
 // MLP forward + backward for the M lanes of the tile.  In: sm.xin (nv, a), as.up (dL/d net_out).
 // Out (owner threads tid < M): up * d net_out / d a.  Side effects: stash blocks of this
 // evaluation (`sh`, `sd`: [L][M][npad]) and the shared-memory gradient accumulators as.sg.
-template <typename W>
+template <typename W, int TN>
 __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W>& as, MlpPipe& pp,
                                               int M, int MG, int NG, W* stash_h, W* stash_d,
                                               const volatile long long* slot_ptr,
                                               size_t slot_elems) {
-  constexpr int TN = MlpTileCfg<W>::TN;
   constexpr int V = MlpTileCfg<W>::V;
   const MlpSmem<W>& sm = as.mlp;
   const int tid = threadIdx.x;
@@ -214,9 +209,9 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
 #pragma unroll
       for (int i = 0; i < kTM; ++i) h[i][j] = leaky(ikr_fma(wb, aa[i], ikr_fma(wa, nv[i], bb)), slope);
     }
-    tile_store_smem<W>(sm.Hs, M, MG, tc, h);
-    tile_store_mask<W>(as.mask, MG, tc, h);
-    tile_store_stash<W>(sh, npad, MG, tc, h);
+    tile_store_smem<W, TN>(sm.Hs, M, MG, tc, h);
+    tile_store_mask<W, TN>(as.mask, MG, tc, h);
+    tile_store_stash<W, TN>(sh, npad, MG, tc, h);
   }
   __syncthreads();
 
@@ -224,22 +219,22 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
   for (int l = 1; l <= L; ++l) {
     const W* bh = sp_bh<W>(mv, sm, l - 1) + tc.gn * TN;
     if (l < L) {
-      mlp_layer<W>(mv, sm, pp, M, MG, tc, warp_works, [&](W (&acc)[kTM][TN]) {
+      mlp_layer<W, TN>(mv, sm, pp, M, MG, tc, warp_works, [&](W (&acc)[kTM][TN]) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
           W bb = bh[j];
 #pragma unroll
           for (int i = 0; i < kTM; ++i) acc[i][j] = leaky(acc[i][j] + bb, slope);
         }
-        tile_store_smem<W>(sm.Hs, M, MG, tc, acc);
-        tile_store_mask<W>(as.mask + (size_t)l * npad * MG, MG, tc, acc);
-        tile_store_stash<W>(sh + (size_t)l * blk, npad, MG, tc, acc);
+        tile_store_smem<W, TN>(sm.Hs, M, MG, tc, acc);
+        tile_store_mask<W, TN>(as.mask + (size_t)l * npad * MG, MG, tc, acc);
+        tile_store_stash<W, TN>(sh + (size_t)l * blk, npad, MG, tc, acc);
       });
     } else {
       // last hidden layer: H_L feeds the output layer Linear(n, 1).  Its gradient is rank-1, so
       // it is consumed here: d w_last += sum_m up[m] H_L[:, m], and dz_L = w_last up leaky'(H_L)
       // replaces H_L in shared memory (and goes to the stash for dW_L).
-      mlp_layer<W>(mv, sm, pp, M, MG, tc, warp_works, [&](W (&acc)[kTM][TN]) {
+      mlp_layer<W, TN>(mv, sm, pp, M, MG, tc, warp_works, [&](W (&acc)[kTM][TN]) {
         W upv[kTM];
 #pragma unroll
         for (int i = 0; i < kTM; ++i) upv[i] = as.up[tile_row<V>(i, tc.gm, MG)];
@@ -256,15 +251,15 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
           }
           atomicAdd(&as.sg[3 * npad + tc.gn * TN + j], (double)s);
         }
-        tile_store_smem<W>(sm.Hs, M, MG, tc, acc);
-        tile_store_stash<W>(sd + (size_t)(L - 1) * blk, npad, MG, tc, acc);
+        tile_store_smem<W, TN>(sm.Hs, M, MG, tc, acc);
+        tile_store_stash<W, TN>(sd + (size_t)(L - 1) * blk, npad, MG, tc, acc);
       });
     }
   }
 
   // ---- hidden layers backward: dz_{l-1} = (dz_l W_l) * leaky'(H_{l-1}) ---------------------------
   for (int l = L; l >= 1; --l) {
-    mlp_layer<W>(mv, sm, pp, M, MG, tc, warp_works, [&](W (&acc)[kTM][TN]) {
+    mlp_layer<W, TN>(mv, sm, pp, M, MG, tc, warp_works, [&](W (&acc)[kTM][TN]) {
       const unsigned char* mk = as.mask + (size_t)(l - 1) * npad * MG;
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
@@ -272,8 +267,8 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
 #pragma unroll
         for (int i = 0; i < kTM; ++i) acc[i][j] = acc[i][j] * (((bits >> i) & 1u) ? (W)1 : slope);
       }
-      tile_store_smem<W>(sm.Hs, M, MG, tc, acc);
-      if (l >= 2) tile_store_stash<W>(sd + (size_t)(l - 2) * blk, npad, MG, tc, acc);
+      tile_store_smem<W, TN>(sm.Hs, M, MG, tc, acc);
+      if (l >= 2) tile_store_stash<W, TN>(sd + (size_t)(l - 2) * blk, npad, MG, tc, acc);
     });
   }
 
@@ -315,7 +310,7 @@ __device__ __forceinline__ W mlp_tile_fwd_bwd(const MlpView& mv, const AdjSmem<W
   return da;
 }
 
-template <typename S, typename W>
+template <typename S, typename W, int TN>
 __global__ void __launch_bounds__(512, 1) ikr_adjoint_kernel(const BwdParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   typedef typename Vec2<S>::type V2;
@@ -408,7 +403,7 @@ __global__ void __launch_bounds__(512, 1) ikr_adjoint_kernel(const BwdParams p) 
         as.up[tid] = act ? (W)up : (W)0;
       }
       if (tid == 0) misc[1] = (long long)atomicAdd(&p.counters[1], 1ULL);
-      return mlp_tile_fwd_bwd<W>(p.mlp, as, pp, M, p.MG, p.NG, stash_h, stash_d, misc + 1,
+      return mlp_tile_fwd_bwd<W, TN>(p.mlp, as, pp, M, p.MG, p.NG, stash_h, stash_d, misc + 1,
                                  slot_elems);
     };
 

@@ -88,46 +88,59 @@ double warp_throughput(int workers) {
 // mapping bank-conflict free; 1..3 only serve tiny batches.
 const int kMgCandidates[] = {1, 2, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64};
 
-Geometry make_geometry(const ikr_desc* d, int n_jobs, const long long* B, bool pool = false) {
+// The register tile is 8 trajectories x TN features per thread.  The wide tile (TN = 8 fp32 / 4
+// fp64) has the best FMA : LDS ratio; the narrow tile (TN = 4 / 2) doubles the worker threads of
+// a small trajectory tile so that small batches still put >= 2 warps on every scheduler.
+constexpr double kNarrowTilePenalty = 0.85;
+
+template <typename SmemFn>
+Geometry search_geometry(const ikr_desc* d, int n_jobs, const long long* B, bool pool,
+                         SmemFn smem_of) {
   Geometry g;
   long long off[5], total;
   mlp_layout(d, &g.npad, &g.kc, &g.cpl, off, &total);
-  g.TN = d->mlp_dtype == IKR_F32 ? 8 : 4;
-  g.NG = g.npad / g.TN;
+  const int tn_wide = d->mlp_dtype == IKR_F32 ? 8 : 4;
   g.sms = device_sms();
   long long b_total = 0;
   for (int j = 0; j < n_jobs; ++j) b_total += B[j];
   double best_score = -1.0;
-  int best_mg = 1;
+  int best_mg = 1, best_tn = tn_wide;
   const int forced = d->tile_m > 0 ? round_up(d->tile_m, 8) / 8 : 0;
-  for (int mg : kMgCandidates) {
-    const int M = 8 * mg;
-    const int workers = tile_worker_threads(mg, g.NG);
-    const int threads = round_up(workers > M ? workers : M, 32);
-    if (threads > kMaxThreads) continue;
-    if (fwd_smem_dyn(d, M, g.npad, g.kc) > kSmemLimit) continue;
-    if (forced) {
-      if (mg <= forced) best_mg = mg;       // largest feasible candidate not above the request
-      continue;
+  for (int tn = tn_wide; tn >= tn_wide / 2; tn /= 2) {
+    const int ng = g.npad / tn;
+    for (int mg : kMgCandidates) {
+      const int M = 8 * mg;
+      const int workers = tile_worker_threads(mg, ng);
+      const int threads = round_up(workers > M ? workers : M, 32);
+      if (threads > kMaxThreads) continue;
+      if (smem_of(M) > kSmemLimit) continue;
+      if (forced) {
+        // largest feasible candidate not above the request (wide tile only)
+        if (tn == tn_wide && mg <= forced) { best_mg = mg; best_tn = tn; }
+        continue;
+      }
+      long long tiles = 0;
+      for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + M - 1) / M;
+      double wave_eff, fill;
+      if (pool) {
+        // lane-pool kernel: slots refill from one queue, so only an under-filled GPU costs
+        tiles = (b_total + M - 1) / M;
+        const long long ctas = tiles < g.sms ? tiles : g.sms;
+        wave_eff = (double)ctas / g.sms;
+        fill = b_total >= ctas * (long long)M ? 1.0 : (double)b_total / ((double)ctas * M);
+      } else {
+        const double waves = (double)tiles / g.sms;
+        wave_eff = waves / (double)((tiles + g.sms - 1) / g.sms);
+        fill = (double)b_total / ((double)tiles * M);
+      }
+      const double amort = (double)M / (M + 6.0);   // per-evaluation owner-phase overhead
+      const double score = wave_eff * fill * warp_throughput(workers) * amort *
+                           (tn == tn_wide ? 1.0 : kNarrowTilePenalty);
+      if (score > best_score) { best_score = score; best_mg = mg; best_tn = tn; }
     }
-    long long tiles = 0;
-    for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + M - 1) / M;
-    double wave_eff, fill;
-    if (pool) {
-      // lane-pool kernel: slots refill from one queue, so only an under-filled GPU costs
-      tiles = (b_total + M - 1) / M;
-      const long long ctas = tiles < g.sms ? tiles : g.sms;
-      wave_eff = (double)ctas / g.sms;
-      fill = b_total >= ctas * (long long)M ? 1.0 : (double)b_total / ((double)ctas * M);
-    } else {
-      const double waves = (double)tiles / g.sms;
-      wave_eff = waves / (double)((tiles + g.sms - 1) / g.sms);
-      fill = (double)b_total / ((double)tiles * M);
-    }
-    const double amort = (double)M / (M + 6.0);   // per-evaluation owner-phase overhead
-    const double score = wave_eff * fill * warp_throughput(workers) * amort;
-    if (score > best_score) { best_score = score; best_mg = mg; }
   }
+  g.TN = best_tn;
+  g.NG = g.npad / g.TN;
   g.MG = best_mg;
   g.M = 8 * best_mg;
   const int workers = tile_worker_threads(g.MG, g.NG);
@@ -138,8 +151,16 @@ Geometry make_geometry(const ikr_desc* d, int n_jobs, const long long* B, bool p
   else for (int j = 0; j < n_jobs; ++j) g.n_tiles += (B[j] + g.M - 1) / g.M;
   g.grid = (int)(g.n_tiles < g.sms ? g.n_tiles : g.sms);
   if (g.grid < 1) g.grid = 1;
-  g.smem = fwd_smem_dyn(d, g.M, g.npad, g.kc);
+  g.smem = smem_of(g.M);
   return g;
+}
+
+Geometry make_geometry(const ikr_desc* d, int n_jobs, const long long* B, bool pool = false) {
+  long long off[5], total;
+  int npad, kc, cpl;
+  mlp_layout(d, &npad, &kc, &cpl, off, &total);
+  return search_geometry(d, n_jobs, B, pool,
+                         [&](int M) { return fwd_smem_dyn(d, M, npad, kc); });
 }
 
 MlpView make_view(const ikr_desc* d, const void* weights) {
@@ -182,9 +203,9 @@ SolverCfg make_cfg(const ikr_desc* d) {
 // and loses ~3 % on the five-protocol bench mix, so it is opt-in.  rk4 is always tile-scheduled.
 bool use_pool(const ikr_desc* d) { return d->method == IKR_DOPRI5 && (d->reserved & 1); }
 
-template <typename S, typename W>
-int launch_forward(const FwdParams& p, const Geometry& g, cudaStream_t st, bool pool) {
-  auto kern = pool ? ikr_forward_pool_kernel<S, W> : ikr_forward_kernel<S, W>;
+template <typename S, typename W, int TN>
+int launch_forward_tn(const FwdParams& p, const Geometry& g, cudaStream_t st, bool pool) {
+  auto kern = pool ? ikr_forward_pool_kernel<S, W, TN> : ikr_forward_kernel<S, W, TN>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) !=
       cudaSuccess) {
     cudaGetLastError();
@@ -192,6 +213,13 @@ int launch_forward(const FwdParams& p, const Geometry& g, cudaStream_t st, bool 
   }
   kern<<<g.grid, g.threads, g.smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
+template <typename S, typename W>
+int launch_forward(const FwdParams& p, const Geometry& g, cudaStream_t st, bool pool) {
+  constexpr int wide = MlpTileCfg<W>::TN;
+  if (g.TN == wide) return launch_forward_tn<S, W, wide>(p, g, st, pool);
+  return launch_forward_tn<S, W, wide / 2>(p, g, st, pool);
 }
 
 
@@ -208,43 +236,10 @@ size_t adj_smem_dyn(const ikr_desc* d, int M, int npad, int kc) {
 }
 
 Geometry make_geometry_bwd(const ikr_desc* d, long long B) {
-  Geometry g;
   long long off[5], total;
-  mlp_layout(d, &g.npad, &g.kc, &g.cpl, off, &total);
-  g.TN = d->mlp_dtype == IKR_F32 ? 8 : 4;
-  g.NG = g.npad / g.TN;
-  g.sms = device_sms();
-  double best_score = -1.0;
-  int best_mg = 1;
-  const int forced = d->tile_m > 0 ? round_up(d->tile_m, 8) / 8 : 0;
-  for (int mg : kMgCandidates) {
-    const int M = 8 * mg;
-    const int workers = tile_worker_threads(mg, g.NG);
-    const int threads = round_up(workers > M ? workers : M, 32);
-    if (threads > kMaxThreads) continue;
-    if (adj_smem_dyn(d, M, g.npad, g.kc) > kSmemLimit) continue;
-    if (forced) {
-      if (mg <= forced) best_mg = mg;
-      continue;
-    }
-    const long long tiles = (B + M - 1) / M;
-    const double waves = (double)tiles / g.sms;
-    const double wave_eff = waves / (double)((tiles + g.sms - 1) / g.sms);
-    const double fill = (double)B / ((double)tiles * M);
-    const double amort = (double)M / (M + 6.0);
-    const double score = wave_eff * fill * warp_throughput(workers) * amort;
-    if (score > best_score) { best_score = score; best_mg = mg; }
-  }
-  g.MG = best_mg;
-  g.M = 8 * best_mg;
-  const int workers = tile_worker_threads(g.MG, g.NG);
-  g.n_worker_warps = (workers + 31) / 32;
-  g.threads = round_up(workers > g.M ? workers : g.M, 32);
-  g.n_tiles = (B + g.M - 1) / g.M;
-  g.grid = (int)(g.n_tiles < g.sms ? g.n_tiles : g.sms);
-  if (g.grid < 1) g.grid = 1;
-  g.smem = adj_smem_dyn(d, g.M, g.npad, g.kc);
-  return g;
+  int npad, kc, cpl;
+  mlp_layout(d, &npad, &kc, &cpl, off, &total);
+  return search_geometry(d, 1, &B, false, [&](int M) { return adj_smem_dyn(d, M, npad, kc); });
 }
 
 int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
@@ -327,9 +322,9 @@ size_t bwd_workspace_bytes(const ikr_desc* d, long long B) {
   return pl.fixed_bytes + 512 + 2 * (size_t)pl.g.n_tiles * (6 * R + 1) * pl.slot_bytes;
 }
 
-template <typename S, typename W>
-int launch_adjoint(const BwdParams& p, const Geometry& g, cudaStream_t st) {
-  auto kern = ikr_adjoint_kernel<S, W>;
+template <typename S, typename W, int TN>
+int launch_adjoint_tn(const BwdParams& p, const Geometry& g, cudaStream_t st) {
+  auto kern = ikr_adjoint_kernel<S, W, TN>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) !=
       cudaSuccess) {
     cudaGetLastError();
@@ -337,6 +332,13 @@ int launch_adjoint(const BwdParams& p, const Geometry& g, cudaStream_t st) {
   }
   kern<<<g.grid, g.threads, g.smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
+template <typename S, typename W>
+int launch_adjoint(const BwdParams& p, const Geometry& g, cudaStream_t st) {
+  constexpr int wide = MlpTileCfg<W>::TN;
+  if (g.TN == wide) return launch_adjoint_tn<S, W, wide>(p, g, st);
+  return launch_adjoint_tn<S, W, wide / 2>(p, g, st);
 }
 
 template <typename W>

@@ -98,7 +98,7 @@ template <typename W>
 struct MlpTileCfg;
 template <>
 struct MlpTileCfg<float> {
-  static constexpr int TN = 8;  // output features per thread
+  static constexpr int TN = 8;  // output features per thread (wide tile; the narrow tile is TN / 2)
   static constexpr int V = 4;   // elements per 16-byte shared-memory vector
 };
 template <>
@@ -264,23 +264,22 @@ __device__ __forceinline__ int tile_row(int i, int gm, int MG) {
 
 // K-loop of one n x n layer over the weight-chunk ring: acc[i][j] += sum_k Hs[k][row_i] * Wr[k][col_j]
 // for the thread's 8 x TN register tile.  No CTA barrier inside (full/empty mbarriers only).
-template <typename W>
+template <typename W, int TN>
 __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem<W>& sm,
                                                 MlpPipe& pp, int M, int MG, const TileCoord& tc,
-                                                bool warp_works,
-                                                W (&acc)[kTM][MlpTileCfg<W>::TN]) {
-  constexpr int TN = MlpTileCfg<W>::TN;
+                                                bool warp_works, W (&acc)[kTM][TN]) {
   constexpr int V = MlpTileCfg<W>::V;
+  constexpr int NP = TN / 2 > 0 ? TN / 2 : 1;   // packed fp32 pairs per row of the register tile
   const int tid = threadIdx.x;
   const int gm = tc.gm, gn = tc.gn;
   const bool worker = tc.worker;
   // fp32: accumulate in packed pairs (acc[i][2p], acc[i][2p+1]) with FFMA2
-  f32x2 c2[kTM][4];
+  f32x2 c2[kTM][NP];
   if (sizeof(W) == 4) {
 #pragma unroll
     for (int i = 0; i < kTM; ++i)
 #pragma unroll
-      for (int pj = 0; pj < 4; ++pj) c2[i][pj] = f2_pack((float)acc[i][2 * pj], (float)acc[i][2 * pj + 1]);
+      for (int pj = 0; pj < NP; ++pj) c2[i][pj] = f2_pack((float)acc[i][2 * pj], (float)acc[i][2 * pj + 1]);
   }
   for (int c = 0; c < mv.cpl; ++c) {
     const unsigned q = pp.q;
@@ -301,7 +300,8 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
           float4 a0 = *reinterpret_cast<const float4*>(hp);
           float4 a1 = *reinterpret_cast<const float4*>(hp + a1_off);
           float4 b0 = *reinterpret_cast<const float4*>(wp);
-          float4 b1 = *reinterpret_cast<const float4*>(wp + 4);
+          float4 b1 = b0;
+          if (TN == 8) b1 = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll 2
           for (int kk = 0; kk < rows; ++kk) {
             hp += M;
@@ -309,7 +309,8 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
             const float4 na0 = *reinterpret_cast<const float4*>(hp);
             const float4 na1 = *reinterpret_cast<const float4*>(hp + a1_off);
             const float4 nb0 = *reinterpret_cast<const float4*>(wp);
-            const float4 nb1 = *reinterpret_cast<const float4*>(wp + 4);
+            float4 nb1 = nb0;
+            if (TN == 8) nb1 = *reinterpret_cast<const float4*>(wp + 4);
             const float a[kTM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const f32x2 b[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y),
                                 f2_pack(b1.z, b1.w)};
@@ -317,7 +318,7 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
             for (int i = 0; i < kTM; ++i) {
               const f32x2 aa = f2_pack(a[i], a[i]);
 #pragma unroll
-              for (int pj = 0; pj < 4; ++pj) f2_fma(c2[i][pj], aa, b[pj]);
+              for (int pj = 0; pj < NP; ++pj) f2_fma(c2[i][pj], aa, b[pj]);
             }
             a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
           }
@@ -330,9 +331,11 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
               double2 av = *reinterpret_cast<const double2*>(Hk + (size_t)kk * M + g * MG * V);
               a[2 * g] = av.x; a[2 * g + 1] = av.y;
             }
-            double2 b0 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad);
-            double2 b1 = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad + 2);
-            b[0] = b0.x; b[1] = b0.y; b[TN - 2] = b1.x; b[TN - 1] = b1.y;
+#pragma unroll
+            for (int g = 0; g < TN / 2; ++g) {
+              double2 bv = *reinterpret_cast<const double2*>(Wk + (size_t)kk * mv.npad + 2 * g);
+              b[2 * g] = bv.x; b[2 * g + 1] = bv.y;
+            }
 #pragma unroll
             for (int i = 0; i < kTM; ++i)
 #pragma unroll
@@ -356,7 +359,7 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
 #pragma unroll
     for (int i = 0; i < kTM; ++i)
 #pragma unroll
-      for (int pj = 0; pj < 4; ++pj) {
+      for (int pj = 0; pj < NP; ++pj) {
         float lo, hi;
         f2_unpack(c2[i][pj], lo, hi);
         acc[i][2 * pj] = (W)lo; acc[i][2 * pj + 1] = (W)hi;
@@ -369,10 +372,9 @@ __device__ __forceinline__ void mlp_layer_kloop(const MlpView& mv, const MlpSmem
 // warps drift up to kStages-1 chunks apart; thread 0 refills a ring slot one chunk late so that
 // it rarely waits for the slowest warp).  Two CTA barriers per layer remain (all reads of the
 // input activations before the in-place overwrite, all writes before the next layer reads).
-template <typename W>
+template <typename W, int TN>
 __device__ __forceinline__ void mlp_tile_hidden(const MlpView& mv, const MlpSmem<W>& sm,
                                                 MlpPipe& pp, int M, int MG, const TileCoord& tc) {
-  constexpr int TN = MlpTileCfg<W>::TN;
   constexpr int V = MlpTileCfg<W>::V;
   const int tid = threadIdx.x;
   const W slope = (W)mv.slope;
@@ -388,7 +390,7 @@ __device__ __forceinline__ void mlp_tile_hidden(const MlpView& mv, const MlpSmem
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = (W)0;
 
-    mlp_layer_kloop<W>(mv, sm, pp, M, MG, tc, warp_works, acc);
+    mlp_layer_kloop<W, TN>(mv, sm, pp, M, MG, tc, warp_works, acc);
     __syncthreads();  // all reads of this layer's input activations are done
 
     if (worker) {
@@ -423,10 +425,9 @@ __device__ __forceinline__ void mlp_tile_hidden(const MlpView& mv, const MlpSmem
 // Evaluate the MLP for the M trajectories of the CTA tile.  Inputs in sm.xin, result (the
 // network output before /netscale) returned to the owner threads tid < M.  Executed by every
 // thread of the CTA (contains barriers).
-template <typename W>
+template <typename W, int TN>
 __device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W>& sm,
                                               MlpPipe& pp, int M, int MG, int NG) {
-  constexpr int TN = MlpTileCfg<W>::TN;
   constexpr int V = MlpTileCfg<W>::V;
   const int tid = threadIdx.x;
   const TileCoord tc = tile_coord(tid, MG, NG);
@@ -458,7 +459,7 @@ __device__ __forceinline__ W mlp_tile_forward(const MlpView& mv, const MlpSmem<W
   }
   __syncthreads();
 
-  mlp_tile_hidden<W>(mv, sm, pp, M, MG, tc);
+  mlp_tile_hidden<W, TN>(mv, sm, pp, M, MG, tc);
 
   // ---- output layer: Linear(n, 1), one owner thread per trajectory ---------------------------
   W out = (W)0;

@@ -87,7 +87,7 @@ struct FwdSmemLayout {
   }
 };
 
-template <typename S, typename W>
+template <typename S, typename W, int TN>
 __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
         init_prepare_f0<S>(lanes[tid], cfg, &nv, &ain);
         sm.xin[tid] = (W)nv; sm.xin[M + tid] = (W)ain;
       }
-      W out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+      W out = mlp_tile_forward<W, TN>(p.mlp, sm, pp, M, p.MG, p.NG);
       if (owner) {
         Lane<S>& L = lanes[tid];
         init_store_f0<S>(L, cfg, (double)out);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
         }
       }
       if (!(cfg.first_step > 0)) {
-        out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+        out = mlp_tile_forward<W, TN>(p.mlp, sm, pp, M, p.MG, p.NG);
         if (owner) init_store_f1<S>(lanes[tid], cfg, (double)out);
       }
       if (owner && T <= 1 && lane_active(lanes[tid])) lanes[tid].status = LANE_DONE;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
             dp_prepare_stage<S>(lanes[tid], cfg, s, &nv, &ain);
             sm.xin[tid] = (W)nv; sm.xin[M + tid] = (W)ain;
           }
-          out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+          out = mlp_tile_forward<W, TN>(p.mlp, sm, pp, M, p.MG, p.NG);
           if (owner) dp_store_stage<S>(lanes[tid], cfg, s, (double)out);
         }
         if (owner) dp_finish_step<S>(lanes[tid], cfg, job.t_out, T, emit, ckpt);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
                                  &nv, &ain);
             sm.xin[tid] = (W)nv; sm.xin[M + tid] = (W)ain;
           }
-          W out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+          W out = mlp_tile_forward<W, TN>(p.mlp, sm, pp, M, p.MG, p.NG);
           if (owner) rk4_store_stage<S>(lanes[tid], cfg, s, (double)out);
         }
         if (owner) {
@@ -306,7 +306,7 @@ struct LaneAux {
 };
 enum { POOL_EMPTY = 0, POOL_INIT = 1, POOL_STEP = 2 };
 
-template <typename S, typename W>
+template <typename S, typename W, int TN>
 __global__ void __launch_bounds__(512, 1) ikr_forward_pool_kernel(const FwdParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_pool_kernel(const FwdParam
         }
         sm.xin[tid] = (W)nv; sm.xin[M + tid] = (W)ain;
       }
-      const W out = mlp_tile_forward<W>(p.mlp, sm, pp, M, p.MG, p.NG);
+      const W out = mlp_tile_forward<W, TN>(p.mlp, sm, pp, M, p.MG, p.NG);
       if (what) {
         Lane<S>& L = lanes[tid];
         SolverCfg c = p.cfg;
