@@ -156,6 +156,13 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
 int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, void* workspace,
                  size_t workspace_bytes, void* cuda_stream);
 
+/* Hodgkin-Huxley candidate model without a network (train-d0.py:321-376 `ODEFunc`; the forward
+ * model of the PINTS CMA-ES fit, `Model.simulate` train-d0.py:415-439), batched over a population:
+ * trajectory b uses hh_params[b][0..7] = p1..p8 (nullable: desc->p for every trajectory).  One
+ * job; `desc` supplies method / dtypes / tolerances (n_layers, n_nodes, mlp_dtype are ignored);
+ * io->weights and the checkpoint fields are ignored.  No workspace.                              */
+int ikr_forward_hh(const ikr_desc* d, const ikr_io* io, const double* hh_params, void* cuda_stream);
+
 /* V(t) of the protocol table at T query times (scipy interp1d linear semantics; out-of-table
  * => -80 like the callers' ValueError branch, train-s1.py:234-237).                             */
 int ikr_interp_protocol(const ikr_io* table, const double* t_query, int64_t T, double* v_out,

@@ -14,6 +14,7 @@ from .models import (ARCHITECTURES, PARAMETER_SETS, ODEFunc, ODEFuncNNd, ODEFunc
                      build_net, load_weights)
 from .solver import IkrResult, describe, integrate, integrate_many, odeint  # noqa: F401
 from .adjoint import loss_and_grad  # noqa: F401
+from .hh import HHPopulationModel, integrate_hh  # noqa: F401
 
-__all__ = ['odeint', 'integrate', 'loss_and_grad', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
+__all__ = ['odeint', 'integrate', 'loss_and_grad', 'integrate_hh', 'HHPopulationModel', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
            'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols', 'parallel']

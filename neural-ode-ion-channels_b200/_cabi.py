@@ -91,6 +91,8 @@ def lib():
     L.ikr_backward.restype = c_i32
     L.ikr_backward.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(IkrIO),
                                ctypes.POINTER(IkrBwdIO), c_vp, ctypes.c_size_t, c_vp]
+    L.ikr_forward_hh.restype = c_i32
+    L.ikr_forward_hh.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(IkrIO), c_vp, c_vp]
     L.ikr_interp_protocol.restype = c_i32
     L.ikr_interp_protocol.argtypes = [ctypes.POINTER(IkrIO), c_vp, c_i64, c_vp, c_vp]
     L.ikr_fma_peak.restype = c_i32
@@ -103,7 +105,7 @@ def lib():
 
 EXPORTS = ('ikr_abi_version', 'ikr_error_string', 'ikr_packed_weight_elems', 'ikr_packed_layout',
            'ikr_param_count', 'ikr_tile_m', 'ikr_launch_geometry', 'ikr_workspace_bytes',
-           'ikr_forward', 'ikr_backward', 'ikr_interp_protocol', 'ikr_fma_peak')
+           'ikr_forward', 'ikr_backward', 'ikr_forward_hh', 'ikr_interp_protocol', 'ikr_fma_peak')
 
 
 def check(code, what):

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, 'libikr_b200.so')
 SOURCES = ['ikr_capi.cu']
-HEADERS = ['ikr_math.h', 'ikr_device.cuh', 'ikr_forward.cuh', 'ikr_backward.cuh',
+HEADERS = ['ikr_math.h', 'ikr_device.cuh', 'ikr_forward.cuh', 'ikr_backward.cuh', 'ikr_hh.cuh',
            os.path.join('..', '..', 'include', 'ikr.h')]
 
 NVCC_FLAGS = [

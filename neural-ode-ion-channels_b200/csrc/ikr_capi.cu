@@ -9,6 +9,7 @@
 
 #include "../../include/ikr.h"
 #include "ikr_backward.cuh"
+#include "ikr_hh.cuh"
 
 using namespace ikr;
 
@@ -587,6 +588,40 @@ int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, voi
                  size_t workspace_bytes, void* cuda_stream) {
   if (!valid_desc(d) || !io || !bio) return IKR_ERR_ARG;
   return bwd_dispatch(d, io, bio, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+}
+
+int ikr_forward_hh(const ikr_desc* d, const ikr_io* io, const double* hh_params, void* cuda_stream) {
+  if (!d || !io) return IKR_ERR_ARG;
+  if (d->state_dtype != IKR_F32 && d->state_dtype != IKR_F64) return IKR_ERR_ARG;
+  if (d->method != IKR_DOPRI5 && d->method != IKR_RK4) return IKR_ERR_ARG;
+  if (io->B < 1 || io->T < 1 || !io->table_t || !io->table_v || !io->y0 || !io->t_out ||
+      !io->stats_out || io->table_len < 2)
+    return IKR_ERR_ARG;
+  if (d->method == IKR_RK4 && (!io->grid || io->G < 1)) return IKR_ERR_ARG;
+  if ((io->i_out || io->loss_out) && !io->v_out) return IKR_ERR_ARG;
+  if (io->data && io->data_B != 1 && io->data_B != io->B) return IKR_ERR_ARG;
+  if (io->T > 2147483647LL || io->G > 2147483647LL) return IKR_ERR_ARG;
+  HhKernelParams p;
+  p.cfg = make_cfg(d);
+  p.cfg.mlp_is_f64 = 1;   // no network: the (absent) MLP term is an exact zero in any precision
+  FwdJob& fj = p.job;
+  fj.tab = make_table(io);
+  fj.B = io->B; fj.T = (int)io->T; fj.G = (int)io->G;
+  fj.tile_begin = 0; fj.traj_begin = 0;
+  fj.y0 = io->y0; fj.t_out = io->t_out; fj.grid = io->grid; fj.v_out = io->v_out;
+  fj.g = io->g; fj.e_rev = io->e_rev; fj.e_scalar = io->e_scalar;
+  fj.data = io->data; fj.data_B = io->data_B;
+  fj.y_out = io->y_out; fj.i_out = io->i_out; fj.loss_out = io->loss_out;
+  fj.stats_out = io->stats_out;
+  fj.ckpt_cap = 0; fj.ckpt_t = nullptr; fj.ckpt_y = nullptr;
+  p.hh_params = hh_params;
+  p.method = d->method; p.time_f32 = d->time_f32; p.rk4_perturb = d->rk4_perturb;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((io->B + threads - 1) / threads);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (d->state_dtype == IKR_F32) ikr_hh_kernel<float><<<blocks, threads, 0, st>>>(p);
+  else ikr_hh_kernel<double><<<blocks, threads, 0, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
 }
 
 int ikr_interp_protocol(const ikr_io* table, const double* t_query, int64_t T, double* v_out,

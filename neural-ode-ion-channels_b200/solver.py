@@ -504,6 +504,14 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     squeeze = False
     if isinstance(y0, torch.Tensor) and y0.dim() == 1:
         y0, squeeze = y0.reshape(1, -1), True
+    from .hh import hh_params_of, integrate_hh, is_hh_func
+    if is_hh_func(func):
+        # network-free HH candidate (train-d0.py:321-376): same call, dedicated kernel
+        y = integrate_hh(hh_params_of(func), y0, t, _protocol_arrays(func), rtol=rtol, atol=atol,
+                         method=method, options=options).y
+        if not y0.is_cuda:
+            y = y.to(y0.device)
+        return y[:, 0, :] if squeeze else y
     needs_grad = torch.is_grad_enabled() and any(
         p.requires_grad for p in getattr(func, 'net', nn.Sequential()).parameters())
     if needs_grad:

@@ -10,6 +10,7 @@ What is restated here (citations relative to ``/root/reference``):
 * ``NNdRhs``   -- ``ODEFunc`` NN-d,  ``train-d2.py:191-272`` (= ``train-s2.py:180-259``,
                   ``train-r2.py:137-219``)
 * ``HHRhs``    -- 2-state Hodgkin-Huxley ``Lambda``, ``train-s1.py:134-177``
+* ``HHFitRhs`` -- the network-free HH candidate ``ODEFunc`` fitted by PINTS, ``train-d0.py:321-376``
 * ``MarkovRhs``-- 6-state Markov ``Lambda`` (d-study ground truth), ``train-d1.py:134-187``
 * ``build_mlp``-- architecture builder, ``train-r1-tune.py:155-163`` with
                   ``architectures/sNN.py:1-2`` hyper-parameters
@@ -119,6 +120,34 @@ class HHRhs(nn.Module, _ProtocolMixin):
         dadt = k1 * (1. - a) - k2 * a
         drdt = -k3 * r + k4 * (1. - r)
         return torch.stack([dadt[0], drdt[0]])
+
+
+class HHFitRhs(nn.Module, _ProtocolMixin):
+    """HH candidate model of the CMA-ES fit (train-d0.py:321-376): ``set_parameters(x)`` sets
+    p1..p4, p5..p8 are fixed; returns shape (1, 2); ``unity`` is an int64 tensor like the
+    reference's, so ``unity - a`` follows the state dtype."""
+
+    def __init__(self, inact=INACT_D):
+        super().__init__()
+        self.p1, self.p2, self.p3, self.p4 = 1.13e-4, 7.45e-2, 3.60e-5, 4.49e-2
+        self.p5, self.p6, self.p7, self.p8 = inact
+        self.unity = torch.tensor([1])
+        self.nfe = 0
+
+    def set_parameters(self, x):
+        self.p1, self.p2, self.p3, self.p4 = x
+
+    def forward(self, t, y):
+        self.nfe += 1
+        a, r = torch.unbind(y, dim=1)
+        v = self._v_or_holding(t)
+        k1 = self.p1 * torch.exp(self.p2 * v)
+        k2 = self.p3 * torch.exp(-self.p4 * v)
+        k3 = self.p5 * torch.exp(self.p6 * v)
+        k4 = self.p7 * torch.exp(-self.p8 * v)
+        dadt = k1 * (self.unity - a) - k2 * a
+        drdt = -k3 * r + k4 * (self.unity - r)
+        return torch.stack([dadt[0], drdt[0]]).reshape(1, -1)
 
 
 class MarkovRhs(nn.Module, _ProtocolMixin):

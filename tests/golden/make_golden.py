@@ -115,6 +115,52 @@ def make_rhs_vectors():
     print('rhs_vectors.npz: %d probes x 4 models' % n)
 
 
+def nested_class(script, name):
+    """exec a class defined anywhere in a reference script (train-d0.py nests its ODEFunc under
+    the ``--myokit`` else-branch)."""
+    path = os.path.join(REF, script)
+    with open(path) as fh:
+        src = fh.read()
+    ns = {'torch': torch, 'nn': nn, 'np': np, 'interp1d': interp1d,
+          'device': torch.device('cpu')}
+    import textwrap
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.ClassDef) and node.name == name:
+            lines = src.splitlines()[node.lineno - 1:node.end_lineno]
+            exec(compile(textwrap.dedent('\n'.join(lines)), path, 'exec'), ns)
+            return ns[name]
+    raise KeyError(name)
+
+
+def make_hh_fit_vectors():
+    """Outputs of the reference's own HH candidate ``ODEFunc`` (train-d0.py:321-376) for a few
+    CMA-ES-like parameter vectors on seeded (t, y) probes -> ``hh_fit_vectors.npz``."""
+    from neural_ode_ion_channels_b200 import protocols
+    t_tab, v_tab = protocols.ap2hz()
+    rng = np.random.RandomState(4321)
+    n = 32
+    tq = np.concatenate([rng.uniform(0, 3499.9, n - 4), [0.0, 3499.9, 3600.0, 1e4]])
+    aq, rq = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    X = np.array([[1.13e-4, 7.45e-2, 3.60e-5, 4.49e-2],
+                  [2.26e-4, 6.99e-2, 3.45e-5, 5.46e-2],
+                  [5.0e-5, 9.0e-2, 1.0e-4, 3.0e-2]])
+    func = nested_class('train-d0.py', 'ODEFunc')()
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    blob = {'t': tq, 'a': aq, 'r': rq, 'X': X}
+    for st_dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
+        out = np.zeros((len(X), n, 2))
+        with torch.no_grad():
+            for k, x in enumerate(X):
+                func.set_parameters(list(x))
+                for i in range(n):
+                    t = torch.tensor(tq[i]).to(st_dtype)
+                    y = torch.tensor([[aq[i], rq[i]]]).to(st_dtype)
+                    out[k, i] = func(t, y).double().numpy().reshape(-1)
+        blob['out_' + tag] = out
+    np.savez_compressed(os.path.join(HERE, 'hh_fit_vectors.npz'), **blob)
+    print('hh_fit_vectors.npz: %d probes x %d parameter vectors' % (n, len(X)))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--traces', action='store_true')
@@ -122,6 +168,7 @@ def main():
     torch.set_num_threads(1)
     make_kat()
     make_rhs_vectors()
+    make_hh_fit_vectors()
     if args.traces:
         from tests.golden import make_traces
         make_traces.main()

@@ -47,3 +47,23 @@ def test_fallback_voltage_is_minus_80():
     k3 = f.p5 * np.exp(f.p6 * -80.0)
     k4 = f.p7 * np.exp(-f.p8 * -80.0)
     assert abs(out[0, 1].item() - (-k3 * 0.6 + k4 * 0.4)) < 1e-7
+
+
+@pytest.mark.parametrize('tag', ['f32', 'f64'])
+def test_hh_fit_rhs_matches_reference_class(tag):
+    """HH candidate ODEFunc of the PINTS fit (train-d0.py:321-376): restated class vs vectors
+    produced by the reference's own class (tests/golden/make_golden.py::make_hh_fit_vectors)."""
+    import os
+    from neural_ode_ion_channels_b200 import protocols
+    from oracle import ref_models as rm
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'hh_fit_vectors.npz'))
+    f = rm.HHFitRhs()
+    f.set_fixed_form_voltage_protocol(*protocols.ap2hz())
+    dt = torch.float32 if tag == 'f32' else torch.float64
+    with torch.no_grad():
+        for k, x in enumerate(g['X']):
+            f.set_parameters(list(x))
+            for i in range(len(g['t'])):
+                out = f(torch.tensor(g['t'][i]).to(dt),
+                        torch.tensor([[g['a'][i], g['r'][i]]]).to(dt)).double().numpy().reshape(-1)
+                assert np.array_equal(out, g['out_' + tag][k, i])
