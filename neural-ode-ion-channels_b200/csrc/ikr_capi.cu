@@ -9,6 +9,7 @@
 
 #include "../../include/ikr.h"
 #include "ikr_backward.cuh"
+#include "ikr_forward_tc.cuh"
 #include "ikr_hh.cuh"
 
 using namespace ikr;
@@ -203,6 +204,50 @@ SolverCfg make_cfg(const ikr_desc* d) {
 // pool wins when one long job has many more trajectories than lane slots (+3.5 % at 65,536 x pr4)
 // and loses ~3 % on the five-protocol bench mix, so it is opt-in.  rk4 is always tile-scheduled.
 bool use_pool(const ikr_desc* d) { return d->method == IKR_DOPRI5 && (d->reserved & 1); }
+
+// Tensor-core forward path (ikr_forward_tc.cuh): fp32 MLP whose hidden width fits the TMEM budget
+// (n <= 200 covers every shipped model; s06-s08, n = 500, stay on the FFMA2 kernel).  desc.reserved
+// bit 1 opts out (A/B measurements, FFMA-only parity runs).
+struct TcPlan {
+  bool ok;
+  TcGeom g;
+  size_t smem, img_bytes;
+};
+
+TcPlan make_tc_plan(const ikr_desc* d) {
+  TcPlan t;
+  t.ok = false;
+  t.smem = 0; t.img_bytes = 0;
+  t.g = tc_geometry(d->n_nodes, d->n_layers);
+  if (d->mlp_dtype != IKR_F32 || (d->reserved & 2) || use_pool(d) || d->tile_m > 0) return t;
+  if (!tc_geometry_ok(t.g)) return t;
+  const size_t fixed = d->state_dtype == IKR_F32 ? TcSmemLayout<float>(t.g, 0).total
+                                                  : TcSmemLayout<double>(t.g, 0).total;
+  if (fixed + (size_t)(kTcRefillLag + 2) * t.g.stage_bytes > kSmemLimit) return t;
+  int stages = (int)((kSmemLimit - fixed) / t.g.stage_bytes);
+  if (stages > kTcMaxStages) stages = kTcMaxStages;
+  t.g.stages = stages;
+  t.smem = fixed + (size_t)stages * t.g.stage_bytes;
+  t.img_bytes = (size_t)d->n_layers * t.g.KST * t.g.stage_bytes;
+  t.ok = true;
+  return t;
+}
+
+size_t fwd_fixed_workspace(int n_jobs) {
+  return (256 + (size_t)n_jobs * sizeof(FwdJob) + 255) & ~(size_t)255;
+}
+
+template <typename S>
+int launch_forward_tc(const TcFwdParams& tp, const TcPlan& t, int grid, cudaStream_t st) {
+  auto kern = ikr_forward_tc_kernel<S>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return IKR_ERR_LAUNCH;
+  }
+  kern<<<grid, kTcThreads, t.smem, st>>>(tp);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
 
 template <typename S, typename W, int TN>
 int launch_forward_tn(const FwdParams& p, const Geometry& g, cudaStream_t st, bool pool) {
@@ -483,12 +528,22 @@ int64_t ikr_param_count(const ikr_desc* d) {
 int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B) {
   if (!valid_desc(d) || n_jobs < 1 || !B) return IKR_ERR_ARG;
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
+  if (make_tc_plan(d).ok) return kTcM;
   return make_geometry(d, n_jobs, (const long long*)B, use_pool(d)).M;
 }
 
 int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[8]) {
   if (!valid_desc(d) || n_jobs < 1 || !B || !out) return IKR_ERR_ARG;
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
+  const TcPlan tcp = make_tc_plan(d);
+  if (tcp.ok) {
+    long long tiles = 0;
+    for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + kTcM - 1) / kTcM;
+    const int sms = device_sms();
+    out[0] = kTcM; out[1] = kTcThreads; out[2] = tiles < sms ? tiles : sms; out[3] = (int64_t)tcp.smem;
+    out[4] = tiles; out[5] = 16; out[6] = tcp.g.KST; out[7] = sms;
+    return 0;
+  }
   Geometry g = make_geometry(d, n_jobs, (const long long*)B, use_pool(d));
   out[0] = g.M; out[1] = g.threads; out[2] = g.grid; out[3] = (int64_t)g.smem;
   out[4] = g.n_tiles; out[5] = g.kc; out[6] = g.cpl; out[7] = g.sms;
@@ -498,8 +553,9 @@ int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int
 size_t ikr_workspace_bytes(const ikr_desc* d, int32_t n_jobs, int64_t B_total,
                            int32_t with_backward) {
   if (!valid_desc(d) || n_jobs < 1 || B_total < 1) return 0;
-  size_t bytes = 256 + (size_t)n_jobs * sizeof(FwdJob);
-  bytes = (bytes + 255) & ~(size_t)255;
+  size_t bytes = fwd_fixed_workspace(n_jobs);
+  const TcPlan tcp = make_tc_plan(d);
+  if (tcp.ok) bytes += (tcp.img_bytes + 255) & ~(size_t)255;   // bf16 weight image of the tcgen05 path
   if (with_backward) bytes += bwd_workspace_bytes(d, B_total);
   return bytes;
 }
@@ -519,7 +575,8 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
     if (io->T > 2147483647LL || io->G > 2147483647LL) return IKR_ERR_ARG;
     if (io->weights != jobs[0].weights) return IKR_ERR_ARG;
   }
-  const size_t need = 256 + (size_t)n_jobs * sizeof(FwdJob);
+  const TcPlan tcp = make_tc_plan(d);
+  const size_t need = fwd_fixed_workspace(n_jobs) + (tcp.ok ? tcp.img_bytes : 0);
   if (!workspace || workspace_bytes < need) return IKR_ERR_WORKSPACE;
 
   // longest jobs first (LPT) so that the dynamic tile queue balances the SMs
@@ -534,6 +591,15 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
   for (int j = 0; j < n_jobs; ++j) Bs[j] = jobs[order[j]].B;
   const bool pool = use_pool(d);
   Geometry g = make_geometry(d, n_jobs, Bs.data(), pool);
+  if (tcp.ok) {
+    // tensor-core kernel: fixed 128-trajectory tiles (one per TMEM lane)
+    g.M = kTcM;
+    g.n_tiles = 0;
+    for (int j = 0; j < n_jobs; ++j) g.n_tiles += (Bs[j] + kTcM - 1) / kTcM;
+    g.grid = (int)(g.n_tiles < g.sms ? g.n_tiles : g.sms);
+    g.threads = kTcThreads;
+    g.smem = tcp.smem;
+  }
   if (g.smem > kSmemLimit || g.threads > kMaxThreads) return IKR_ERR_UNSUPPORTED;
 
   std::vector<FwdJob> table(n_jobs);
@@ -579,6 +645,22 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
   p.jobs = reinterpret_cast<const FwdJob*>(ws + 256);
   p.queue = reinterpret_cast<unsigned long long*>(ws);
 
+  if (tcp.ok) {
+    TcFwdParams tp;
+    tp.f = p;
+    tp.g = tcp.g;
+    unsigned char* img = ws + fwd_fixed_workspace(n_jobs);
+    tp.img = img;
+    TcPackParams pk;
+    pk.wn = reinterpret_cast<const float*>(jobs[0].weights) + p.mlp.off_wn;
+    pk.npad = p.mlp.npad;
+    pk.g = tcp.g;
+    pk.img = reinterpret_cast<uint16_t*>(img);
+    ikr_tc_pack_kernel<<<g.sms, 256, 0, st>>>(pk);
+    if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
+    if (d->state_dtype == IKR_F32) return launch_forward_tc<float>(tp, tcp, g.grid, st);
+    return launch_forward_tc<double>(tp, tcp, g.grid, st);
+  }
   if (d->state_dtype == IKR_F32) return launch_forward<float, float>(p, g, st, pool);
   if (d->mlp_dtype == IKR_F32) return launch_forward<double, float>(p, g, st, pool);
   return launch_forward<double, double>(p, g, st, pool);

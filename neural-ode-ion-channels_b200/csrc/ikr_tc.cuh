@@ -1,0 +1,122 @@
+// ikr_tc.cuh -- sm_100a tensor-core (tcgen05) building blocks: TMEM allocation, TMEM <-> register
+// transfers, the single-thread MMA issue with the A operand in TMEM and the B operand in shared
+// memory, and the descriptor encodings.  Raw PTX only (no CUTLASS types).
+//
+// Layout conventions used by every caller (validated on B200 by tests/tc_probe.cu):
+//   * accumulator D (fp32, M = 128): D[m][n] lives in TMEM lane m, column d_col + n;
+//   * operand A (bf16, M = 128, K-major) in TMEM: A[m][k] lives in lane m, column a_col + k / 2,
+//     low half-word = even k;
+//   * operand B (bf16, K-major, no swizzle) in shared memory: 8 x 8 core matrices of 128
+//     contiguous bytes (row n % 8 at 16-byte pitch, k % 8 at 2-byte pitch); core matrices of one
+//     K = 16 step are ordered (n / 8, k / 8): SBO (8-row group pitch) = 256 B, LBO (k-half pitch)
+//     = 128 B, so one MMA reads N x 32 contiguous bytes.
+#ifndef IKR_TC_CUH_
+#define IKR_TC_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ikr {
+namespace tc {
+
+constexpr uint32_t kTmemCols = 512;   // whole tensor memory of the SM (one CTA per SM)
+
+// ---- TMEM allocation (one full warp executes these) -------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst_addr, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst_addr),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- TMEM <-> registers: 32 lanes x 32 bit, thread i of the warp <-> TMEM lane (warp % 4) * 32 + i
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+      "%13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                 "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a),
+               "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+
+// ---- descriptors ----------------------------------------------------------------------------------
+// instruction descriptor of tcgen05.mma.kind::f16: BF16 x BF16 -> FP32, both operands K-major
+__host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
+  return (1u << 4)                      // D format F32
+         | (1u << 7)                    // A format BF16
+         | (1u << 10)                   // B format BF16
+         | ((uint32_t)(N >> 3) << 17)   // N / 8
+         | ((uint32_t)(M >> 4) << 24);  // M / 16
+}
+// shared-memory matrix descriptor, no swizzle: start address, leading / stride byte offsets (all / 16)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);   // descriptor version 1 (sm_100)
+}
+
+// D[tmem] (+)= A[tmem] . B[smem]^T ; issued by ONE thread
+__device__ __forceinline__ void mma_ts(uint32_t d_taddr, uint32_t a_taddr, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_taddr),
+      "r"(a_taddr), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void commit(uint32_t bar_saddr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr)
+               : "memory");
+}
+
+// ---- fp32 -> three bf16 terms (x = h + m + l up to 2^-24 relative) ----------------------------------
+// Packs two values: result words hold (even element in the low half, odd element in the high half).
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void split3(float x0, float x1, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+  w1 = pack_bf16x2(x0, x1);
+  float r0 = x0 - __uint_as_float(w1 << 16);
+  float r1 = x1 - __uint_as_float(w1 & 0xFFFF0000u);
+  w2 = pack_bf16x2(r0, r1);
+  r0 -= __uint_as_float(w2 << 16);
+  r1 -= __uint_as_float(w2 & 0xFFFF0000u);
+  w3 = pack_bf16x2(r0, r1);
+}
+
+}  // namespace tc
+}  // namespace ikr
+#endif  // IKR_TC_CUH_

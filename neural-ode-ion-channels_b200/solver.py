@@ -31,7 +31,7 @@ from .protocols import compact_table
 
 _ADAPTIVE_OPTS = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps'}
 _FIXED_OPTS = {'step_size', 'perturb'}
-_EXT_OPTS = {'tile_m', 'check_status', 'compact_table', 'ckpt_cap', 'lane_pool'}
+_EXT_OPTS = {'tile_m', 'check_status', 'compact_table', 'ckpt_cap', 'lane_pool', 'tensor_cores'}
 
 
 # =============================================================================================
@@ -150,7 +150,8 @@ def _make_desc(spec: ModelSpec, state_dtype, method, rtol, atol, opts, time_f32=
     d.dfactor = float(opts.get('dfactor', 0.2))
     d.max_num_steps = int(opts.get('max_num_steps', 2 ** 31 - 1))
     d.tile_m = int(opts.get('tile_m', 0))
-    d.reserved = 1 if opts.get('lane_pool', False) else 0
+    # bit 0: lane-pool kernel; bit 1: keep the fp32 MLP on the FFMA2 kernel (no tcgen05 path)
+    d.reserved = (1 if opts.get('lane_pool', False) else 0) | (0 if opts.get('tensor_cores', True) else 2)
     return d
 
 
