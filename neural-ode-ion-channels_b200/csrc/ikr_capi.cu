@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -211,8 +212,11 @@ bool use_pool(const ikr_desc* d) { return d->method == IKR_DOPRI5 && (d->reserve
 struct TcPlan {
   bool ok;
   TcGeom g;
+  int groups;            // threads sharing one TMEM lane (epilogue column groups)
   size_t smem, img_bytes;
 };
+
+constexpr int kTcDefaultGroups = 3;
 
 TcPlan make_tc_plan(const ikr_desc* d) {
   TcPlan t;
@@ -221,9 +225,14 @@ TcPlan make_tc_plan(const ikr_desc* d) {
   t.g = tc_geometry(d->n_nodes, d->n_layers);
   if (d->mlp_dtype != IKR_F32 || (d->reserved & 2) || use_pool(d) || d->tile_m > 0) return t;
   if (!tc_geometry_ok(t.g)) return t;
-  const size_t fixed = d->state_dtype == IKR_F32 ? TcSmemLayout<float>(t.g, 0).total
-                                                  : TcSmemLayout<double>(t.g, 0).total;
-  if (fixed + (size_t)(kTcRefillLag + 2) * t.g.stage_bytes > kSmemLimit) return t;
+  t.groups = kTcDefaultGroups;
+  if (const char* e = getenv("IKR_TC_GROUPS")) {   // tuning / A-B runs
+    const int v = atoi(e);
+    if (v >= 1 && v <= 3) t.groups = v;
+  }
+  const size_t fixed = d->state_dtype == IKR_F32 ? TcSmemLayout<float>(t.g, 0, t.groups).total
+                                                  : TcSmemLayout<double>(t.g, 0, t.groups).total;
+  if (fixed + (size_t)kTcMinStages * t.g.stage_bytes > kSmemLimit) return t;
   int stages = (int)((kSmemLimit - fixed) / t.g.stage_bytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   t.g.stages = stages;
@@ -237,16 +246,23 @@ size_t fwd_fixed_workspace(int n_jobs) {
   return (256 + (size_t)n_jobs * sizeof(FwdJob) + 255) & ~(size_t)255;
 }
 
-template <typename S>
-int launch_forward_tc(const TcFwdParams& tp, const TcPlan& t, int grid, cudaStream_t st) {
-  auto kern = ikr_forward_tc_kernel<S>;
+template <typename S, int G>
+int launch_forward_tc_g(const TcFwdParams& tp, const TcPlan& t, int grid, cudaStream_t st) {
+  auto kern = ikr_forward_tc_kernel<S, G>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) !=
       cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
   }
-  kern<<<grid, kTcThreads, t.smem, st>>>(tp);
+  kern<<<grid, tc_threads(G), t.smem, st>>>(tp);
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
+template <typename S>
+int launch_forward_tc(const TcFwdParams& tp, const TcPlan& t, int grid, cudaStream_t st) {
+  if (t.groups == 1) return launch_forward_tc_g<S, 1>(tp, t, grid, st);
+  if (t.groups == 2) return launch_forward_tc_g<S, 2>(tp, t, grid, st);
+  return launch_forward_tc_g<S, 3>(tp, t, grid, st);
 }
 
 template <typename S, typename W, int TN>
@@ -540,7 +556,7 @@ int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int
     long long tiles = 0;
     for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + kTcM - 1) / kTcM;
     const int sms = device_sms();
-    out[0] = kTcM; out[1] = kTcThreads; out[2] = tiles < sms ? tiles : sms; out[3] = (int64_t)tcp.smem;
+    out[0] = kTcM; out[1] = tc_threads(tcp.groups); out[2] = tiles < sms ? tiles : sms; out[3] = (int64_t)tcp.smem;
     out[4] = tiles; out[5] = 16; out[6] = tcp.g.KST; out[7] = sms;
     return 0;
   }
@@ -597,7 +613,7 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
     g.n_tiles = 0;
     for (int j = 0; j < n_jobs; ++j) g.n_tiles += (Bs[j] + kTcM - 1) / kTcM;
     g.grid = (int)(g.n_tiles < g.sms ? g.n_tiles : g.sms);
-    g.threads = kTcThreads;
+    g.threads = tc_threads(tcp.groups);
     g.smem = tcp.smem;
   }
   if (g.smem > kSmemLimit || g.threads > kMaxThreads) return IKR_ERR_UNSUPPORTED;
@@ -651,6 +667,7 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
     tp.g = tcp.g;
     unsigned char* img = ws + fwd_fixed_workspace(n_jobs);
     tp.img = img;
+    tp.timing = getenv("IKR_TC_TIMING") != nullptr;
     TcPackParams pk;
     pk.wn = reinterpret_cast<const float*>(jobs[0].weights) + p.mlp.off_wn;
     pk.npad = p.mlp.npad;

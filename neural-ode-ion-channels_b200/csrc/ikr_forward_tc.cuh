@@ -5,11 +5,15 @@
 // thread per trajectory); the tile is fixed at M = 128 trajectories = the 128 TMEM lanes, and
 // thread i owns TMEM lane i, so the whole MLP needs NO cross-thread exchange:
 //
-//   layer 0      owner thread: h = LeakyReLU(w0a nv + w0b a + b0)           -> A operand (TMEM)
-//   layer 1..L   engine thread: D[128 x n] = A[128 x n] . W_l^T  (tcgen05.mma, B = W_l streamed
-//                L2 -> shared memory by cp.async.bulk through a full/empty mbarrier ring)
-//                owner thread: tcgen05.ld its D row, + bias, LeakyReLU      -> A operand (TMEM)
-//   output       owner thread: dot(h, w_last) + b_last while reading the last D row
+//   layer 0      lane threads: h = LeakyReLU(w0a nv + w0b a + b0)           -> A operand (TMEM)
+//   layer 1..L   MMA thread: D[128 x n] = A[128 x n] . W_l^T  (tcgen05.mma, B = W_l streamed
+//                L2 -> shared memory by cp.async.bulk through a full/empty mbarrier ring that a
+//                separate producer thread keeps full)
+//                lane threads: tcgen05.ld the D row, + bias, LeakyReLU      -> A operand (TMEM)
+//   output       lane threads: dot(h, w_last) while reading the last D row, owner adds b_last
+// G threads share one TMEM lane (column groups, warps w and w + 4 c see the same lane quarter):
+// they split the k-steps of every epilogue; the owner broadcasts (nv, a) and collects the G partial
+// output sums through shared memory.
 //
 // FP32 accuracy on BF16 tensor cores: every fp32 value x is split into three bf16 terms
 // x = x1 + x2 + x3 (exact to 2^-24 |x|), and each layer issues the six products whose weight is
@@ -24,23 +28,30 @@
 #ifndef IKR_FORWARD_TC_CUH_
 #define IKR_FORWARD_TC_CUH_
 
+#include <stdio.h>
+
 #include "ikr_forward.cuh"
 #include "ikr_tc.cuh"
 
 namespace ikr {
 
 constexpr int kTcM = 128;        // trajectories per tile = TMEM lanes
-constexpr int kTcThreads = 160;  // 4 owner warps + 1 engine warp
 constexpr int kTcMaxStages = 12;
-constexpr int kTcRefillLag = 2;  // ring slot of k-step q - lag is refilled after issuing k-step q
+constexpr int kTcMinStages = 4;
+// Threads: G column groups x 128 epilogue threads (group 0 = the owner threads of the trajectories;
+// thread 128 c + i of group c works on TMEM lane i and on the k-steps j = c (mod G)), then one
+// warp whose lane 0 issues the MMAs and one warp whose lane 0 streams the weight ring.
+__host__ __device__ constexpr int tc_threads(int G) { return 128 * G + 64; }
 
 struct TcGeom {
   int n, L, NP;      // NP = roundup(n, 16): D columns = rows of every B block
   int KSf;           // regular K = 16 steps per layer (incl. a zero-padded one when n % 16 > 8)
   int tail;          // 1: a final tail step covers the last n % 16 <= 8 features
   int KST;           // steps per layer = KSf + tail = ring stages consumed per layer
-  int col_a[3];      // TMEM column of the three bf16 terms of A (relative to the allocation base)
-  int col_t1, col_t2;
+  int units;         // epilogue work units: pairs of k-steps (the last one may hold a single k-step)
+  int col_a;         // TMEM column of the A operand: unit u at col_a + 48 u as [a1 | a2 | a3], each
+                     // 16 columns (two k-steps) -- or 8 columns each for a single-k-step unit
+  int col_t1, col_t2;  // tail blocks [a1t | a2t], [a1t | a3t] (adjacent: one 16-column store)
   int cols;          // TMEM columns used
   int block_bytes;   // one B block: NP x 16 bf16 = NP * 32 bytes
   int stage_bytes;   // one k-step: 3 blocks
@@ -56,11 +67,11 @@ __host__ __device__ inline TcGeom tc_geometry(int n, int L) {
   g.KSf = n / 16 + (rem > 8 ? 1 : 0);
   g.tail = (rem > 0 && rem <= 8) ? 1 : 0;
   g.KST = g.KSf + g.tail;
-  int c = g.NP;
-  for (int s = 0; s < 3; ++s) { g.col_a[s] = c; c += 8 * g.KSf; }
-  g.col_t1 = c; g.col_t2 = c + 8;
-  if (g.tail) c += 16;
-  g.cols = c;
+  g.units = (g.KSf + 1) / 2;
+  g.col_a = g.NP;
+  g.col_t1 = g.col_a + 24 * g.KSf;
+  g.col_t2 = g.col_t1 + 8;
+  g.cols = g.col_t1 + (g.tail ? 16 : 0);
   g.block_bytes = g.NP * 32;
   g.stage_bytes = 3 * g.block_bytes;
   g.stages = 0;
@@ -69,6 +80,12 @@ __host__ __device__ inline TcGeom tc_geometry(int n, int L) {
 }
 __host__ __device__ inline bool tc_geometry_ok(const TcGeom& g) {
   return g.n >= 16 && g.NP <= 256 && g.cols <= (int)tc::kTmemCols && g.KST >= 1;
+}
+// TMEM column (relative to the allocation) of bf16 term t of k-step j
+__host__ __device__ inline int tc_a_col(const TcGeom& g, int t, int j) {
+  const int u = j >> 1;
+  const bool full = 2 * u + 1 < g.KSf;
+  return g.col_a + 48 * u + (full ? 16 * t + 8 * (j & 1) : 8 * t);
 }
 
 // ---- weight image: [layer][k-step][block 0..2][NP x 16 bf16 in core-matrix order] -----------------
@@ -119,14 +136,16 @@ __global__ void ikr_tc_pack_kernel(const TcPackParams p) {
 // ---- shared memory carve-up --------------------------------------------------------------------------
 template <typename S>
 struct TcSmemLayout {
-  size_t off_bar, off_misc, off_job, off_lanes, off_obs, off_sp, off_ring, total;
-  __host__ __device__ TcSmemLayout(const TcGeom& g, int stages) {
+  size_t off_bar, off_misc, off_job, off_lanes, off_obs, off_xin, off_part, off_sp, off_ring, total;
+  __host__ __device__ TcSmemLayout(const TcGeom& g, int stages, int G) {
     size_t o = 0;
     off_bar = o; o += (size_t)(2 * kTcMaxStages + 2) * 8;          // full[], empty[], a_ready, d_ready
     off_misc = o; o += 32;                                          // tmem base, stop flag, tile slot
     off_job = o; o += (sizeof(FwdJob) + 15) & ~(size_t)15;
     off_lanes = o; o += (size_t)kTcM * sizeof(Lane<S>); o = (o + 15) & ~(size_t)15;
     off_obs = o; o += (size_t)kTcM * 2 * sizeof(double);
+    off_xin = o; o += (size_t)kTcM * 2 * sizeof(float);
+    off_part = o; o += (size_t)G * kTcM * sizeof(float);
     off_sp = o; o += (size_t)g.small_elems * sizeof(float); o = (o + 127) & ~(size_t)127;
     off_ring = o; o += (size_t)stages * g.stage_bytes;
     total = o;
@@ -137,16 +156,19 @@ struct TcFwdParams {
   FwdParams f;           // f.M == 128; MG / NG / n_worker_warps unused
   TcGeom g;
   const void* img;       // weight image written by ikr_tc_pack_kernel
+  int timing;            // debug: block 0 prints its phase clocks (IKR_TC_TIMING=1)
 };
 
-// named barrier over the 128 owner threads (the engine warp never joins it)
-__device__ __forceinline__ void owners_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barriers: 1 = every lane thread (128 G), 2 = the 128 owner threads
+template <int G>
+__device__ __forceinline__ void lanes_sync() { asm volatile("bar.sync 1, %0;" ::"n"(128 * G) : "memory"); }
+__device__ __forceinline__ void owners_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 __device__ __forceinline__ int owners_or(int pred) {
   uint32_t r;
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.u32 q, %1, 0;\n\t"
-      "bar.red.or.pred p, 1, 128, q;\n\t"
+      "bar.red.or.pred p, 2, 128, q;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(r)
       : "r"(pred)
@@ -154,37 +176,22 @@ __device__ __forceinline__ int owners_or(int pred) {
   return (int)r;
 }
 
-// Per-owner view of the tensor-core MLP
+// Per-thread view of the tensor-core MLP
 struct TcLane {
   uint32_t taddr;        // TMEM address of this thread's lane, column 0 of the allocation
-  uint32_t bar_a, bar_d; // shared-memory addresses of the a_ready / d_ready mbarriers
-  uint64_t* bar_d_ptr;
+  uint32_t bar_a;        // shared-memory address of the a_ready mbarrier
+  uint64_t* bar_d;       // d_ready mbarrier
   unsigned phase_d;      // parity of the next d_ready completion
+  int group;             // column group 0..G-1
+  int lane;              // TMEM lane 0..127
   const float* sp;       // small parameters (stride NP): w0a | w0b | b0 | L x bias | w_last, b_last
+  float* xin;            // [128][2] (nv, a) broadcast by the owner
+  float* part;           // [G][128] partial output sums
   float slope;
+  long long c_l0, c_wait, c_epi;   // phase clocks (timing runs)
 };
 
 __device__ __forceinline__ float tc_leaky(float x, float slope) { return x > 0.0f ? x : x * slope; }
-
-// write 16 consecutive activations (features 16 j .. 16 j + 15) as the three bf16 terms of A
-__device__ __forceinline__ void tc_store_step(const TcGeom& g, uint32_t taddr, int j, const float (&h)[16]) {
-  uint32_t w1[8], w2[8], w3[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) tc::split3(h[2 * q], h[2 * q + 1], w1[q], w2[q], w3[q]);
-  tc::st8(taddr + g.col_a[0] + 8 * j, w1);
-  tc::st8(taddr + g.col_a[1] + 8 * j, w2);
-  tc::st8(taddr + g.col_a[2] + 8 * j, w3);
-}
-// write the 8 tail activations as the blocks [a1t | a2t] and [a1t | a3t]
-__device__ __forceinline__ void tc_store_tail(const TcGeom& g, uint32_t taddr, const float (&h)[8]) {
-  uint32_t u1[4], u2[4], u3[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) tc::split3(h[2 * q], h[2 * q + 1], u1[q], u2[q], u3[q]);
-  const uint32_t t1[8] = {u1[0], u1[1], u1[2], u1[3], u2[0], u2[1], u2[2], u2[3]};
-  const uint32_t t2[8] = {u1[0], u1[1], u1[2], u1[3], u3[0], u3[1], u3[2], u3[3]};
-  tc::st8(taddr + g.col_t1, t1);
-  tc::st8(taddr + g.col_t2, t2);
-}
 
 __device__ __forceinline__ void tc_publish_a(const TcLane& tl) {
   tc::wait_st();
@@ -192,178 +199,192 @@ __device__ __forceinline__ void tc_publish_a(const TcLane& tl) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
 }
 
-// MLP of the trajectory owned by this thread; every owner thread of the CTA must call it
-// (masked lanes included: the a_ready barrier counts 128 arrivals).
-__device__ __forceinline__ float tc_mlp_eval(const TcGeom& g, TcLane& tl, float nv, float a) {
-  const int NP = g.NP;
+// One epilogue work unit of NK = 1 or 2 k-steps (16 NK features starting at feature c0): the
+// pre-activations arrive in v (raw fp32 bits: D columns, or layer-0 sums), get bias + LeakyReLU,
+// and either become the next A operand (three bf16 terms, written with one 16 NK-column store for
+// [a1 | a2] and one 8 NK-column store for a3) or are reduced against w_last.
+template <int NK>
+__device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl, int u, const float* bias,
+                                               uint32_t (&v)[16 * NK], bool last, const float* wl,
+                                               float (&s)[4]) {
+  const int c0 = 32 * u;
   const float slope = tl.slope;
+#pragma unroll
+  for (int q = 0; q < 4 * NK; ++q) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
+    v[4 * q + 0] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 0]) + bb.x, slope));
+    v[4 * q + 1] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 1]) + bb.y, slope));
+    v[4 * q + 2] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 2]) + bb.z, slope));
+    v[4 * q + 3] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 3]) + bb.w, slope));
+  }
+  if (!last) {
+    uint32_t w12[16 * NK], w3[8 * NK];
+#pragma unroll
+    for (int q = 0; q < 8 * NK; ++q)
+      tc::split3(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), w12[q], w12[8 * NK + q], w3[q]);
+    const uint32_t dst = tl.taddr + g.col_a + 48 * u;
+    if (NK == 2) {
+      tc::st32(dst, reinterpret_cast<uint32_t(&)[32]>(w12));
+      tc::st16(dst + 32, reinterpret_cast<uint32_t(&)[16]>(w3));
+    } else {
+      tc::st16(dst, reinterpret_cast<uint32_t(&)[16]>(w12));
+      tc::st8(dst + 16, reinterpret_cast<uint32_t(&)[8]>(w3));
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4 * NK; ++q) {
+      const float4 ww = *reinterpret_cast<const float4*>(wl + c0 + 4 * q);
+      s[0] = __fmaf_rn(__uint_as_float(v[4 * q + 0]), ww.x, s[0]);
+      s[1] = __fmaf_rn(__uint_as_float(v[4 * q + 1]), ww.y, s[1]);
+      s[2] = __fmaf_rn(__uint_as_float(v[4 * q + 2]), ww.z, s[2]);
+      s[3] = __fmaf_rn(__uint_as_float(v[4 * q + 3]), ww.w, s[3]);
+    }
+  }
+}
+// the 8 tail features (columns 16 KSf ..): blocks [a1t | a2t | a1t | a3t] in one 16-column store
+__device__ __forceinline__ void tc_tail_finish(const TcGeom& g, const TcLane& tl, const float* bias,
+                                               uint32_t (&v)[8], bool last, const float* wl, float (&s)[4]) {
+  const int c0 = 16 * g.KSf;
+  const float slope = tl.slope;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
+    v[4 * q + 0] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 0]) + bb.x, slope));
+    v[4 * q + 1] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 1]) + bb.y, slope));
+    v[4 * q + 2] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 2]) + bb.z, slope));
+    v[4 * q + 3] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 3]) + bb.w, slope));
+  }
+  if (!last) {
+    uint32_t t[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      tc::split3(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), t[q], t[4 + q], t[12 + q]);
+      t[8 + q] = t[q];
+    }
+    tc::st16(tl.taddr + g.col_t1, t);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 ww = *reinterpret_cast<const float4*>(wl + c0 + 4 * q);
+      s[0] = __fmaf_rn(__uint_as_float(v[4 * q + 0]), ww.x, s[0]);
+      s[1] = __fmaf_rn(__uint_as_float(v[4 * q + 1]), ww.y, s[1]);
+      s[2] = __fmaf_rn(__uint_as_float(v[4 * q + 2]), ww.z, s[2]);
+      s[3] = __fmaf_rn(__uint_as_float(v[4 * q + 3]), ww.w, s[3]);
+    }
+  }
+}
+
+// layer-0 pre-activations (without the bias, which tc_*_finish adds) of NV features from c0
+template <int NV>
+__device__ __forceinline__ void tc_layer0_sums(const TcLane& tl, int NP, int c0, float nv, float a,
+                                               uint32_t (&v)[NV]) {
+  const float* w0a = tl.sp + c0;
+  const float* w0b = tl.sp + NP + c0;
+#pragma unroll
+  for (int q = 0; q < NV / 4; ++q) {
+    const float4 wa = *reinterpret_cast<const float4*>(w0a + 4 * q);
+    const float4 wb = *reinterpret_cast<const float4*>(w0b + 4 * q);
+    v[4 * q + 0] = __float_as_uint(__fmaf_rn(wb.x, a, wa.x * nv));
+    v[4 * q + 1] = __float_as_uint(__fmaf_rn(wb.y, a, wa.y * nv));
+    v[4 * q + 2] = __float_as_uint(__fmaf_rn(wb.z, a, wa.z * nv));
+    v[4 * q + 3] = __float_as_uint(__fmaf_rn(wb.w, a, wa.w * nv));
+  }
+}
+
+// One MLP evaluation of the 128-trajectory tile, executed by EVERY lane thread (all G groups, masked
+// lanes included: the a_ready barrier counts 128 G arrivals).  The caller has published (nv, a) in
+// tl.xin and passed the lanes barrier; the partial output sums land in tl.part (caller syncs).
+// Group c works on the contiguous unit range [c upg, (c + 1) upg); the last group adds the tail.
+template <int G>
+__device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl) {
+  const int NP = g.NP;
+  const float2 in = *reinterpret_cast<const float2*>(tl.xin + 2 * tl.lane);
+  const float nv = in.x, a = in.y;
+  const int upg = (g.units + G - 1) / G;
+  const int u_begin = tl.group * upg;
+  const int u_end = min(g.units, u_begin + upg);
+  const bool tail_mine = g.tail && tl.group == G - 1;
+  float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  const float* wl = tl.sp + (size_t)(3 + g.L) * NP;
+  long long c0 = clock64();
   // ---- layer 0 ------------------------------------------------------------------------------
   {
-    const float* w0a = tl.sp;
-    const float* w0b = tl.sp + NP;
     const float* b0 = tl.sp + 2 * NP;
-    for (int j = 0; j < g.KSf; ++j) {
-      float h[16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 wa = *reinterpret_cast<const float4*>(w0a + 16 * j + 4 * q);
-        const float4 wb = *reinterpret_cast<const float4*>(w0b + 16 * j + 4 * q);
-        const float4 bb = *reinterpret_cast<const float4*>(b0 + 16 * j + 4 * q);
-        h[4 * q + 0] = tc_leaky(__fmaf_rn(wb.x, a, __fmaf_rn(wa.x, nv, bb.x)), slope);
-        h[4 * q + 1] = tc_leaky(__fmaf_rn(wb.y, a, __fmaf_rn(wa.y, nv, bb.y)), slope);
-        h[4 * q + 2] = tc_leaky(__fmaf_rn(wb.z, a, __fmaf_rn(wa.z, nv, bb.z)), slope);
-        h[4 * q + 3] = tc_leaky(__fmaf_rn(wb.w, a, __fmaf_rn(wa.w, nv, bb.w)), slope);
+    for (int u = u_begin; u < u_end; ++u) {
+      if (2 * u + 1 < g.KSf) {
+        uint32_t v[32];
+        tc_layer0_sums<32>(tl, NP, 32 * u, nv, a, v);
+        tc_unit_finish<2>(g, tl, u, b0, v, false, wl, s);
+      } else {
+        uint32_t v[16];
+        tc_layer0_sums<16>(tl, NP, 32 * u, nv, a, v);
+        tc_unit_finish<1>(g, tl, u, b0, v, false, wl, s);
       }
-      tc_store_step(g, tl.taddr, j, h);
     }
-    if (g.tail) {
-      float h[8];
-      const int c0 = 16 * g.KSf;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const float4 wa = *reinterpret_cast<const float4*>(w0a + c0 + 4 * q);
-        const float4 wb = *reinterpret_cast<const float4*>(w0b + c0 + 4 * q);
-        const float4 bb = *reinterpret_cast<const float4*>(b0 + c0 + 4 * q);
-        h[4 * q + 0] = tc_leaky(__fmaf_rn(wb.x, a, __fmaf_rn(wa.x, nv, bb.x)), slope);
-        h[4 * q + 1] = tc_leaky(__fmaf_rn(wb.y, a, __fmaf_rn(wa.y, nv, bb.y)), slope);
-        h[4 * q + 2] = tc_leaky(__fmaf_rn(wb.z, a, __fmaf_rn(wa.z, nv, bb.z)), slope);
-        h[4 * q + 3] = tc_leaky(__fmaf_rn(wb.w, a, __fmaf_rn(wa.w, nv, bb.w)), slope);
-      }
-      tc_store_tail(g, tl.taddr, h);
+    if (tail_mine) {
+      uint32_t v[8];
+      tc_layer0_sums<8>(tl, NP, 16 * g.KSf, nv, a, v);
+      tc_tail_finish(g, tl, b0, v, false, wl, s);
     }
     tc_publish_a(tl);
   }
+  { const long long c1 = clock64(); tl.c_l0 += c1 - c0; c0 = c1; }
   // ---- hidden layers: read D, bias + LeakyReLU, write the next A (or reduce the output) -----------
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-  const float* wl = tl.sp + (size_t)(3 + g.L) * NP;
   for (int layer = 0; layer < g.L; ++layer) {
     const float* bias = tl.sp + (size_t)(3 + layer) * NP;
     const bool last = layer + 1 == g.L;
-    mbar_wait(tl.bar_d_ptr, tl.phase_d);
+    mbar_wait(tl.bar_d, tl.phase_d);
     tl.phase_d ^= 1u;
     tc::fence_after_sync();
-    for (int j = 0; j < g.KSf; ++j) {
-      uint32_t v[16];
-      tc::ld16(tl.taddr + 16 * j, v);
-      tc::wait_ld();
-      float h[16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 bb = *reinterpret_cast<const float4*>(bias + 16 * j + 4 * q);
-        h[4 * q + 0] = tc_leaky(__uint_as_float(v[4 * q + 0]) + bb.x, slope);
-        h[4 * q + 1] = tc_leaky(__uint_as_float(v[4 * q + 1]) + bb.y, slope);
-        h[4 * q + 2] = tc_leaky(__uint_as_float(v[4 * q + 2]) + bb.z, slope);
-        h[4 * q + 3] = tc_leaky(__uint_as_float(v[4 * q + 3]) + bb.w, slope);
-      }
-      if (!last) {
-        tc_store_step(g, tl.taddr, j, h);
+    { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
+    for (int u = u_begin; u < u_end; ++u) {
+      if (2 * u + 1 < g.KSf) {
+        uint32_t v[32];
+        tc::ld32(tl.taddr + 32 * u, v);
+        tc::wait_ld();
+        tc_unit_finish<2>(g, tl, u, bias, v, last, wl, s);
       } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 ww = *reinterpret_cast<const float4*>(wl + 16 * j + 4 * q);
-          s0 = __fmaf_rn(h[4 * q + 0], ww.x, s0);
-          s1 = __fmaf_rn(h[4 * q + 1], ww.y, s1);
-          s2 = __fmaf_rn(h[4 * q + 2], ww.z, s2);
-          s3 = __fmaf_rn(h[4 * q + 3], ww.w, s3);
-        }
+        uint32_t v[16];
+        tc::ld16(tl.taddr + 32 * u, v);
+        tc::wait_ld();
+        tc_unit_finish<1>(g, tl, u, bias, v, last, wl, s);
       }
     }
-    if (g.tail) {
+    if (tail_mine) {
       uint32_t v[8];
-      const int c0 = 16 * g.KSf;
-      tc::ld8(tl.taddr + c0, v);
+      tc::ld8(tl.taddr + 16 * g.KSf, v);
       tc::wait_ld();
-      float h[8];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-        h[4 * q + 0] = tc_leaky(__uint_as_float(v[4 * q + 0]) + bb.x, slope);
-        h[4 * q + 1] = tc_leaky(__uint_as_float(v[4 * q + 1]) + bb.y, slope);
-        h[4 * q + 2] = tc_leaky(__uint_as_float(v[4 * q + 2]) + bb.z, slope);
-        h[4 * q + 3] = tc_leaky(__uint_as_float(v[4 * q + 3]) + bb.w, slope);
-      }
-      if (!last) {
-        tc_store_tail(g, tl.taddr, h);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const float4 ww = *reinterpret_cast<const float4*>(wl + c0 + 4 * q);
-          s0 = __fmaf_rn(h[4 * q + 0], ww.x, s0);
-          s1 = __fmaf_rn(h[4 * q + 1], ww.y, s1);
-          s2 = __fmaf_rn(h[4 * q + 2], ww.z, s2);
-          s3 = __fmaf_rn(h[4 * q + 3], ww.w, s3);
-        }
-      }
+      tc_tail_finish(g, tl, bias, v, last, wl, s);
     }
     if (!last) tc_publish_a(tl);
+    { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
   }
-  return ((s0 + s1) + (s2 + s3)) + wl[NP];
+  tl.part[tl.group * kTcM + tl.lane] = (s[0] + s[1]) + (s[2] + s[3]);
 }
 
-// ---- engine thread: weight ring + MMA issue -----------------------------------------------------------
-struct TcEngine {
-  uint64_t* full;
-  uint64_t* empty;
-  unsigned char* ring;
-  const unsigned char* img;
-  unsigned issued, consumed;   // k-steps (global sequence numbers)
-  unsigned steps_per_cycle;    // L * KST
-};
-
-__device__ __forceinline__ void tc_engine_issue_copy(const TcGeom& g, TcEngine& e) {
-  const unsigned q = e.issued;
-  const unsigned s = q % (unsigned)g.stages;
-  const unsigned src = q % e.steps_per_cycle;
-  mbar_expect_tx(&e.full[s], (unsigned)g.stage_bytes);
-  bulk_g2s(e.ring + (size_t)s * g.stage_bytes, e.img + (size_t)src * g.stage_bytes,
-           (unsigned)g.stage_bytes, &e.full[s]);
-  e.issued = q + 1;
+// Owner-side wrapper: publish the inputs, run the evaluation with the helper groups, collect.
+template <int G>
+__device__ __forceinline__ float tc_owner_eval(const TcGeom& g, TcLane& tl, float nv, float a) {
+  *reinterpret_cast<float2*>(tl.xin + 2 * tl.lane) = make_float2(nv, a);
+  if (G > 1) lanes_sync<G>();        // inputs visible to the helper groups (cmd word = run)
+  tc_mlp_eval<G>(g, tl);
+  if (G > 1) lanes_sync<G>();        // partial sums visible
+  float out = tl.part[tl.lane];
+#pragma unroll
+  for (int c = 1; c < G; ++c) out += tl.part[c * kTcM + tl.lane];
+  return out + tl.sp[(size_t)(4 + g.L) * g.NP];
 }
 
-// all MMAs of one hidden layer
-__device__ __forceinline__ void tc_engine_layer(const TcGeom& g, TcEngine& e, uint32_t tbase, uint32_t idesc) {
-  for (int j = 0; j < g.KST; ++j) {
-    const unsigned q = e.consumed;
-    const unsigned s = q % (unsigned)g.stages;
-    mbar_wait(&e.full[s], (q / (unsigned)g.stages) & 1u);
-    tc::fence_after_sync();
-    const uint32_t sb = smem_u32(e.ring + (size_t)s * g.stage_bytes);
-    const uint64_t b1 = tc::smem_desc(sb, 128, 256);
-    const uint64_t b2 = tc::smem_desc(sb + g.block_bytes, 128, 256);
-    const uint64_t b3 = tc::smem_desc(sb + 2 * g.block_bytes, 128, 256);
-    if (j < g.KSf) {
-      const uint32_t a1 = tbase + g.col_a[0] + 8 * j, a2 = tbase + g.col_a[1] + 8 * j,
-                     a3 = tbase + g.col_a[2] + 8 * j;
-      tc::mma_ts(tbase, a1, b1, idesc, j > 0 ? 1u : 0u);
-      tc::mma_ts(tbase, a2, b1, idesc, 1u);
-      tc::mma_ts(tbase, a3, b1, idesc, 1u);
-      tc::mma_ts(tbase, a1, b2, idesc, 1u);
-      tc::mma_ts(tbase, a2, b2, idesc, 1u);
-      tc::mma_ts(tbase, a1, b3, idesc, 1u);
-    } else {
-      tc::mma_ts(tbase, tbase + g.col_t1, b1, idesc, j > 0 ? 1u : 0u);
-      tc::mma_ts(tbase, tbase + g.col_t1, b2, idesc, 1u);
-      tc::mma_ts(tbase, tbase + g.col_t2, b3, idesc, 1u);
-    }
-    tc::commit(smem_u32(&e.empty[s]));
-    e.consumed = q + 1;
-    if (q >= (unsigned)kTcRefillLag) {
-      const unsigned qp = q - kTcRefillLag;      // its MMAs are (nearly) complete
-      if (qp + g.stages == e.issued) {
-        mbar_wait(&e.empty[qp % (unsigned)g.stages], (qp / (unsigned)g.stages) & 1u);
-        tc_engine_issue_copy(g, e);
-      }
-    }
-  }
-}
-
-template <typename S>
-__global__ void __launch_bounds__(kTcThreads, 1) ikr_forward_tc_kernel(const TcFwdParams tp) {
+template <typename S, int G>
+__global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const TcFwdParams tp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const FwdParams& p = tp.f;
   const TcGeom g = tp.g;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const TcSmemLayout<S> lay(g, g.stages);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
+  constexpr int kLaneThreads = 128 * G;
+  constexpr int kMmaWarp = 4 * G, kLoadWarp = 4 * G + 1;
+  const TcSmemLayout<S> lay(g, g.stages, G);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + lay.off_bar);
   uint64_t* bar_full = bars;
   uint64_t* bar_empty = bars + kTcMaxStages;
@@ -372,32 +393,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) ikr_forward_tc_kernel(const TcF
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + lay.off_misc);
   volatile int* stop_flag = reinterpret_cast<volatile int*>(smem_raw + lay.off_misc + 4);
   long long* tile_slot = reinterpret_cast<long long*>(smem_raw + lay.off_misc + 8);
+  volatile int* cmd_exit = reinterpret_cast<volatile int*>(smem_raw + lay.off_misc + 16);
   FwdJob* jobp = reinterpret_cast<FwdJob*>(smem_raw + lay.off_job);
   Lane<S>* lanes = reinterpret_cast<Lane<S>*>(smem_raw + lay.off_lanes);
   double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);
   float* sp = reinterpret_cast<float*>(smem_raw + lay.off_sp);
   unsigned char* ring = smem_raw + lay.off_ring;
+  const unsigned stages = (unsigned)g.stages;
 
   // ---- one-time setup ------------------------------------------------------------------------------
-  if (tid == kTcM) {
+  if (tid == 0) {
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    mbar_init(bar_a, kTcM);
+    mbar_init(bar_a, kLaneThreads);
     mbar_init(bar_d, 1);
     mbar_fence_init();
     *stop_flag = 0;
+    *cmd_exit = 0;
   }
-  if (warp == 4) {
-    __syncwarp();
-    tc::tmem_alloc(smem_u32(tmem_slot), tc::kTmemCols);
-  }
+  if (warp == kMmaWarp) tc::tmem_alloc(smem_u32(tmem_slot), tc::kTmemCols);
   {
     // small parameters, zero-padded to stride NP
     const float* P = reinterpret_cast<const float*>(p.mlp.base);
     const int NP = g.NP, npad = p.mlp.npad, n = g.n;
-    for (int i = tid; i < g.small_elems; i += kTcThreads) {
+    for (int i = tid; i < g.small_elems; i += tc_threads(G)) {
       const int row = i / NP, c = i - row * NP;
       float v = 0.0f;
       if (row < 3) { if (c < n) v = P[p.mlp.off_w0 + (long long)row * npad + c]; }
@@ -412,181 +433,255 @@ __global__ void __launch_bounds__(kTcThreads, 1) ikr_forward_tc_kernel(const TcF
   tc::fence_after_sync();
   const uint32_t tbase = *tmem_slot;
 
-  if (warp == 4) {
-    // ================================ engine ===========================================================
-    if (tid == kTcM) {
-      TcEngine e;
-      e.full = bar_full; e.empty = bar_empty; e.ring = ring;
-      e.img = reinterpret_cast<const unsigned char*>(tp.img);
-      e.issued = 0; e.consumed = 0;
-      e.steps_per_cycle = (unsigned)(g.L * g.KST);
-      const uint32_t idesc = tc::idesc_bf16_f32(kTcM, g.NP);
-      for (int s = 0; s < g.stages; ++s) tc_engine_issue_copy(g, e);
-      unsigned phase_a = 0;
-      while (true) {
-        mbar_wait(bar_a, phase_a);
-        phase_a ^= 1u;
-        if (*stop_flag) break;
+  if (warp == kMmaWarp) {
+    // ================================ MMA issuer ========================================================
+    // The whole warp runs the loop (warp-uniform control flow and operands => the descriptors live in
+    // uniform registers and each MMA is one UTCHMMA); one elected lane issues the MMAs and commits.
+    const uint32_t idesc = tc::idesc_bf16_f32(kTcM, g.NP);
+    const uint64_t desc0 = tc::smem_desc(smem_u32(ring), 128, 256);
+    const uint32_t blk16 = (uint32_t)g.block_bytes >> 4, stage16 = (uint32_t)g.stage_bytes >> 4;
+    const uint32_t a_base = tbase + g.col_a;
+    unsigned s = 0, round = 0, consumed = 0, phase_a = 0;
+    long long e_wait = 0, e_issue = 0, ec = clock64();
+    while (true) {
+      mbar_wait(bar_a, phase_a);
+      phase_a ^= 1u;
+      if (*stop_flag) break;
+      tc::fence_after_sync();
+      { const long long c1 = clock64(); e_wait += c1 - ec; ec = c1; }
+#pragma unroll 1
+      for (int j = 0; j < g.KST; ++j) {
+        mbar_wait(&bar_full[s], round);
         tc::fence_after_sync();
-        tc_engine_layer(g, e, tbase, idesc);
-        tc::commit(smem_u32(bar_d));
+        if (tc::elect_one()) {
+          const uint64_t b1 = desc0 + (uint64_t)(s * stage16);
+          const uint64_t b2 = b1 + blk16, b3 = b2 + blk16;
+          if (j < g.KSf) {
+            const bool full = (j | 1) < g.KSf;
+            const uint32_t a1 = a_base + 48 * (j >> 1) + (full ? 8 * (j & 1) : 0);
+            const uint32_t dt = full ? 16u : 8u;
+            tc::mma_ts(tbase, a1, b1, idesc, j > 0 ? 1u : 0u);
+            tc::mma_ts(tbase, a1 + dt, b1, idesc, 1u);
+            tc::mma_ts(tbase, a1 + 2 * dt, b1, idesc, 1u);
+            tc::mma_ts(tbase, a1, b2, idesc, 1u);
+            tc::mma_ts(tbase, a1 + dt, b2, idesc, 1u);
+            tc::mma_ts(tbase, a1, b3, idesc, 1u);
+          } else {
+            tc::mma_ts(tbase, tbase + g.col_t1, b1, idesc, j > 0 ? 1u : 0u);
+            tc::mma_ts(tbase, tbase + g.col_t1, b2, idesc, 1u);
+            tc::mma_ts(tbase, tbase + g.col_t2, b3, idesc, 1u);
+          }
+          tc::commit(smem_u32(&bar_empty[s]));   // slot free once these MMAs have read it
+        }
+        __syncwarp();
+        ++consumed;
+        if (++s == stages) { s = 0; round ^= 1u; }
       }
-      // every MMA has completed (its D was consumed); wait for the copies still in flight
-      for (unsigned q = e.consumed; q < e.issued; ++q)
-        mbar_wait(&bar_full[q % (unsigned)g.stages], (q / (unsigned)g.stages) & 1u);
+      if (tc::elect_one()) tc::commit(smem_u32(bar_d));
+      __syncwarp();
+      { const long long c1 = clock64(); e_issue += c1 - ec; ec = c1; }
+    }
+    // stop: every MMA has completed (its D was consumed).  The producer can only be blocked on the
+    // slot of the next k-step to consume: complete that phase by hand (it re-checks the flag).
+    if (tc::elect_one()) {
+      mbar_arrive(&bar_empty[s]);
+      if (tp.timing && blockIdx.x == 0)
+        printf("[tc timing] mma warp: wait_a %lld issue %lld cycles, %u k-steps\n", e_wait, e_issue, consumed);
+    }
+    __syncwarp();
+  } else if (warp == kLoadWarp) {
+    // ================================ weight producer ===================================================
+    if ((tid & 31) == 0) {
+      const unsigned char* img = reinterpret_cast<const unsigned char*>(tp.img);
+      const unsigned per_cycle = (unsigned)(g.L * g.KST);
+      unsigned issued = 0;
+      for (;; ++issued) {
+        const unsigned q = issued, s = q % stages;
+        if (q >= stages) mbar_wait(&bar_empty[s], ((q / stages) - 1u) & 1u);
+        if (*stop_flag) break;
+        mbar_expect_tx(&bar_full[s], (unsigned)g.stage_bytes);
+        bulk_g2s(ring + (size_t)s * g.stage_bytes, img + (size_t)(q % per_cycle) * g.stage_bytes,
+                 (unsigned)g.stage_bytes, &bar_full[s]);
+      }
+      // wait for the copies still in flight (the last `stages` issued chunks cover every slot once)
+      for (unsigned q = issued > stages ? issued - stages : 0; q < issued; ++q)
+        mbar_wait(&bar_full[q % stages], (q / stages) & 1u);
     }
   } else {
-    // ================================ owners ===========================================================
+    // ================================ lane threads ======================================================
     TcLane tl;
-    tl.taddr = tbase + ((uint32_t)(warp * 32) << 16);
+    tl.group = warp >> 2;
+    tl.lane = tid & 127;
+    tl.taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
     tl.bar_a = smem_u32(bar_a);
-    tl.bar_d = smem_u32(bar_d);
-    tl.bar_d_ptr = bar_d;
+    tl.bar_d = bar_d;
     tl.phase_d = 0;
     tl.sp = sp;
+    tl.xin = reinterpret_cast<float*>(smem_raw + lay.off_xin);
+    tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
     tl.slope = (float)p.mlp.slope;
-    SolverCfg cfg = p.cfg;
+    tl.c_l0 = tl.c_wait = tl.c_epi = 0;
+    const long long c_begin = clock64();
 
-    while (true) {
-      if (tid == 0) {
-        long long tile = (long long)atomicAdd(p.queue, 1ULL);
-        *tile_slot = tile;
-        if (tile < p.n_tiles) {
-          int j = 0;
-          while (j + 1 < p.n_jobs && p.jobs[j + 1].tile_begin <= tile) ++j;
-          *jobp = p.jobs[j];
-        }
+    if (tl.group > 0) {
+      // ---- helper groups: evaluate on command until the owners say exit -----------------------------
+      while (true) {
+        lanes_sync<G>();
+        if (*cmd_exit) break;
+        tc_mlp_eval<G>(g, tl);
+        lanes_sync<G>();
       }
-      owners_sync();
-      const long long tile = *tile_slot;
-      if (tile >= p.n_tiles) break;
-      const FwdJob& job = *jobp;
-      cfg.tab = job.tab;
-      const S* y0 = reinterpret_cast<const S*>(job.y0);
-      const S* gptr = reinterpret_cast<const S*>(job.g);
-      const S* eptr = reinterpret_cast<const S*>(job.e_rev);
-      const S* dptr = reinterpret_cast<const S*>(job.data);
-      S* y_out = reinterpret_cast<S*>(job.y_out);
-      S* i_out = reinterpret_cast<S*>(job.i_out);
-      S* ckpt_y = reinterpret_cast<S*>(job.ckpt_y);
-      const bool observe = (job.v_out != nullptr) && (job.i_out != nullptr || job.loss_out != nullptr);
-      const long long jB = job.B;
-      const int T = job.T;
-      const long long b = (tile - job.tile_begin) * kTcM + tid;
-      const bool valid = b < jB;
-      S g_b = (S)1, e_b = (S)job.e_scalar;
-
-      auto emit = [&](int idx, S a, S r) {
-        if (y_out) {
-          typename Vec2<S>::type v;
-          v.x = a; v.y = r;
-          *reinterpret_cast<typename Vec2<S>::type*>(y_out + ((size_t)idx * jB + b) * 2) = v;
-        }
-        if (observe) {
-          double cur = (double)(g_b * a * r) * (job.v_out[idx] - (double)e_b);
-          if (i_out) i_out[(size_t)idx * jB + b] = (S)cur;
-          if (dptr) {
-            double d = (double)dptr[(size_t)idx * job.data_B + (job.data_B == 1 ? 0 : b)];
-            double diff = cur - d;
-            obs[2 * tid] += diff * diff;
-            obs[2 * tid + 1] += fabs(diff);
+    } else {
+      // ---- owner threads: the solver ---------------------------------------------------------------
+      SolverCfg cfg = p.cfg;
+      while (true) {
+        if (tid == 0) {
+          long long tile = (long long)atomicAdd(p.queue, 1ULL);
+          *tile_slot = tile;
+          if (tile < p.n_tiles) {
+            int j = 0;
+            while (j + 1 < p.n_jobs && p.jobs[j + 1].tile_begin <= tile) ++j;
+            *jobp = p.jobs[j];
           }
         }
-      };
-      auto ckpt = [&](int step, const Lane<S>& lane) -> bool {
-        if (!job.ckpt_t) return true;
-        if (step >= job.ckpt_cap) return false;
-        size_t o = (size_t)step * jB + b;
-        double2 tt;
-        tt.x = lane.t0; tt.y = lane.dt;
-        *reinterpret_cast<double2*>(job.ckpt_t + 2 * o) = tt;
-        S buf[kCkptVals];
-        ckpt_pack<S>(lane, buf);
-        typedef typename Vec2<S>::type V2;
-        V2* dst = reinterpret_cast<V2*>(ckpt_y + (size_t)kCkptVals * o);
+        owners_sync();
+        const long long tile = *tile_slot;
+        if (tile >= p.n_tiles) break;
+        const FwdJob& job = *jobp;
+        cfg.tab = job.tab;
+        const S* y0 = reinterpret_cast<const S*>(job.y0);
+        const S* gptr = reinterpret_cast<const S*>(job.g);
+        const S* eptr = reinterpret_cast<const S*>(job.e_rev);
+        const S* dptr = reinterpret_cast<const S*>(job.data);
+        S* y_out = reinterpret_cast<S*>(job.y_out);
+        S* i_out = reinterpret_cast<S*>(job.i_out);
+        S* ckpt_y = reinterpret_cast<S*>(job.ckpt_y);
+        const bool observe = (job.v_out != nullptr) && (job.i_out != nullptr || job.loss_out != nullptr);
+        const long long jB = job.B;
+        const int T = job.T;
+        const long long b = (tile - job.tile_begin) * kTcM + tid;
+        const bool valid = b < jB;
+        S g_b = (S)1, e_b = (S)job.e_scalar;
+
+        auto emit = [&](int idx, S a, S r) {
+          if (y_out) {
+            typename Vec2<S>::type v;
+            v.x = a; v.y = r;
+            *reinterpret_cast<typename Vec2<S>::type*>(y_out + ((size_t)idx * jB + b) * 2) = v;
+          }
+          if (observe) {
+            double cur = (double)(g_b * a * r) * (job.v_out[idx] - (double)e_b);
+            if (i_out) i_out[(size_t)idx * jB + b] = (S)cur;
+            if (dptr) {
+              double d = (double)dptr[(size_t)idx * job.data_B + (job.data_B == 1 ? 0 : b)];
+              double diff = cur - d;
+              obs[2 * tid] += diff * diff;
+              obs[2 * tid + 1] += fabs(diff);
+            }
+          }
+        };
+        auto ckpt = [&](int step, const Lane<S>& lane) -> bool {
+          if (!job.ckpt_t) return true;
+          if (step >= job.ckpt_cap) return false;
+          size_t o = (size_t)step * jB + b;
+          double2 tt;
+          tt.x = lane.t0; tt.y = lane.dt;
+          *reinterpret_cast<double2*>(job.ckpt_t + 2 * o) = tt;
+          S buf[kCkptVals];
+          ckpt_pack<S>(lane, buf);
+          typedef typename Vec2<S>::type V2;
+          V2* dst = reinterpret_cast<V2*>(ckpt_y + (size_t)kCkptVals * o);
 #pragma unroll
-        for (int i = 0; i < kCkptVals / 2; ++i) {
-          V2 v;
-          v.x = buf[2 * i]; v.y = buf[2 * i + 1];
-          dst[i] = v;
-        }
-        return true;
-      };
+          for (int i = 0; i < kCkptVals / 2; ++i) {
+            V2 v;
+            v.x = buf[2 * i]; v.y = buf[2 * i + 1];
+            dst[i] = v;
+          }
+          return true;
+        };
 
-      Lane<S>& L = lanes[tid];
-      {
-        S ya = (S)0, yr = (S)1;
-        if (valid) {
-          ya = y0[2 * b]; yr = y0[2 * b + 1];
-          if (gptr) g_b = gptr[b];
-          if (eptr) e_b = eptr[b];
+        Lane<S>& L = lanes[tid];
+        {
+          S ya = (S)0, yr = (S)1;
+          if (valid) {
+            ya = y0[2 * b]; yr = y0[2 * b + 1];
+            if (gptr) g_b = gptr[b];
+            if (eptr) e_b = eptr[b];
+          }
+          lane_reset<S>(L, ya, yr, job.t_out[0], valid);
+          obs[2 * tid] = 0.0; obs[2 * tid + 1] = 0.0;
+          if (valid) emit(0, ya, yr);
         }
-        lane_reset<S>(L, ya, yr, job.t_out[0], valid);
-        obs[2 * tid] = 0.0; obs[2 * tid + 1] = 0.0;
-        if (valid) emit(0, ya, yr);
-      }
 
-      double nv, ain;
-      if (p.method == 0) {
-        init_prepare_f0<S>(L, cfg, &nv, &ain);
-        float out = tc_mlp_eval(g, tl, (float)nv, (float)ain);
-        init_store_f0<S>(L, cfg, (double)out);
-        if (cfg.first_step > 0) {
-          L.dt = cfg.first_step;
+        double nv, ain;
+        if (p.method == 0) {
+          init_prepare_f0<S>(L, cfg, &nv, &ain);
+          float out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+          init_store_f0<S>(L, cfg, (double)out);
+          if (cfg.first_step > 0) {
+            L.dt = cfg.first_step;
+          } else {
+            init_prepare_f1<S>(L, cfg, &nv, &ain);
+            out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+            init_store_f1<S>(L, cfg, (double)out);
+          }
+          if (T <= 1 && lane_active(L)) L.status = LANE_DONE;
+
+          while (true) {
+            dp_check_before_step<S>(L, cfg);
+            if (!owners_or(lane_active(L) ? 1 : 0)) break;
+#pragma unroll 1
+            for (int s = 0; s < 6; ++s) {
+              dp_prepare_stage<S>(L, cfg, s, &nv, &ain);
+              out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+              dp_store_stage<S>(L, cfg, s, (double)out);
+            }
+            dp_finish_step<S>(L, cfg, job.t_out, T, emit, ckpt);
+          }
         } else {
-          init_prepare_f1<S>(L, cfg, &nv, &ain);
-          out = tc_mlp_eval(g, tl, (float)nv, (float)ain);
-          init_store_f1<S>(L, cfg, (double)out);
-        }
-        if (T <= 1 && lane_active(L)) L.status = LANE_DONE;
-
-        while (true) {
-          dp_check_before_step<S>(L, cfg);
-          if (!owners_or(lane_active(L) ? 1 : 0)) break;
+          if (T <= 1 && lane_active(L)) L.status = LANE_DONE;
+          for (int gi = 0; gi + 1 < job.G; ++gi) {
+            const double g0 = job.grid[gi], g1 = job.grid[gi + 1];
+            if (!owners_or(lane_active(L) ? 1 : 0)) break;
 #pragma unroll 1
-          for (int s = 0; s < 6; ++s) {
-            dp_prepare_stage<S>(L, cfg, s, &nv, &ain);
-            out = tc_mlp_eval(g, tl, (float)nv, (float)ain);
-            dp_store_stage<S>(L, cfg, s, (double)out);
+            for (int s = 0; s < 4; ++s) {
+              rk4_prepare_stage<S>(L, cfg, s, g0, g1, p.time_f32 != 0, p.rk4_perturb != 0, &nv, &ain);
+              const float out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+              rk4_store_stage<S>(L, cfg, s, (double)out);
+            }
+            rk4_finish_step<S>(L, g0, g1, p.time_f32 != 0, job.t_out, T, emit);
           }
-          dp_finish_step<S>(L, cfg, job.t_out, T, emit, ckpt);
         }
-      } else {
-        if (T <= 1 && lane_active(L)) L.status = LANE_DONE;
-        for (int gi = 0; gi + 1 < job.G; ++gi) {
-          const double g0 = job.grid[gi], g1 = job.grid[gi + 1];
-          if (!owners_or(lane_active(L) ? 1 : 0)) break;
-#pragma unroll 1
-          for (int s = 0; s < 4; ++s) {
-            rk4_prepare_stage<S>(L, cfg, s, g0, g1, p.time_f32 != 0, p.rk4_perturb != 0, &nv, &ain);
-            const float out = tc_mlp_eval(g, tl, (float)nv, (float)ain);
-            rk4_store_stage<S>(L, cfg, s, (double)out);
-          }
-          rk4_finish_step<S>(L, g0, g1, p.time_f32 != 0, job.t_out, T, emit);
-        }
-      }
 
-      if (valid) {
-        job.stats_out[4 * b + 0] = L.n_acc;
-        job.stats_out[4 * b + 1] = L.n_rej;
-        job.stats_out[4 * b + 2] = L.nfe;
-        job.stats_out[4 * b + 3] = L.status == LANE_DONE ? 0 : L.status;
-        if (job.loss_out) {
-          job.loss_out[2 * b] = obs[2 * tid];
-          job.loss_out[2 * b + 1] = obs[2 * tid + 1];
+        if (valid) {
+          job.stats_out[4 * b + 0] = L.n_acc;
+          job.stats_out[4 * b + 1] = L.n_rej;
+          job.stats_out[4 * b + 2] = L.nfe;
+          job.stats_out[4 * b + 3] = L.status == LANE_DONE ? 0 : L.status;
+          if (job.loss_out) {
+            job.loss_out[2 * b] = obs[2 * tid];
+            job.loss_out[2 * b + 1] = obs[2 * tid + 1];
+          }
         }
+        owners_sync();   // the job slot is rewritten by the next tile
       }
-      owners_sync();   // the job slot is rewritten by the next tile
+      if (tp.timing && blockIdx.x == 0 && tid == 0) {
+        const long long tot = clock64() - c_begin;
+        printf("[tc timing] owner 0: total %lld cycles: layer0 %lld, wait_d %lld, epilogue %lld, solver+other %lld\n",
+               tot, tl.c_l0, tl.c_wait, tl.c_epi, tot - tl.c_l0 - tl.c_wait - tl.c_epi);
+      }
+      // release the helper groups and the engine warps
+      if (tid == 0) { *cmd_exit = 1; *stop_flag = 1; }
+      owners_sync();
+      if (G > 1) lanes_sync<G>();
     }
-    // release the engine: stop flag, then one more a_ready phase
-    if (tid == 0) *stop_flag = 1;
-    owners_sync();
+    // one more a_ready phase wakes the MMA thread, which sees the stop flag
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
   }
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tbase, tc::kTmemCols);
+  if (warp == kMmaWarp) tc::tmem_dealloc(tbase, tc::kTmemCols);
 }
 
 }  // namespace ikr

@@ -69,6 +69,47 @@ __device__ __forceinline__ void st4(uint32_t taddr, uint32_t a, uint32_t b, uint
                : "memory");
 }
 
+#define IKR_TC_R4(v, o) "r"(v[o]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3])
+#define IKR_TC_W4(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3])
+// Wide variants: a TMEM store costs ~140 cycles per instruction plus ~1.5 cycles per column
+// (measured, tests/tc_probe.cu "tmem"), so the epilogues write 16 / 32 columns per instruction.
+__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : IKR_TC_W4(v, 0), IKR_TC_W4(v, 4), IKR_TC_W4(v, 8), IKR_TC_W4(v, 12), IKR_TC_W4(v, 16),
+        IKR_TC_W4(v, 20), IKR_TC_W4(v, 24), IKR_TC_W4(v, 28)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15, %16};" ::"r"(taddr),
+      IKR_TC_R4(v, 0), IKR_TC_R4(v, 4), IKR_TC_R4(v, 8), IKR_TC_R4(v, 12)
+      : "memory");
+}
+__device__ __forceinline__ void st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(
+          taddr),
+      IKR_TC_R4(v, 0), IKR_TC_R4(v, 4), IKR_TC_R4(v, 8), IKR_TC_R4(v, 12), IKR_TC_R4(v, 16),
+      IKR_TC_R4(v, 20), IKR_TC_R4(v, 24), IKR_TC_R4(v, 28)
+      : "memory");
+}
+
+// one lane of a converged warp (the same lane every time)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- descriptors ----------------------------------------------------------------------------------
 // instruction descriptor of tcgen05.mma.kind::f16: BF16 x BF16 -> FP32, both operands K-major
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {

@@ -244,12 +244,19 @@ def test_batch_is_independent_trajectories_and_tile_invariant():
     B = 333                                     # ragged: not a multiple of any tile
     y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1),
                       dtype=torch.float32).cuda()
-    full = ikr.integrate(func, y0, t)
+    # FFMA2 kernel: bit-identical whatever the tile size and the batch the trajectory sits in
+    full = ikr.integrate(func, y0, t, options={'tensor_cores': False})
     for tile in (8, 64):
         part = ikr.integrate(func, y0[:77], t, options={'tile_m': tile})
         assert torch.equal(part.y, full.y[:, :77])
         assert torch.equal(part.stats, full.stats[:77])
     assert full.geometry['n_tiles'] * full.geometry['tile_m'] >= B
+    # tcgen05 kernel (default): bit-identical whatever the lane / tile the trajectory sits in
+    tc_full = ikr.integrate(func, y0, t)
+    assert tc_full.geometry['tile_m'] == 128
+    tc_part = ikr.integrate(func, y0[200:277], t)
+    assert torch.equal(tc_part.y, tc_full.y[:, 200:277])
+    assert torch.equal(tc_part.stats, tc_full.stats[200:277])
 
 
 def test_fused_current_and_loss_epilogue():
@@ -389,10 +396,12 @@ def test_interp_kernel_matches_scipy():
         assert np.array_equal(out.cpu().numpy(), want)      # bit-exact, compacted or not
 
 
-def test_integrate_many_equals_separate_calls():
+@pytest.mark.parametrize('tensor_cores', [True, False])
+def test_integrate_many_equals_separate_calls(tensor_cores):
     """One launch over several (protocol, batch) jobs == the reference's protocol loop of separate
-    odeint calls (train-s1.py:316-543)."""
+    odeint calls (train-s1.py:316-543), bit for bit, on the tcgen05 and on the FFMA2 kernel."""
     func, _ = _nn('d1')
+    single_opts = {'tensor_cores': True} if tensor_cores else {'tensor_cores': False, 'tile_m': 32}
     rng = np.random.RandomState(11)
     jobs, singles = [], []
     for fam, nb in (('pr3', 37), ('pr4', 200), ('aps', 5)):
@@ -405,8 +414,8 @@ def test_integrate_many_equals_separate_calls():
         jobs.append(dict(protocol=(t_tab, v_tab), y0=y0, t=t, g=g, data=data, want_current=True))
         func.set_fixed_form_voltage_protocol(t_tab, v_tab)
         singles.append(ikr.integrate(func, y0, t, g=g, data=data, want_current=True,
-                                     options={'tile_m': 32}))
-    many = ikr.integrate_many(func, jobs)
+                                     options=single_opts))
+    many = ikr.integrate_many(func, jobs, options={'tensor_cores': tensor_cores})
     assert len(many) == 3
     for a, b in zip(many, singles):
         assert torch.equal(a.y, b.y) and torch.equal(a.current, b.current)
@@ -443,8 +452,8 @@ def test_lane_pool_kernel_equals_tile_scheduled_kernel():
         assert n > 0
 
 
-@pytest.mark.parametrize('B', [65536, 1048576])
-def test_full_size_ensembles_duplicate_invariance(B):
+@pytest.mark.parametrize('B,tensor_cores', [(65536, True), (65536, False), (1048576, True)])
+def test_full_size_ensembles_duplicate_invariance(B, tensor_cores):
     """BASELINE configs[1] / configs[4] sizes (65,536 and 1M trajectories): 256 distinct (y0, g)
     instances, each repeated B/256 times in shuffled positions.  Size-independent properties:
     every copy of an instance gives bit-identical results wherever it sits (tile / CTA / slot
@@ -459,9 +468,12 @@ def test_full_size_ensembles_duplicate_invariance(B):
     t = torch.linspace(0., 120., 13)
     data = torch.zeros(13)
     big = ikr.integrate(func, torch.from_numpy(base_y0[idx]).cuda(), t, g=torch.from_numpy(base_g[idx]),
-                        data=data, want_y=False, want_current=False)
+                        data=data, want_y=False, want_current=False,
+                        options={'tensor_cores': tensor_cores})
     small = ikr.integrate(func, torch.from_numpy(base_y0).cuda(), t, g=torch.from_numpy(base_g),
-                          data=data, want_y=False, want_current=False, options={'tile_m': 32})
+                          data=data, want_y=False, want_current=False,
+                          options={'tensor_cores': True} if tensor_cores else
+                          {'tensor_cores': False, 'tile_m': 32})
     assert int((big.stats[:, 3] != 0).sum()) == 0
     idx_d = torch.from_numpy(idx).cuda()
     assert torch.equal(big.stats, small.stats[idx_d])
