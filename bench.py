@@ -36,6 +36,52 @@ FLOP_PER_EVAL = 2 * 200600          # BASELINE.md section 3 (s00 architecture, f
 METRIC = 'NN-ODE RHS evals/sec (batched dopri5; headline = configs[1] forward, fwd+backward in "train")'
 
 
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written on this pool's B200s) or the profiling guide's fallback."""
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as fh:
+            mp = json.load(fh)
+        return {'bf16_sustained': float(mp['bf16_tflops_sustained']), 'bf16_burst': float(mp['bf16_tflops']),
+                'hbm_gbs': float(mp['hbm_gbs']), 'source': 'MEASURED_PEAKS.json'}
+    except (OSError, KeyError, ValueError):
+        return {'bf16_sustained': 1590.0, 'bf16_burst': 1590.0, 'hbm_gbs': 6650.0,
+                'source': 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)'}
+
+
+def forward_roofline(achieved_tflops, fma_peak_tflops, tensor_cores):
+    """Roofline object of the forward kernel.  `achieved` is ALGORITHMIC work (401,200 FLOP per RHS
+    evaluation) / kernel time.  On the tcgen05 path every fp32 product is six
+    bf16 MMAs (bf16x3 split, fp32-faithful), so the executed tensor FLOPs are 6 x the algorithmic
+    hidden-layer FLOPs; both fractions are reported.  HBM traffic is ~1 MB per launch (weights +
+    tables; everything else lives in SMEM / TMEM / L2)."""
+    if not tensor_cores:
+        return {
+            'bound': 'fma', 'achieved': achieved_tflops, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
+            'frac': achieved_tflops / fma_peak_tflops if fma_peak_tflops else None,
+            'traffic': 1.2e6, 'flop_per_eval': FLOP_PER_EVAL,
+            'peak_source': 'FP32 FFMA pipe measured in this run by ikr_fma_peak (nominal 148 SM x 128 '
+                           'lanes x 2 x 1.965 GHz = 74.5 TFLOP/s)',
+        }
+    mp = measured_peaks()
+    hidden_share = (2.0 * 5 * 200 * 200) / FLOP_PER_EVAL       # hidden layers / all layers (s00)
+    executed = achieved_tflops * hidden_share * 6.0 * (208.0 / 200.0)   # N padded 200 -> 208
+    return {
+        'bound': 'tensor', 'achieved': achieved_tflops, 'peak': mp['bf16_sustained'], 'unit': 'TFLOP/s',
+        'frac': achieved_tflops / mp['bf16_sustained'],
+        'traffic': 1.2e6, 'flop_per_eval': FLOP_PER_EVAL,
+        'peak_source': 'dense bf16 tensor peak, sustained figure of %s (kernel timed inside a long '
+                       'step)' % mp['source'],
+        'executed_bf16_tflops': executed, 'frac_executed': executed / mp['bf16_sustained'],
+        'fp32_emulation': 'bf16x3 split: 6 bf16 MMAs (a1b1 a2b1 a3b1 a1b2 a2b2 a1b3) per fp32 product, '
+                          'fp32 accumulation in TMEM; ceiling for fp32-faithful work = peak / 6 = '
+                          '%.1f TFLOP/s' % (mp['bf16_sustained'] / 6.0),
+        'frac_of_fp32_emulation_ceiling': achieved_tflops / (mp['bf16_sustained'] / 6.0),
+        'fma_peak': fma_peak_tflops,
+        'vs_fma_peak': achieved_tflops / fma_peak_tflops if fma_peak_tflops else None,
+    }
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -329,7 +375,8 @@ def run_b200(args):
     _cabi.check(_cabi.lib().ikr_fma_peak(_cabi.F32, 200000, ctypes.byref(peak), None), 'fma_peak')
     fma_peak_tflops = peak.value
 
-    opts = {'check_status': False, 'lane_pool': bool(os.environ.get('IKR_LANE_POOL'))}
+    opts = {'check_status': False, 'lane_pool': bool(os.environ.get('IKR_LANE_POOL')),
+            'tensor_cores': not os.environ.get('IKR_NO_TC')}
 
     def step_device():
         return ikr.integrate_many(func, jobs_dev, options=opts)
@@ -416,6 +463,7 @@ def run_b200(args):
         # the forward kernel is >99.9 % of the timed region (profiles/): its launch duration is the
         # event-timed step
         achieved = (nfe_rank0 * FLOP_PER_EVAL) / (ms_rank0 * 1e-3) / 1e12
+        roofline = forward_roofline(achieved, fma_peak_tflops, bool(geo.get('tensor_cores')))
         line = {
             'metric': METRIC,
             'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps,
@@ -438,21 +486,11 @@ def run_b200(args):
                     'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': n_launch_fwd,
             'clocks': clocks,
-            'roofline': {
-                'bound': 'fma', 'achieved': achieved, 'peak': fma_peak_tflops,
-                'unit': 'TFLOP/s', 'frac': achieved / fma_peak_tflops if fma_peak_tflops else None,
-                'traffic': 1.2e6,
-                'peak_source': 'FP32 FFMA pipe, measured in this run by ikr_fma_peak '
-                               '(MEASURED_PEAKS.json holds HBM and bf16-tensor peaks only; this '
-                               'kernel is FMA-bound: ncu dram bytes per launch ~1 MB). nominal '
-                               '148 SM x 128 lanes x 2 x 1.965 GHz = 74.5 TFLOP/s',
-                'nominal_peak': 74.5, 'frac_of_nominal': achieved / 74.5,
-                'flop_per_eval': FLOP_PER_EVAL,
-            },
+            'roofline': roofline,
             'cpu_baseline': cpu_base,
         }
         if train is not None:
-            train['roofline_frac'] = train['algorithmic_tflops'] / fma_peak_tflops
+            train['frac_of_fma_peak'] = train['algorithmic_tflops'] / fma_peak_tflops
             line['train'] = train
         print(json.dumps(line))
     if world > 1:

@@ -68,7 +68,8 @@ typedef struct ikr_desc {
   double safety, ifactor, dfactor; /* 0.9, 10, 0.2                                               */
   int64_t max_num_steps;  /* per output interval, torchdiffeq semantics                          */
   int32_t tile_m;         /* 0: library picks the trajectories-per-CTA tile                      */
-  int32_t reserved;       /* bit 0: dopri5 on the lane-pool kernel (slots refill from a queue)     */
+  int32_t reserved;       /* bit 0: dopri5 on the lane-pool kernel (slots refill from a queue);
+                             bit 1: keep an fp32 MLP on the FFMA2 kernel (no tensor cores)          */
 } ikr_desc;
 
 /* One JOB = one protocol table + one batch of trajectories, i.e. the shape of one reference
@@ -139,6 +140,11 @@ int ikr_packed_layout(const ikr_desc* d, int64_t out[8]);
 int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B);
 /* out[8] = tile_m, threads/CTA, grid, dynamic smem bytes, n_tiles, kc, chunks/layer, SM count */
 int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[8]);
+
+/* 1 when ikr_forward will run this configuration on the tcgen05 tensor-core kernel (fp32 MLP with
+ * n_nodes <= 200: hidden layers as bf16x3 split MMAs, fp32-faithful), 0 for the FFMA2 / DFMA kernel.
+ * desc->reserved bit 1 opts out. */
+int32_t ikr_uses_tensor_cores(const ikr_desc* d);
 
 /* device workspace (caller-allocated) needed by ikr_forward / ikr_backward for n_jobs jobs   */
 size_t ikr_workspace_bytes(const ikr_desc* d, int32_t n_jobs, int64_t B_total,

@@ -78,6 +78,8 @@ def lib():
     L.ikr_packed_layout.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(c_i64)]
     L.ikr_param_count.restype = c_i64
     L.ikr_param_count.argtypes = [ctypes.POINTER(IkrDesc)]
+    L.ikr_uses_tensor_cores.restype = c_i32
+    L.ikr_uses_tensor_cores.argtypes = [ctypes.POINTER(IkrDesc)]
     L.ikr_tile_m.restype = c_i32
     L.ikr_tile_m.argtypes = [ctypes.POINTER(IkrDesc), c_i32, ctypes.POINTER(c_i64)]
     L.ikr_launch_geometry.restype = c_i32
@@ -104,7 +106,7 @@ def lib():
 
 
 EXPORTS = ('ikr_abi_version', 'ikr_error_string', 'ikr_packed_weight_elems', 'ikr_packed_layout',
-           'ikr_param_count', 'ikr_tile_m', 'ikr_launch_geometry', 'ikr_workspace_bytes',
+           'ikr_param_count', 'ikr_uses_tensor_cores', 'ikr_tile_m', 'ikr_launch_geometry', 'ikr_workspace_bytes',
            'ikr_forward', 'ikr_backward', 'ikr_forward_hh', 'ikr_interp_protocol', 'ikr_fma_peak')
 
 
@@ -126,4 +128,5 @@ def launch_geometry(desc, B):
     arr = (c_i64 * len(Bs))(*Bs)
     check(lib().ikr_launch_geometry(ctypes.byref(desc), len(Bs), arr, out), 'ikr_launch_geometry')
     return {'tile_m': out[0], 'threads': out[1], 'grid': out[2], 'smem': out[3],
-            'n_tiles': out[4], 'kc': out[5], 'cpl': out[6], 'sms': out[7]}
+            'n_tiles': out[4], 'kc': out[5], 'cpl': out[6], 'sms': out[7],
+            'tensor_cores': bool(lib().ikr_uses_tensor_cores(ctypes.byref(desc)) == 1)}

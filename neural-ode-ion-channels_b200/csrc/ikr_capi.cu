@@ -541,6 +541,11 @@ int64_t ikr_param_count(const ikr_desc* d) {
   return 2 * n + n + L * (n * n + n) + n + 1;
 }
 
+int32_t ikr_uses_tensor_cores(const ikr_desc* d) {
+  if (!valid_desc(d)) return IKR_ERR_ARG;
+  return make_tc_plan(d).ok ? 1 : 0;
+}
+
 int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B) {
   if (!valid_desc(d) || n_jobs < 1 || !B) return IKR_ERR_ARG;
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;

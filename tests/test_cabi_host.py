@@ -86,9 +86,20 @@ def test_packed_layout_and_param_count(lib):
         assert geo['n_tiles'] * geo['tile_m'] >= 65536
         multi = _cabi.launch_geometry(d, [13107] * 4 + [13108])
         assert multi['n_tiles'] >= sum(-(-b // multi['tile_m']) for b in [13107] * 4 + [13108])
-    # the default network at the bench batch gets the 16-warp, 160-trajectory tile
-    geo = _cabi.launch_geometry(_desc(), [13107] * 4 + [13108])
+    # the default network (fp32 MLP, n = 200) runs on the tcgen05 kernel: 128-trajectory tiles (one
+    # per TMEM lane), 3 x 128 lane threads + MMA warp + weight-producer warp
+    d = _desc()
+    geo = _cabi.launch_geometry(d, [13107] * 4 + [13108])
+    assert lib.ikr_uses_tensor_cores(ctypes.byref(d)) == 1 and geo['tensor_cores']
+    assert (geo['tile_m'], geo['threads']) == (128, 448)
+    # opting out (reserved bit 1) gives the FFMA2 kernel its 16-warp, 160-trajectory tile
+    d.reserved = 2
+    geo = _cabi.launch_geometry(d, [13107] * 4 + [13108])
+    assert lib.ikr_uses_tensor_cores(ctypes.byref(d)) == 0 and not geo['tensor_cores']
     assert (geo['tile_m'], geo['threads']) == (160, 512)
+    # n = 500 (s06-s08) and fp64 MLPs do not fit the TMEM budget / are not fp32: FFMA2 / DFMA kernel
+    big = _desc(ikr.ODEFunc(arch='s06'))
+    assert lib.ikr_uses_tensor_cores(ctypes.byref(big)) == 0
 
 
 def test_pack_weights_roundtrip(lib):
