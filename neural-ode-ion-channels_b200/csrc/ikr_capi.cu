@@ -10,7 +10,7 @@
 
 #include "../../include/ikr.h"
 #include "ikr_backward.cuh"
-#include "ikr_forward_tc.cuh"
+#include "ikr_backward_tc.cuh"
 #include "ikr_hh.cuh"
 
 using namespace ikr;
@@ -415,6 +415,183 @@ int launch_wgrad(const WgradParams& p, const BwdPlan& pl, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
 }
 
+// ---------------------------------------------------------------------------------------------
+// tensor-core backward (ikr_backward_tc.cuh): plan, workspace, round loop
+// ---------------------------------------------------------------------------------------------
+struct TcBwdPlan {
+  bool ok;
+  TcGeom g;
+  TcStashGeom sg;
+  int groups, mask_words;
+  size_t smem;
+  long long n_tiles;
+  int grid, sms;
+  int wg_S, wg_stages;
+  size_t wg_smem;
+  size_t off_counters, off_lanes, off_partial, off_img, fixed_bytes, partial_bytes, img_bytes;
+};
+
+TcBwdPlan make_tc_bwd_plan(const ikr_desc* d, long long B) {
+  TcBwdPlan pl;
+  pl.ok = false;
+  const TcPlan fw = make_tc_plan(d);
+  if (!fw.ok || !tc_backward_ok(fw.g) || d->method != IKR_DOPRI5) return pl;
+  pl.g = fw.g;
+  pl.sg = tc_stash_geometry(pl.g);
+  pl.groups = fw.groups;
+  pl.mask_words = (pl.g.units + pl.groups - 1) / pl.groups + 1;
+  const size_t fixed = d->state_dtype == IKR_F32
+                           ? TcAdjSmemLayout<float>(pl.g, 0, pl.groups, pl.mask_words).total
+                           : TcAdjSmemLayout<double>(pl.g, 0, pl.groups, pl.mask_words).total;
+  if (fixed + (size_t)kTcMinStages * pl.g.stage_bytes > kSmemLimit) return pl;
+  int stages = (int)((kSmemLimit - fixed) / pl.g.stage_bytes);
+  if (stages > kTcMaxStages) stages = kTcMaxStages;
+  pl.g.stages = stages;
+  pl.smem = fixed + (size_t)stages * pl.g.stage_bytes;
+  pl.sms = device_sms();
+  pl.n_tiles = (B + kTcM - 1) / kTcM;
+  pl.grid = (int)(pl.n_tiles < pl.sms ? pl.n_tiles : pl.sms);
+  // weight-gradient GEMM: (L + 2) pseudo-layers x S splits
+  pl.wg_S = pl.sms / (d->n_layers + 2);
+  if (pl.wg_S < 1) pl.wg_S = 1;
+  const size_t wg_stage = 4ull * pl.sg.NGb * 128 * 2;   // largest stage: two big operands, two terms each
+  pl.wg_stages = (int)((kSmemLimit - 256) / wg_stage);
+  if (pl.wg_stages > kWgTcMaxStages) pl.wg_stages = kWgTcMaxStages;
+  if (pl.wg_stages < 2) return pl;
+  pl.wg_smem = 256 + (size_t)pl.wg_stages * wg_stage;
+  const size_t lane_save = d->state_dtype == IKR_F32 ? sizeof(BLaneSave<float>) : sizeof(BLaneSave<double>);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
+  pl.off_counters = take(256);
+  pl.off_lanes = take((size_t)pl.n_tiles * kTcM * lane_save);
+  pl.partial_bytes = (size_t)(d->n_layers + 2) * pl.wg_S * pl.g.NP * pl.g.NP * sizeof(double);
+  pl.off_partial = take(pl.partial_bytes);
+  pl.img_bytes = (size_t)2 * d->n_layers * pl.g.KST * pl.g.stage_bytes;
+  pl.off_img = take(pl.img_bytes);
+  pl.fixed_bytes = o;
+  pl.ok = true;
+  return pl;
+}
+
+int tc_bwd_steps_per_round(const TcBwdPlan& pl, size_t bytes) {
+  if (bytes <= pl.fixed_bytes + 512) return 0;
+  const long long slots = (long long)((bytes - pl.fixed_bytes - 512) / (size_t)pl.sg.slot);
+  const long long per_tile = slots / pl.n_tiles;               // 6 R + 1 slots per tile
+  if (per_tile < 7) return 0;
+  const long long R = (per_tile - 1) / 6;
+  return (int)(R > 4096 ? 4096 : R);
+}
+
+size_t tc_bwd_workspace_bytes(const TcBwdPlan& pl) {
+  // default: a stash of about 4 GiB, at least one step per round
+  const double target = 4.0 * 1024 * 1024 * 1024;
+  long long R = (long long)((target / (double)pl.sg.slot / (double)pl.n_tiles - 1) / 6);
+  if (R < 1) R = 1;
+  if (R > 64) R = 64;
+  return pl.fixed_bytes + 512 + (size_t)pl.n_tiles * (6 * R + 1) * (size_t)pl.sg.slot;
+}
+
+template <typename S, int G>
+int launch_adjoint_tc_g(const TcAdjParams& tp, const TcBwdPlan& pl, cudaStream_t st) {
+  auto kern = ikr_adjoint_tc_kernel<S, G>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return IKR_ERR_LAUNCH;
+  }
+  kern<<<pl.grid, tc_threads(G), pl.smem, st>>>(tp);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+template <typename S>
+int launch_adjoint_tc(const TcAdjParams& tp, const TcBwdPlan& pl, cudaStream_t st) {
+  if (pl.groups == 1) return launch_adjoint_tc_g<S, 1>(tp, pl, st);
+  if (pl.groups == 2) return launch_adjoint_tc_g<S, 2>(tp, pl, st);
+  return launch_adjoint_tc_g<S, 3>(tp, pl, st);
+}
+
+int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, const TcBwdPlan& pl,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int R = tc_bwd_steps_per_round(pl, workspace_bytes);
+  if (R < 1) return IKR_ERR_WORKSPACE;
+  unsigned char* ws = (unsigned char*)workspace;
+  const size_t off_stash = (pl.fixed_bytes + 255) & ~(size_t)255;
+  if (off_stash + (size_t)pl.n_tiles * (6 * (size_t)R + 1) * (size_t)pl.sg.slot > workspace_bytes)
+    return IKR_ERR_WORKSPACE;
+  if (cudaMemsetAsync(ws + pl.off_partial, 0, pl.partial_bytes, st) != cudaSuccess) return IKR_ERR_DEVICE;
+
+  const MlpView mv = make_view(d, io->weights);
+  TcPackParams pk;
+  pk.wn = reinterpret_cast<const float*>(io->weights) + mv.off_wn;
+  pk.wt = reinterpret_cast<const float*>(io->weights) + mv.off_wt;
+  pk.npad = mv.npad;
+  pk.n_seq = 2 * d->n_layers;
+  pk.g = pl.g;
+  pk.img = reinterpret_cast<uint16_t*>(ws + pl.off_img);
+  ikr_tc_pack_kernel<<<pl.sms, 256, 0, st>>>(pk);
+  if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
+
+  TcAdjParams tp;
+  BwdParams& p = tp.b;
+  p.mlp = mv;
+  p.cfg = make_cfg(d);
+  p.cfg.tab = make_table(io);
+  p.M = kTcM; p.MG = 0; p.NG = 0; p.n_worker_warps = 0;
+  p.B = io->B; p.T = (int)io->T; p.n_tiles = pl.n_tiles;
+  p.y0 = io->y0; p.t_out = io->t_out; p.stats = io->stats_out;
+  p.ckpt_t = io->ckpt_t; p.ckpt_y = io->ckpt_y;
+  p.grad_y = bio->grad_y; p.fused_loss = bio->fused_loss;
+  p.y_out = io->y_out; p.v_out = io->v_out; p.g = io->g; p.e_rev = io->e_rev;
+  p.e_scalar = io->e_scalar; p.data = io->data; p.data_B = io->data_B;
+  p.lane_state = ws + pl.off_lanes;
+  p.steps_per_round = R;
+  p.stash_h = nullptr; p.stash_d = nullptr;
+  p.counters = reinterpret_cast<unsigned long long*>(ws + pl.off_counters);
+  p.small_grad = nullptr; p.small_stride = 0;
+  p.grad_y0 = bio->grad_y0; p.grad_g = bio->grad_g;
+  tp.g = pl.g;
+  tp.sg = pl.sg;
+  tp.img = ws + pl.off_img;
+  tp.stash = ws + off_stash;
+  tp.mask_words = pl.mask_words;
+
+  TcWgradParams wp;
+  wp.g = pl.g; wp.sg = pl.sg;
+  wp.stash = tp.stash;
+  wp.counters = p.counters;
+  wp.S = pl.wg_S;
+  wp.stages = pl.wg_stages;
+  wp.partial = reinterpret_cast<double*>(ws + pl.off_partial);
+  if (cudaFuncSetAttribute(ikr_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)pl.wg_smem) != cudaSuccess) {
+    cudaGetLastError();
+    return IKR_ERR_LAUNCH;
+  }
+
+  long long max_steps = bio->max_accepted_steps > 0 ? bio->max_accepted_steps : io->ckpt_cap;
+  if (max_steps > io->ckpt_cap) max_steps = io->ckpt_cap;
+  const long long rounds = max_steps > 0 ? (max_steps + R - 1) / R : 1;
+  for (long long r = 0; r < rounds; ++r) {
+    if (cudaMemsetAsync(ws + pl.off_counters, 0, 256, st) != cudaSuccess) return IKR_ERR_DEVICE;
+    p.first_round = r == 0 ? 1 : 0;
+    const int rc = d->state_dtype == IKR_F32 ? launch_adjoint_tc<float>(tp, pl, st)
+                                             : launch_adjoint_tc<double>(tp, pl, st);
+    if (rc != 0) return rc;
+    ikr_wgrad_tc_kernel<<<(d->n_layers + 2) * pl.wg_S, kWgTcThreads, pl.wg_smem, st>>>(wp);
+    if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
+  }
+
+  TcReduceParams rp;
+  rp.L = d->n_layers; rp.n = d->n_nodes; rp.NP = pl.g.NP; rp.S = pl.wg_S;
+  rp.partial = wp.partial;
+  rp.out = bio->grad_weights;
+  const long long n = d->n_nodes, Ln = d->n_layers;
+  rp.n_params = 3 * n + Ln * (n * n + n) + n + 1;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((rp.n_params + threads - 1) / threads);
+  ikr_grad_reduce_tc_kernel<<<blocks, threads, 0, st>>>(rp);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
 int bwd_dispatch(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, void* workspace,
                  size_t workspace_bytes, cudaStream_t st) {
   if (d->method != IKR_DOPRI5) return IKR_ERR_UNSUPPORTED;
@@ -426,6 +603,10 @@ int bwd_dispatch(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, voi
   if (bio->fused_loss != 0 && (!io->y_out || !io->v_out || !io->data)) return IKR_ERR_ARG;
   if (bio->fused_loss < 0 || bio->fused_loss > 2) return IKR_ERR_ARG;
   if (!workspace) return IKR_ERR_WORKSPACE;
+  {
+    const TcBwdPlan tpl = make_tc_bwd_plan(d, io->B);
+    if (tpl.ok) return bwd_dispatch_tc(d, io, bio, tpl, workspace, workspace_bytes, st);
+  }
   const BwdPlan pl = make_bwd_plan(d, io->B);
   const Geometry& g = pl.g;
   if (g.smem > kSmemLimit || g.threads > kMaxThreads || pl.wg_smem > kSmemLimit)
@@ -577,7 +758,10 @@ size_t ikr_workspace_bytes(const ikr_desc* d, int32_t n_jobs, int64_t B_total,
   size_t bytes = fwd_fixed_workspace(n_jobs);
   const TcPlan tcp = make_tc_plan(d);
   if (tcp.ok) bytes += (tcp.img_bytes + 255) & ~(size_t)255;   // bf16 weight image of the tcgen05 path
-  if (with_backward) bytes += bwd_workspace_bytes(d, B_total);
+  if (with_backward) {
+    const TcBwdPlan tpl = make_tc_bwd_plan(d, B_total);
+    bytes += tpl.ok ? tc_bwd_workspace_bytes(tpl) : bwd_workspace_bytes(d, B_total);
+  }
   return bytes;
 }
 
@@ -675,6 +859,8 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
     tp.timing = getenv("IKR_TC_TIMING") != nullptr;
     TcPackParams pk;
     pk.wn = reinterpret_cast<const float*>(jobs[0].weights) + p.mlp.off_wn;
+    pk.wt = reinterpret_cast<const float*>(jobs[0].weights) + p.mlp.off_wt;
+    pk.n_seq = d->n_layers;
     pk.npad = p.mlp.npad;
     pk.g = tcp.g;
     pk.img = reinterpret_cast<uint16_t*>(img);

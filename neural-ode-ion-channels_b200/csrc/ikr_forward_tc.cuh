@@ -91,7 +91,9 @@ __host__ __device__ inline int tc_a_col(const TcGeom& g, int t, int j) {
 // ---- weight image: [layer][k-step][block 0..2][NP x 16 bf16 in core-matrix order] -----------------
 struct TcPackParams {
   const float* wn;   // [L][n][npad] rows = output features (packed-parameter section off_wn)
+  const float* wt;   // [L][n][npad] rows = input features  (section off_wt = W^T), backward images
   int npad;
+  int n_seq;         // L: forward images W_1..W_L; 2L: followed by the transposed W_L..W_1
   TcGeom g;
   uint16_t* img;
 };
@@ -106,10 +108,12 @@ __device__ __forceinline__ uint16_t bf16_term(float w, int term) {
   return (uint16_t)h;
 }
 
+// B operand image of layer-MMA number `seq`: B[row][k] = src[row][k], src = W_l (forward: D = A W_l^T)
+// or W_l^T (backward: D = A W_l)
 __global__ void ikr_tc_pack_kernel(const TcPackParams p) {
   const TcGeom& g = p.g;
   const long long per_block = (long long)g.NP * 16;
-  const long long total = (long long)g.L * g.KST * 3 * per_block;
+  const long long total = (long long)p.n_seq * g.KST * 3 * per_block;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int kk = (int)(i % 16);
@@ -117,7 +121,9 @@ __global__ void ikr_tc_pack_kernel(const TcPackParams p) {
     const long long blk = i / per_block;
     const int c = (int)(blk % 3);
     const int step = (int)((blk / 3) % g.KST);
-    const int layer = (int)(blk / (3LL * g.KST));
+    const int seq = (int)(blk / (3LL * g.KST));
+    const float* src = seq < g.L ? p.wn + (long long)seq * g.n * p.npad
+                                 : p.wt + (long long)(2 * g.L - 1 - seq) * g.n * p.npad;
     int k, term;
     if (step < g.KSf) {
       k = 16 * step + kk;
@@ -127,7 +133,7 @@ __global__ void ikr_tc_pack_kernel(const TcPackParams p) {
       term = c == 0 ? 0 : (c == 1 ? 1 : (kk < 8 ? 2 : 0));
     }
     float w = 0.0f;
-    if (o < g.n && k < g.n) w = p.wn[((long long)layer * g.n + o) * p.npad + k];
+    if (o < g.n && k < g.n) w = src[(long long)o * p.npad + k];
     const long long byte = (long long)(o >> 3) * 256 + (kk >> 3) * 128 + (o & 7) * 16 + (kk & 7) * 2;
     p.img[(blk * g.block_bytes + byte) >> 1] = bf16_term(w, term);
   }
@@ -375,6 +381,93 @@ __device__ __forceinline__ float tc_owner_eval(const TcGeom& g, TcLane& tl, floa
   return out + tl.sp[(size_t)(4 + g.L) * g.NP];
 }
 
+// ---- engine warps (shared by the forward and the adjoint kernel) ---------------------------------------
+struct TcEngineCtx {
+  uint64_t* bar_full;
+  uint64_t* bar_empty;
+  uint64_t* bar_a;        // every lane thread arrives once its part of the A operand is in TMEM
+  uint64_t* bar_d;        // tcgen05.commit: the layer's D is complete
+  volatile int* stop_flag;
+  unsigned char* ring;
+};
+
+// MMA issuer.  The whole warp runs the loop (warp-uniform control flow and operands => the descriptors
+// live in uniform registers and each MMA is one UTCHMMA); one elected lane issues the MMAs and commits.
+// Every a_ready phase triggers the MMAs of ONE layer: KST ring stages, six MMAs per regular K-step.
+__device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& c, uint32_t tbase, bool timing) {
+  const unsigned stages = (unsigned)g.stages;
+  const uint32_t idesc = tc::idesc_bf16_f32(kTcM, g.NP);
+  const uint64_t desc0 = tc::smem_desc(smem_u32(c.ring), 128, 256);
+  const uint32_t blk16 = (uint32_t)g.block_bytes >> 4, stage16 = (uint32_t)g.stage_bytes >> 4;
+  const uint32_t a_base = tbase + g.col_a;
+  unsigned s = 0, round = 0, consumed = 0, phase_a = 0;
+  long long e_wait = 0, e_issue = 0, ec = clock64();
+  while (true) {
+    mbar_wait(c.bar_a, phase_a);
+    phase_a ^= 1u;
+    if (*c.stop_flag) break;
+    tc::fence_after_sync();
+    { const long long c1 = clock64(); e_wait += c1 - ec; ec = c1; }
+#pragma unroll 1
+    for (int j = 0; j < g.KST; ++j) {
+      mbar_wait(&c.bar_full[s], round);
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint64_t b1 = desc0 + (uint64_t)(s * stage16);
+        const uint64_t b2 = b1 + blk16, b3 = b2 + blk16;
+        if (j < g.KSf) {
+          const bool full = (j | 1) < g.KSf;
+          const uint32_t a1 = a_base + 48 * (j >> 1) + (full ? 8 * (j & 1) : 0);
+          const uint32_t dt = full ? 16u : 8u;
+          tc::mma_ts(tbase, a1, b1, idesc, j > 0 ? 1u : 0u);
+          tc::mma_ts(tbase, a1 + dt, b1, idesc, 1u);
+          tc::mma_ts(tbase, a1 + 2 * dt, b1, idesc, 1u);
+          tc::mma_ts(tbase, a1, b2, idesc, 1u);
+          tc::mma_ts(tbase, a1 + dt, b2, idesc, 1u);
+          tc::mma_ts(tbase, a1, b3, idesc, 1u);
+        } else {
+          tc::mma_ts(tbase, tbase + g.col_t1, b1, idesc, j > 0 ? 1u : 0u);
+          tc::mma_ts(tbase, tbase + g.col_t1, b2, idesc, 1u);
+          tc::mma_ts(tbase, tbase + g.col_t2, b3, idesc, 1u);
+        }
+        tc::commit(smem_u32(&c.bar_empty[s]));   // slot free once these MMAs have read it
+      }
+      __syncwarp();
+      ++consumed;
+      if (++s == stages) { s = 0; round ^= 1u; }
+    }
+    if (tc::elect_one()) tc::commit(smem_u32(c.bar_d));
+    __syncwarp();
+    { const long long c1 = clock64(); e_issue += c1 - ec; ec = c1; }
+  }
+  // stop: every MMA has completed (its D was consumed).  The producer can only be blocked on the
+  // slot of the next k-step to consume: complete that phase by hand (it re-checks the flag).
+  if (tc::elect_one()) {
+    mbar_arrive(&c.bar_empty[s]);
+    if (timing)
+      printf("[tc timing] mma warp: wait_a %lld issue %lld cycles, %u k-steps\n", e_wait, e_issue, consumed);
+  }
+  __syncwarp();
+}
+
+// Weight producer (one thread): streams the image cyclically (`per_cycle` k-steps) through the ring.
+__device__ __forceinline__ void tc_producer_thread(const TcGeom& g, const TcEngineCtx& c,
+                                                   const unsigned char* img, unsigned per_cycle) {
+  const unsigned stages = (unsigned)g.stages;
+  unsigned issued = 0;
+  for (;; ++issued) {
+    const unsigned q = issued, s = q % stages;
+    if (q >= stages) mbar_wait(&c.bar_empty[s], ((q / stages) - 1u) & 1u);
+    if (*c.stop_flag) break;
+    mbar_expect_tx(&c.bar_full[s], (unsigned)g.stage_bytes);
+    bulk_g2s(c.ring + (size_t)s * g.stage_bytes, img + (size_t)(q % per_cycle) * g.stage_bytes,
+             (unsigned)g.stage_bytes, &c.bar_full[s]);
+  }
+  // wait for the copies still in flight (the last `stages` issued chunks cover every slot once)
+  for (unsigned q = issued > stages ? issued - stages : 0; q < issued; ++q)
+    mbar_wait(&c.bar_full[q % stages], (q / stages) & 1u);
+}
+
 template <typename S, int G>
 __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const TcFwdParams tp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -399,7 +492,9 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
   double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);
   float* sp = reinterpret_cast<float*>(smem_raw + lay.off_sp);
   unsigned char* ring = smem_raw + lay.off_ring;
-  const unsigned stages = (unsigned)g.stages;
+  TcEngineCtx eng;
+  eng.bar_full = bar_full; eng.bar_empty = bar_empty; eng.bar_a = bar_a; eng.bar_d = bar_d;
+  eng.stop_flag = stop_flag; eng.ring = ring;
 
   // ---- one-time setup ------------------------------------------------------------------------------
   if (tid == 0) {
@@ -434,79 +529,10 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
   const uint32_t tbase = *tmem_slot;
 
   if (warp == kMmaWarp) {
-    // ================================ MMA issuer ========================================================
-    // The whole warp runs the loop (warp-uniform control flow and operands => the descriptors live in
-    // uniform registers and each MMA is one UTCHMMA); one elected lane issues the MMAs and commits.
-    const uint32_t idesc = tc::idesc_bf16_f32(kTcM, g.NP);
-    const uint64_t desc0 = tc::smem_desc(smem_u32(ring), 128, 256);
-    const uint32_t blk16 = (uint32_t)g.block_bytes >> 4, stage16 = (uint32_t)g.stage_bytes >> 4;
-    const uint32_t a_base = tbase + g.col_a;
-    unsigned s = 0, round = 0, consumed = 0, phase_a = 0;
-    long long e_wait = 0, e_issue = 0, ec = clock64();
-    while (true) {
-      mbar_wait(bar_a, phase_a);
-      phase_a ^= 1u;
-      if (*stop_flag) break;
-      tc::fence_after_sync();
-      { const long long c1 = clock64(); e_wait += c1 - ec; ec = c1; }
-#pragma unroll 1
-      for (int j = 0; j < g.KST; ++j) {
-        mbar_wait(&bar_full[s], round);
-        tc::fence_after_sync();
-        if (tc::elect_one()) {
-          const uint64_t b1 = desc0 + (uint64_t)(s * stage16);
-          const uint64_t b2 = b1 + blk16, b3 = b2 + blk16;
-          if (j < g.KSf) {
-            const bool full = (j | 1) < g.KSf;
-            const uint32_t a1 = a_base + 48 * (j >> 1) + (full ? 8 * (j & 1) : 0);
-            const uint32_t dt = full ? 16u : 8u;
-            tc::mma_ts(tbase, a1, b1, idesc, j > 0 ? 1u : 0u);
-            tc::mma_ts(tbase, a1 + dt, b1, idesc, 1u);
-            tc::mma_ts(tbase, a1 + 2 * dt, b1, idesc, 1u);
-            tc::mma_ts(tbase, a1, b2, idesc, 1u);
-            tc::mma_ts(tbase, a1 + dt, b2, idesc, 1u);
-            tc::mma_ts(tbase, a1, b3, idesc, 1u);
-          } else {
-            tc::mma_ts(tbase, tbase + g.col_t1, b1, idesc, j > 0 ? 1u : 0u);
-            tc::mma_ts(tbase, tbase + g.col_t1, b2, idesc, 1u);
-            tc::mma_ts(tbase, tbase + g.col_t2, b3, idesc, 1u);
-          }
-          tc::commit(smem_u32(&bar_empty[s]));   // slot free once these MMAs have read it
-        }
-        __syncwarp();
-        ++consumed;
-        if (++s == stages) { s = 0; round ^= 1u; }
-      }
-      if (tc::elect_one()) tc::commit(smem_u32(bar_d));
-      __syncwarp();
-      { const long long c1 = clock64(); e_issue += c1 - ec; ec = c1; }
-    }
-    // stop: every MMA has completed (its D was consumed).  The producer can only be blocked on the
-    // slot of the next k-step to consume: complete that phase by hand (it re-checks the flag).
-    if (tc::elect_one()) {
-      mbar_arrive(&bar_empty[s]);
-      if (tp.timing && blockIdx.x == 0)
-        printf("[tc timing] mma warp: wait_a %lld issue %lld cycles, %u k-steps\n", e_wait, e_issue, consumed);
-    }
-    __syncwarp();
+    tc_mma_warp(g, eng, tbase, tp.timing && blockIdx.x == 0);
   } else if (warp == kLoadWarp) {
-    // ================================ weight producer ===================================================
-    if ((tid & 31) == 0) {
-      const unsigned char* img = reinterpret_cast<const unsigned char*>(tp.img);
-      const unsigned per_cycle = (unsigned)(g.L * g.KST);
-      unsigned issued = 0;
-      for (;; ++issued) {
-        const unsigned q = issued, s = q % stages;
-        if (q >= stages) mbar_wait(&bar_empty[s], ((q / stages) - 1u) & 1u);
-        if (*stop_flag) break;
-        mbar_expect_tx(&bar_full[s], (unsigned)g.stage_bytes);
-        bulk_g2s(ring + (size_t)s * g.stage_bytes, img + (size_t)(q % per_cycle) * g.stage_bytes,
-                 (unsigned)g.stage_bytes, &bar_full[s]);
-      }
-      // wait for the copies still in flight (the last `stages` issued chunks cover every slot once)
-      for (unsigned q = issued > stages ? issued - stages : 0; q < issued; ++q)
-        mbar_wait(&bar_full[q % stages], (q / stages) & 1u);
-    }
+    if ((tid & 31) == 0) tc_producer_thread(g, eng, reinterpret_cast<const unsigned char*>(tp.img),
+                                            (unsigned)(g.L * g.KST));
   } else {
     // ================================ lane threads ======================================================
     TcLane tl;

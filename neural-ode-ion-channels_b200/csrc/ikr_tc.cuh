@@ -119,6 +119,10 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
          | ((uint32_t)(N >> 3) << 17)   // N / 8
          | ((uint32_t)(M >> 4) << 24);  // M / 16
 }
+// same with both operands MN-major (the reduction index is the slow one in shared memory)
+__host__ __device__ constexpr uint32_t idesc_bf16_f32_mn(int M, int N) {
+  return idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16);
+}
 // shared-memory matrix descriptor, no swizzle: start address, leading / stride byte offsets (all / 16)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -133,6 +137,16 @@ __device__ __forceinline__ void mma_ts(uint32_t d_taddr, uint32_t a_taddr, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_taddr),
       "r"(a_taddr), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T ; issued by ONE thread
+__device__ __forceinline__ void mma_ss(uint32_t d_taddr, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_taddr),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrive on an mbarrier once every MMA issued so far by this thread has completed

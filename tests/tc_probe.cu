@@ -290,6 +290,105 @@ static int run_tmem(int argc, char** argv) {
   return 0;
 }
 
+// ---- mode "mn": D[128 x N] = A[128 x K] . B[N x K]^T with BOTH operands MN-major in shared memory
+// (the weight-gradient GEMM: K = samples).  Image of one K = 16 step: [k / 8][mn / 8][k % 8][mn % 8] bf16.
+__global__ void __launch_bounds__(192, 1) mn_kernel(const void* a_img, const void* b_img, float* d_out, int N,
+                                                    int KS, uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b,
+                                                    uint32_t sbo_b) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
+  unsigned char* as = smem + 128;
+  const unsigned a_step = 2 * 16 * 128, b_step = 2 * (N / 8) * 128;
+  unsigned char* bs = as + KS * a_step;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 128) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+    mbar_expect_tx(&bar[0], KS * (a_step + b_step));
+    bulk_g2s(as, a_img, KS * a_step, &bar[0]);
+    bulk_g2s(bs, b_img, KS * b_step, &bar[0]);
+  }
+  if (warp == 5) tc::tmem_alloc(smem_u32(tmem_slot), tc::kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  if (tid == 160) {
+    mbar_wait(&bar[0], 0);
+    tc::fence_after_sync();
+    const uint32_t idesc = tc::idesc_bf16_f32_mn(128, N);
+    for (int ks = 0; ks < KS; ++ks)
+      tc::mma_ss(tbase, tc::smem_desc(smem_u32(as) + ks * a_step, lbo_a, sbo_a),
+                 tc::smem_desc(smem_u32(bs) + ks * b_step, lbo_b, sbo_b), idesc, ks > 0);
+    tc::commit(smem_u32(&bar[1]));
+  }
+  if (tid < 128) {
+    mbar_wait(&bar[1], 0);
+    tc::fence_after_sync();
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < N; c += 16) {
+      uint32_t v[16];
+      tc::ld16(lane_addr + c, v);
+      tc::wait_ld();
+      for (int j = 0; j < 16; ++j) d_out[(size_t)tid * N + c + j] = __uint_as_float(v[j]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tbase, tc::kTmemCols);
+}
+
+static uint16_t f2bf(float x);
+static float bf2f(uint16_t h);
+
+static int run_mn(int argc, char** argv) {
+  const int variant = argc > 2 ? atoi(argv[2]) : 0;
+  const int N = argc > 3 ? atoi(argv[3]) : 208;
+  const int KS = 8, K = KS * 16, M = 128;
+  std::vector<float> A((size_t)M * K), B((size_t)N * K);
+  srand(2);
+  for (auto& x : A) x = bf2f(f2bf((float)rand() / RAND_MAX - 0.5f));
+  for (auto& x : B) x = bf2f(f2bf((float)rand() / RAND_MAX - 0.5f));
+  auto image = [&](const std::vector<float>& X, int rows) {
+    const int groups = rows / 8;
+    std::vector<uint16_t> img((size_t)KS * 2 * groups * 64);
+    for (int r = 0; r < rows; ++r)
+      for (int k = 0; k < K; ++k) {
+        const size_t e = ((((size_t)(k / 16) * 2 + (k % 16) / 8) * groups + r / 8) * 8 + k % 8) * 8 + r % 8;
+        img[e] = f2bf(X[(size_t)r * K + k]);
+      }
+    return img;
+  };
+  std::vector<uint16_t> ai = image(A, M), bi = image(B, N);
+  uint32_t lbo_a = 16 * 128, sbo_a = 128, lbo_b = (N / 8) * 128, sbo_b = 128;
+  if (variant & 1) { uint32_t t = lbo_a; lbo_a = sbo_a; sbo_a = t; t = lbo_b; lbo_b = sbo_b; sbo_b = t; }
+  void *d_a, *d_b; float* d_d;
+  cudaMalloc(&d_a, ai.size() * 2); cudaMalloc(&d_b, bi.size() * 2); cudaMalloc(&d_d, (size_t)M * N * 4);
+  cudaMemcpy(d_a, ai.data(), ai.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_b, bi.data(), bi.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemset(d_d, 0xFF, (size_t)M * N * 4);
+  const size_t smem = 128 + ai.size() * 2 + bi.size() * 2;
+  cudaFuncSetAttribute(mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mn_kernel<<<1, 192, smem>>>(d_a, d_b, d_d, N, KS, lbo_a, sbo_a, lbo_b, sbo_b);
+  if (cudaDeviceSynchronize() != cudaSuccess) { printf("mn kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 2; }
+  std::vector<float> D((size_t)M * N);
+  cudaMemcpy(D.data(), d_d, D.size() * 4, cudaMemcpyDeviceToHost);
+  double max_err = 0; int bad = 0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double ref = 0;
+      for (int k = 0; k < K; ++k) ref += (double)A[(size_t)m * K + k] * (double)B[(size_t)n * K + k];
+      const double err = fabs(ref - (double)D[(size_t)m * N + n]);
+      if (!(err <= 1e-3)) ++bad;
+      if (err > max_err || err != err) max_err = err;
+    }
+  printf("mn variant %d N %d: lbo_a %u sbo_a %u lbo_b %u sbo_b %u: max_err %.3e bad %d/%d D[0][0..1] %g %g\n", variant, N,
+         lbo_a, sbo_a, lbo_b, sbo_b, max_err, bad, M * N, D[0], D[1]);
+  return bad == 0 ? 0 : 1;
+}
+
 static int run_pattern(int argc, char** argv) {
   const int flags = argc > 2 ? atoi(argv[2]) : 0;
   const int NP = argc > 3 ? atoi(argv[3]) : 208;
@@ -373,6 +472,7 @@ int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "stream")) return run_stream(argc, argv);
   if (argc > 1 && !strcmp(argv[1], "pattern")) return run_pattern(argc, argv);
   if (argc > 1 && !strcmp(argv[1], "tmem")) return run_tmem(argc, argv);
+  if (argc > 1 && !strcmp(argv[1], "mn")) return run_mn(argc, argv);
   const int variant = argc > 1 ? atoi(argv[1]) : 0;
   const int N = argc > 2 ? atoi(argv[2]) : 208;
   const int KS = argc > 3 ? atoi(argv[3]) : 13;
