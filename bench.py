@@ -278,6 +278,8 @@ def run_train_leg(args, ikr, dev, world, rank):
     total, grads, res = step()          # warm-up (also sizes the caching allocator)
     st = res.stats
     assert int((st[:, 3] != 0).sum()) == 0, 'solver status != ok in the training leg'
+    uses_tc = bool(res.geometry.get('tensor_cores'))
+    del total, grads, res, st        # the timed step reuses the cached allocations
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -311,7 +313,7 @@ def run_train_leg(args, ikr, dev, world, rank):
         'ms_per_step': ms_all, 'forward_evals': nfe_f_all, 'adjoint_evals': nfe_b_all,
         'accepted_steps_mean': float(st[:, 0].float().mean()),
         'algorithmic_tflops': (nfe_f * FLOP_PER_EVAL + nfe_b * 3 * FLOP_PER_EVAL) / (ms * 1e-3) / 1e12,
-        'loss': float(total), 'grad_abs_max': gmax,
+        'loss': float(total), 'grad_abs_max': gmax, 'tensor_cores': uses_tc,
     }
 
 

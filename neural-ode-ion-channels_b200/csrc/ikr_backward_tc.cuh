@@ -54,7 +54,7 @@ __host__ __device__ inline long long tc_stash_sample(int lane, int NG) {
 __host__ __device__ inline bool tc_backward_ok(const TcGeom& g) { return tc_geometry_ok(g) && g.tail == 1; }
 
 struct TcAdjParams {
-  BwdParams b;           // b.M == 128; tile geometry fields unused
+  BwdParams b;           // b.M = trajectories per tile (<= 128); other tile geometry fields unused
   TcGeom g;
   TcStashGeom sg;
   const void* img;       // [2L] layer images: forward W_1..W_L, then backward W_L..W_1 (transposed)
@@ -486,8 +486,8 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
         owners_sync();
         const long long tile = *tile_slot;
         if (tile >= p.n_tiles) break;
-        const long long b = tile * kTcM + tid;
-        const bool valid = b < jB;
+        const long long b = tile * p.M + tid;        // p.M <= 128 trajectories per tile
+        const bool valid = tid < p.M && b < jB;
         S g_b = (S)1, e_b = (S)p.e_scalar;
         BLane<S>& L = lanes[tid];
         if (p.first_round) {

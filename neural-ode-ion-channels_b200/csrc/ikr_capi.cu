@@ -242,6 +242,12 @@ TcPlan make_tc_plan(const ikr_desc* d) {
   return t;
 }
 
+// Trajectories per tile of the tensor-core kernels.  Always the 128 TMEM lanes: spreading a small
+// batch over more, thinner tiles was measured (B = 4,096 as 128 tiles of 32) and buys nothing -- a
+// tile's run time is its chain of sequential RHS evaluations (~31 us each) whatever its lane count,
+// and every tile already has an SM to itself -- while the backward stash grows with the tile count.
+int tc_tile_lanes(long long /*b_total*/, int /*sms*/) { return kTcM; }
+
 size_t fwd_fixed_workspace(int n_jobs) {
   return (256 + (size_t)n_jobs * sizeof(FwdJob) + 255) & ~(size_t)255;
 }
@@ -425,7 +431,7 @@ struct TcBwdPlan {
   int groups, mask_words;
   size_t smem;
   long long n_tiles;
-  int grid, sms;
+  int grid, sms, tile_lanes;
   int wg_S, wg_stages;
   size_t wg_smem;
   size_t off_counters, off_lanes, off_partial, off_img, fixed_bytes, partial_bytes, img_bytes;
@@ -449,7 +455,8 @@ TcBwdPlan make_tc_bwd_plan(const ikr_desc* d, long long B) {
   pl.g.stages = stages;
   pl.smem = fixed + (size_t)stages * pl.g.stage_bytes;
   pl.sms = device_sms();
-  pl.n_tiles = (B + kTcM - 1) / kTcM;
+  pl.tile_lanes = tc_tile_lanes(B, pl.sms);
+  pl.n_tiles = (B + pl.tile_lanes - 1) / pl.tile_lanes;
   pl.grid = (int)(pl.n_tiles < pl.sms ? pl.n_tiles : pl.sms);
   // weight-gradient GEMM: (L + 2) pseudo-layers x S splits
   pl.wg_S = pl.sms / (d->n_layers + 2);
@@ -535,7 +542,7 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
   p.mlp = mv;
   p.cfg = make_cfg(d);
   p.cfg.tab = make_table(io);
-  p.M = kTcM; p.MG = 0; p.NG = 0; p.n_worker_warps = 0;
+  p.M = pl.tile_lanes; p.MG = 0; p.NG = 0; p.n_worker_warps = 0;
   p.B = io->B; p.T = (int)io->T; p.n_tiles = pl.n_tiles;
   p.y0 = io->y0; p.t_out = io->t_out; p.stats = io->stats_out;
   p.ckpt_t = io->ckpt_t; p.ckpt_y = io->ckpt_y;
@@ -730,7 +737,11 @@ int32_t ikr_uses_tensor_cores(const ikr_desc* d) {
 int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B) {
   if (!valid_desc(d) || n_jobs < 1 || !B) return IKR_ERR_ARG;
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
-  if (make_tc_plan(d).ok) return kTcM;
+  if (make_tc_plan(d).ok) {
+    long long b_total = 0;
+    for (int j = 0; j < n_jobs; ++j) b_total += B[j];
+    return tc_tile_lanes(b_total, device_sms());
+  }
   return make_geometry(d, n_jobs, (const long long*)B, use_pool(d)).M;
 }
 
@@ -739,10 +750,12 @@ int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
   const TcPlan tcp = make_tc_plan(d);
   if (tcp.ok) {
-    long long tiles = 0;
-    for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + kTcM - 1) / kTcM;
     const int sms = device_sms();
-    out[0] = kTcM; out[1] = tc_threads(tcp.groups); out[2] = tiles < sms ? tiles : sms; out[3] = (int64_t)tcp.smem;
+    long long tiles = 0, b_total = 0;
+    for (int j = 0; j < n_jobs; ++j) b_total += B[j];
+    const int tl = tc_tile_lanes(b_total, sms);
+    for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + tl - 1) / tl;
+    out[0] = tl; out[1] = tc_threads(tcp.groups); out[2] = tiles < sms ? tiles : sms; out[3] = (int64_t)tcp.smem;
     out[4] = tiles; out[5] = 16; out[6] = tcp.g.KST; out[7] = sms;
     return 0;
   }
@@ -797,10 +810,12 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
   const bool pool = use_pool(d);
   Geometry g = make_geometry(d, n_jobs, Bs.data(), pool);
   if (tcp.ok) {
-    // tensor-core kernel: fixed 128-trajectory tiles (one per TMEM lane)
-    g.M = kTcM;
+    // tensor-core kernel: tiles of up to 128 trajectories (one per TMEM lane)
+    long long b_total = 0;
+    for (int j = 0; j < n_jobs; ++j) b_total += Bs[j];
+    g.M = tc_tile_lanes(b_total, g.sms);
     g.n_tiles = 0;
-    for (int j = 0; j < n_jobs; ++j) g.n_tiles += (Bs[j] + kTcM - 1) / kTcM;
+    for (int j = 0; j < n_jobs; ++j) g.n_tiles += (Bs[j] + g.M - 1) / g.M;
     g.grid = (int)(g.n_tiles < g.sms ? g.n_tiles : g.sms);
     g.threads = tc_threads(tcp.groups);
     g.smem = tcp.smem;

@@ -159,7 +159,8 @@ struct TcSmemLayout {
 };
 
 struct TcFwdParams {
-  FwdParams f;           // f.M == 128; MG / NG / n_worker_warps unused
+  FwdParams f;           // f.M = trajectories per tile (<= 128 TMEM lanes; fewer when the batch
+                         // would otherwise leave SMs idle); MG / NG / n_worker_warps unused
   TcGeom g;
   const void* img;       // weight image written by ikr_tc_pack_kernel
   int timing;            // debug: block 0 prints its phase clocks (IKR_TC_TIMING=1)
@@ -585,8 +586,8 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
         const bool observe = (job.v_out != nullptr) && (job.i_out != nullptr || job.loss_out != nullptr);
         const long long jB = job.B;
         const int T = job.T;
-        const long long b = (tile - job.tile_begin) * kTcM + tid;
-        const bool valid = b < jB;
+        const long long b = (tile - job.tile_begin) * p.M + tid;   // p.M <= 128 trajectories per tile
+        const bool valid = tid < p.M && b < jB;
         S g_b = (S)1, e_b = (S)job.e_scalar;
 
         auto emit = [&](int idx, S a, S r) {
