@@ -60,6 +60,7 @@ struct TcAdjParams {
   const void* img;       // [2L] layer images: forward W_1..W_L, then backward W_L..W_1 (transposed)
   unsigned char* stash;  // [slots][sg.slot]
   int mask_words;        // sign-bit words per thread per layer = units per group + 1
+  int timing;            // debug: block 0 prints its phase clocks (IKR_TC_TIMING=1)
 };
 
 template <typename S>
@@ -255,6 +256,7 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
   const bool tail_mine = tl.group == G - 1;     // tc_backward_ok: there is a tail
   const int w_tail = al.mask_words - 1;
   float acc = 0.0f;
+  long long c0 = clock64();
 
   // X = (nv, a, 1) and U = (up): two feature groups each, only the first one carries data
   if (tl.group == 0) {
@@ -298,9 +300,11 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
   for (int l = 1; l <= g.L; ++l) {
     const float* bias = tl.sp + (size_t)(2 + l) * NP;
     const bool last = l == g.L;
+    { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
     mbar_wait(tl.bar_d, tl.phase_d);
     tl.phase_d ^= 1u;
     tc::fence_after_sync();
+    { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
     for (int u = u_begin; u < u_end; ++u) {
       if (2 * u + 1 < g.KSf) {
         uint32_t v[32];
@@ -327,9 +331,11 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
   }
   // ---- backward: D = dz_l W_l  ->  dz_{l-1} = D * leaky'(H_{l-1}) ---------------------------------------
   for (int l = g.L; l >= 1; --l) {
+    { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
     mbar_wait(tl.bar_d, tl.phase_d);
     tl.phase_d ^= 1u;
     tc::fence_after_sync();
+    { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
     const bool first = l == 1;
     for (int u = u_begin; u < u_end; ++u) {
       if (2 * u + 1 < g.KSf) {
@@ -356,6 +362,7 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
     if (!first) tc_publish_a(tl);
   }
   tl.part[tl.group * kTcM + tl.lane] = acc;
+  { const long long c1 = clock64(); tl.c_epi += c1 - c0; }
 }
 
 // Owner-side wrapper of one adjoint evaluation: publish (nv, a, up), take a stash slot, run, collect.
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
   const uint32_t tbase = *tmem_slot;
 
   if (warp == kMmaWarp) {
-    tc_mma_warp(g, eng, tbase, false);
+    tc_mma_warp(g, eng, tbase, tp.timing && blockIdx.x == 0);
   } else if (warp == kLoadWarp) {
     if ((tid & 31) == 0)
       tc_producer_thread(g, eng, reinterpret_cast<const unsigned char*>(tp.img), (unsigned)(2 * g.L * g.KST));
@@ -452,6 +459,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
     tl.slope = (float)p.mlp.slope;
     tl.c_l0 = tl.c_wait = tl.c_epi = 0;
+    const long long c_begin = clock64();
     TcAdjLane al;
     al.samp = tc_stash_sample(tl.lane, sg.NGb);
     al.mask = reinterpret_cast<uint32_t*>(smem_raw + lay.off_mask);
@@ -582,6 +590,11 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
           saved[tile * kTcM + tid] = sv;
         }
         owners_sync();
+      }
+      if (tp.timing && blockIdx.x == 0 && tid == 0) {
+        const long long tot = clock64() - c_begin;
+        printf("[tc timing] adjoint owner 0: total %lld cycles: wait_d %lld, epilogues+layer0+stash %lld, "
+               "solver+other %lld\n", tot, tl.c_wait, tl.c_epi, tot - tl.c_wait - tl.c_epi);
       }
       if (tid == 0) { *cmd_exit = 1; *stop_flag = 1; }
       owners_sync();

@@ -560,6 +560,7 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
   tp.img = ws + pl.off_img;
   tp.stash = ws + off_stash;
   tp.mask_words = pl.mask_words;
+  tp.timing = getenv("IKR_TC_TIMING") != nullptr;
 
   TcWgradParams wp;
   wp.g = pl.g; wp.sg = pl.sg;
