@@ -104,6 +104,17 @@ __device__ __forceinline__ void tc_stash_groups(const TcStashGeom& sg, const TcA
 }
 
 // ---- adjoint epilogue work units ---------------------------------------------------------------------
+// Sign bookkeeping: LeakyReLU keeps the sign of its argument, and so does the bf16 rounding of the
+// first split term, so the "negative" flags of a pair (features 2q, 2q + 1) are bits 15 and 31 of the
+// packed term-1 word; word q of a unit contributes them as bits q and 16 + q of the unit's mask word.
+__device__ __forceinline__ uint32_t tc_sign_bits(uint32_t bits, uint32_t w1, int q) {
+  return bits | ((w1 >> (15 - q)) & (0x00010001u << q));
+}
+// (1 or slope) factors of pair q from a mask word
+__device__ __forceinline__ tc::f32x2_t tc_leaky_grad2(uint32_t bits, int q, float slope) {
+  return tc::p2((bits & (1u << q)) ? slope : 1.0f, (bits & (0x10000u << q)) ? slope : 1.0f);
+}
+
 // MODE 0: forward hidden/first layer: v + bias -> LeakyReLU -> sign bits, A operand, stash Hc_l
 // MODE 1: forward LAST layer (H_L): stash Hc_L; dz_L = up w_last leaky'(H_L) -> A operand, stash dz_L
 // MODE 2: backward layer: dz = v * leaky'(sign bits) -> A operand, stash dz
@@ -113,45 +124,53 @@ __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& 
                                             const TcAdjLane& al, int u, int w_idx, int layer,
                                             const float* bias, uint32_t (&v)[16 * NK], float up,
                                             float& acc) {
-  constexpr int NV = 16 * NK;
+  constexpr int NP2 = 8 * NK;       // pairs
   const int c0 = 32 * u;
   const float slope = tl.slope;
-  uint32_t bits = 0;
+  const tc::f32x2_t slope2 = tc::p2(slope, slope);
   uint32_t* mword = al.mask + ((size_t)layer * al.mask_words + w_idx) * al.nthreads + al.tid;
+  tc::f32x2_t h[NP2];
+  uint32_t w12[2 * NP2], w3[NP2];
+  uint32_t bits = 0;
   if (MODE == 0 || MODE == 1) {
 #pragma unroll
-    for (int q = 0; q < NV / 4; ++q) {
+    for (int q = 0; q < NP2 / 2; ++q) {
       const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float z = __uint_as_float(v[4 * q + e]) + bv[e];
-        bits |= (z > 0.0f ? 1u : 0u) << (4 * q + e);
-        v[4 * q + e] = __float_as_uint(tc_leaky(z, slope));
-      }
+      h[2 * q] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                                     tc::p2(bb.x, bb.y)), slope2);
+      h[2 * q + 1] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])),
+                                         tc::p2(bb.z, bb.w)), slope2);
     }
-    if (MODE == 0) *mword = bits;
+#pragma unroll
+    for (int q = 0; q < NP2; ++q) {
+      tc::split3p(h[q], w12[q], w12[NP2 + q], w3[q]);
+      bits = tc_sign_bits(bits, w12[q], q);
+    }
+    if (MODE == 0) {
+      *mword = bits;
+    } else {
+      // H_L only feeds the output layer: stash it (two terms), then form dz_L = up w_last leaky'(H_L)
+      tc_stash_groups<2 * NK>(sg, al, tc_stash_h(sg, g.L), 4 * u, w12, w12 + NP2);
+      const float* wl = tl.sp + (size_t)(3 + g.L) * g.NP + c0;
+      const tc::f32x2_t up2 = tc::p2(up, up);
+#pragma unroll
+      for (int q = 0; q < NP2 / 2; ++q) {
+        const float4 ww = *reinterpret_cast<const float4*>(wl + 4 * q);
+        h[2 * q] = tc::mul2(tc::mul2(tc::p2(ww.x, ww.y), up2), tc_leaky_grad2(bits, 2 * q, slope));
+        h[2 * q + 1] = tc::mul2(tc::mul2(tc::p2(ww.z, ww.w), up2), tc_leaky_grad2(bits, 2 * q + 1, slope));
+      }
+#pragma unroll
+      for (int q = 0; q < NP2; ++q) tc::split3p(h[q], w12[q], w12[NP2 + q], w3[q]);
+    }
   } else {
     bits = *mword;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      v[i] = __float_as_uint(__uint_as_float(v[i]) * (((bits >> i) & 1u) ? 1.0f : slope));
+    for (int q = 0; q < NP2; ++q) {
+      h[q] = tc::mul2(tc::p2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])),
+                      tc_leaky_grad2(bits, q, slope));
+      tc::split3p(h[q], w12[q], w12[NP2 + q], w3[q]);
+    }
   }
-  uint32_t w12[2 * 8 * NK], w3[8 * NK];
-  if (MODE == 1) {
-    // H_L only feeds the output layer: stash it (two terms), then form dz_L in place
-#pragma unroll
-    for (int q = 0; q < 8 * NK; ++q)
-      tc::split3(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), w12[q], w12[8 * NK + q], w3[q]);
-    tc_stash_groups<2 * NK>(sg, al, tc_stash_h(sg, g.L), 4 * u, w12, w12 + 8 * NK);
-    const float* wl = tl.sp + (size_t)(3 + g.L) * g.NP + c0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-      v[i] = __float_as_uint((wl[i] * up) * (((bits >> i) & 1u) ? 1.0f : slope));
-  }
-#pragma unroll
-  for (int q = 0; q < 8 * NK; ++q)
-    tc::split3(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), w12[q], w12[8 * NK + q], w3[q]);
   if (MODE != 3) {
     const uint32_t dst = tl.taddr + g.col_a + 48 * u;
     if (NK == 2) {
@@ -164,12 +183,17 @@ __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& 
   } else {
     const float* w0b = tl.sp + g.NP + c0;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) acc = __fmaf_rn(__uint_as_float(v[i]), w0b[i], acc);
+    for (int q = 0; q < NP2; ++q) {
+      float d0, d1;
+      tc::u2(h[q], d0, d1);
+      acc = __fmaf_rn(d0, w0b[2 * q], acc);
+      acc = __fmaf_rn(d1, w0b[2 * q + 1], acc);
+    }
   }
   // stash: MODE 0 -> Hc_layer, MODE 1 -> dz_L, MODE 2 -> dz_{layer}, MODE 3 -> dz_0
   const long long mat = MODE == 0 ? tc_stash_h(sg, layer)
                                   : tc_stash_dz(sg, MODE == 1 ? g.L : (MODE == 2 ? layer : 0));
-  tc_stash_groups<2 * NK>(sg, al, mat, 4 * u, w12, w12 + 8 * NK);
+  tc_stash_groups<2 * NK>(sg, al, mat, 4 * u, w12, w12 + NP2);
 }
 
 // the 8 tail features (feature group 2 KSf) -- same four modes; also writes the constant-1 feature of Hc
@@ -180,23 +204,11 @@ __device__ __forceinline__ void tc_adj_tail(const TcGeom& g, const TcStashGeom& 
   const int c0 = 16 * g.KSf;
   const int grp = 2 * g.KSf;
   const float slope = tl.slope;
-  uint32_t bits = 0;
+  const tc::f32x2_t slope2 = tc::p2(slope, slope);
   uint32_t* mword = al.mask + ((size_t)layer * al.mask_words + w_idx) * al.nthreads + al.tid;
-  if (MODE == 0 || MODE == 1) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float z = __uint_as_float(v[i]) + bias[c0 + i];
-      bits |= (z > 0.0f ? 1u : 0u) << i;
-      v[i] = __float_as_uint(tc_leaky(z, slope));
-    }
-    if (MODE == 0) *mword = bits;
-  } else {
-    bits = *mword;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      v[i] = __float_as_uint(__uint_as_float(v[i]) * (((bits >> i) & 1u) ? 1.0f : slope));
-  }
+  tc::f32x2_t h[4];
   uint32_t t1[4], t2[4], t3[4];
+  uint32_t bits = 0;
   const int ones = g.n - c0;   // position of the constant-1 feature: 1..8 (8 => next feature group)
   auto stash_h = [&](int l) {
     // Hc_l tail group with the constant-1 feature (index n) patched in
@@ -216,19 +228,41 @@ __device__ __forceinline__ void tc_adj_tail(const TcGeom& g, const TcStashGeom& 
       tc_stash_groups<1>(sg, al, tc_stash_h(sg, l), grp + 1, o1, o2);
     }
   };
-  if (MODE == 1) {
+  if (MODE == 0 || MODE == 1) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      tc::split3(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), t1[q], t2[q], t3[q]);
-    stash_h(g.L);
-    const float* wl = tl.sp + (size_t)(3 + g.L) * g.NP + c0;
+    for (int q = 0; q < 2; ++q) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
+      h[2 * q] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                                     tc::p2(bb.x, bb.y)), slope2);
+      h[2 * q + 1] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])),
+                                         tc::p2(bb.z, bb.w)), slope2);
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      v[i] = __float_as_uint((wl[i] * up) * (((bits >> i) & 1u) ? 1.0f : slope));
+    for (int q = 0; q < 4; ++q) {
+      tc::split3p(h[q], t1[q], t2[q], t3[q]);
+      bits = tc_sign_bits(bits, t1[q], q);
+    }
+    if (MODE == 0) {
+      *mword = bits;
+    } else {
+      stash_h(g.L);
+      const float* wl = tl.sp + (size_t)(3 + g.L) * g.NP + c0;
+      const tc::f32x2_t up2 = tc::p2(up, up);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        h[q] = tc::mul2(tc::mul2(tc::p2(wl[2 * q], wl[2 * q + 1]), up2), tc_leaky_grad2(bits, q, slope));
+        tc::split3p(h[q], t1[q], t2[q], t3[q]);
+      }
+    }
+  } else {
+    bits = *mword;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      h[q] = tc::mul2(tc::p2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])),
+                      tc_leaky_grad2(bits, q, slope));
+      tc::split3p(h[q], t1[q], t2[q], t3[q]);
+    }
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    tc::split3(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), t1[q], t2[q], t3[q]);
   if (MODE != 3) {
     const uint32_t t[16] = {t1[0], t1[1], t1[2], t1[3], t2[0], t2[1], t2[2], t2[3],
                             t1[0], t1[1], t1[2], t1[3], t3[0], t3[1], t3[2], t3[3]};
@@ -236,7 +270,12 @@ __device__ __forceinline__ void tc_adj_tail(const TcGeom& g, const TcStashGeom& 
   } else {
     const float* w0b = tl.sp + g.NP + c0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc = __fmaf_rn(__uint_as_float(v[i]), w0b[i], acc);
+    for (int q = 0; q < 4; ++q) {
+      float d0, d1;
+      tc::u2(h[q], d0, d1);
+      acc = __fmaf_rn(d0, w0b[2 * q], acc);
+      acc = __fmaf_rn(d1, w0b[2 * q + 1], acc);
+    }
   }
   if (MODE == 0) stash_h(layer);
   else tc_stash_groups<1>(sg, al, tc_stash_dz(sg, MODE == 1 ? g.L : (MODE == 2 ? layer : 0)), grp, t1, t2);
@@ -416,7 +455,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
       mbar_init(&eng.bar_full[s], 1);
       mbar_init(&eng.bar_empty[s], 1);
     }
-    mbar_init(eng.bar_a, kLaneThreads);
+    mbar_init(eng.bar_a, kLaneThreads / 32);
     mbar_init(eng.bar_d, 1);
     mbar_fence_init();
     *stop_flag = 0;
@@ -600,7 +639,8 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
       owners_sync();
       if (G > 1) lanes_sync<G>();
     }
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
+    __syncwarp();
+    if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
   }
 
   tc::fence_before_sync();

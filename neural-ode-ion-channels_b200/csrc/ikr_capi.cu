@@ -224,6 +224,7 @@ TcPlan make_tc_plan(const ikr_desc* d) {
   t.smem = 0; t.img_bytes = 0;
   t.g = tc_geometry(d->n_nodes, d->n_layers);
   if (d->mlp_dtype != IKR_F32 || (d->reserved & 2) || use_pool(d) || d->tile_m > 0) return t;
+  if (!(d->negative_slope >= 0.0 && d->negative_slope <= 1.0)) return t;   // epilogues use max(z, slope z)
   if (!tc_geometry_ok(t.g)) return t;
   t.groups = kTcDefaultGroups;
   if (const char* e = getenv("IKR_TC_GROUPS")) {   // tuning / A-B runs

@@ -196,14 +196,20 @@ struct TcLane {
   float* part;           // [G][128] partial output sums
   float slope;
   long long c_l0, c_wait, c_epi;   // phase clocks (timing runs)
+#ifdef IKR_TC_TRACE
+  int trace_eval;
+#endif
 };
 
 __device__ __forceinline__ float tc_leaky(float x, float slope) { return x > 0.0f ? x : x * slope; }
 
+// A operand of this thread is in TMEM: one arrival per WARP on a_ready (every lane orders its stores
+// before the warp barrier; 12 arrivals instead of 384 keep the mbarrier off the critical path)
 __device__ __forceinline__ void tc_publish_a(const TcLane& tl) {
   tc::wait_st();
   tc::fence_before_sync();
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
+  __syncwarp();
+  if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
 }
 
 // One epilogue work unit of NK = 1 or 2 k-steps (16 NK features starting at feature c0): the
@@ -215,20 +221,20 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
                                                uint32_t (&v)[16 * NK], bool last, const float* wl,
                                                float (&s)[4]) {
   const int c0 = 32 * u;
-  const float slope = tl.slope;
+  const tc::f32x2_t slope2 = tc::p2(tl.slope, tl.slope);
+  tc::f32x2_t h[8 * NK];
 #pragma unroll
   for (int q = 0; q < 4 * NK; ++q) {
     const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-    v[4 * q + 0] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 0]) + bb.x, slope));
-    v[4 * q + 1] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 1]) + bb.y, slope));
-    v[4 * q + 2] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 2]) + bb.z, slope));
-    v[4 * q + 3] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 3]) + bb.w, slope));
+    h[2 * q] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                                   tc::p2(bb.x, bb.y)), slope2);
+    h[2 * q + 1] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])),
+                                       tc::p2(bb.z, bb.w)), slope2);
   }
   if (!last) {
     uint32_t w12[16 * NK], w3[8 * NK];
 #pragma unroll
-    for (int q = 0; q < 8 * NK; ++q)
-      tc::split3(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), w12[q], w12[8 * NK + q], w3[q]);
+    for (int q = 0; q < 8 * NK; ++q) tc::split3p(h[q], w12[q], w12[8 * NK + q], w3[q]);
     const uint32_t dst = tl.taddr + g.col_a + 48 * u;
     if (NK == 2) {
       tc::st32(dst, reinterpret_cast<uint32_t(&)[32]>(w12));
@@ -241,10 +247,13 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
 #pragma unroll
     for (int q = 0; q < 4 * NK; ++q) {
       const float4 ww = *reinterpret_cast<const float4*>(wl + c0 + 4 * q);
-      s[0] = __fmaf_rn(__uint_as_float(v[4 * q + 0]), ww.x, s[0]);
-      s[1] = __fmaf_rn(__uint_as_float(v[4 * q + 1]), ww.y, s[1]);
-      s[2] = __fmaf_rn(__uint_as_float(v[4 * q + 2]), ww.z, s[2]);
-      s[3] = __fmaf_rn(__uint_as_float(v[4 * q + 3]), ww.w, s[3]);
+      float h0, h1, h2, h3;
+      tc::u2(h[2 * q], h0, h1);
+      tc::u2(h[2 * q + 1], h2, h3);
+      s[0] = __fmaf_rn(h0, ww.x, s[0]);
+      s[1] = __fmaf_rn(h1, ww.y, s[1]);
+      s[2] = __fmaf_rn(h2, ww.z, s[2]);
+      s[3] = __fmaf_rn(h3, ww.w, s[3]);
     }
   }
 }
@@ -252,20 +261,21 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
 __device__ __forceinline__ void tc_tail_finish(const TcGeom& g, const TcLane& tl, const float* bias,
                                                uint32_t (&v)[8], bool last, const float* wl, float (&s)[4]) {
   const int c0 = 16 * g.KSf;
-  const float slope = tl.slope;
+  const tc::f32x2_t slope2 = tc::p2(tl.slope, tl.slope);
+  tc::f32x2_t h[4];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-    v[4 * q + 0] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 0]) + bb.x, slope));
-    v[4 * q + 1] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 1]) + bb.y, slope));
-    v[4 * q + 2] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 2]) + bb.z, slope));
-    v[4 * q + 3] = __float_as_uint(tc_leaky(__uint_as_float(v[4 * q + 3]) + bb.w, slope));
+    h[2 * q] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                                   tc::p2(bb.x, bb.y)), slope2);
+    h[2 * q + 1] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])),
+                                       tc::p2(bb.z, bb.w)), slope2);
   }
   if (!last) {
     uint32_t t[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      tc::split3(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), t[q], t[4 + q], t[12 + q]);
+      tc::split3p(h[q], t[q], t[4 + q], t[12 + q]);
       t[8 + q] = t[q];
     }
     tc::st16(tl.taddr + g.col_t1, t);
@@ -273,10 +283,13 @@ __device__ __forceinline__ void tc_tail_finish(const TcGeom& g, const TcLane& tl
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const float4 ww = *reinterpret_cast<const float4*>(wl + c0 + 4 * q);
-      s[0] = __fmaf_rn(__uint_as_float(v[4 * q + 0]), ww.x, s[0]);
-      s[1] = __fmaf_rn(__uint_as_float(v[4 * q + 1]), ww.y, s[1]);
-      s[2] = __fmaf_rn(__uint_as_float(v[4 * q + 2]), ww.z, s[2]);
-      s[3] = __fmaf_rn(__uint_as_float(v[4 * q + 3]), ww.w, s[3]);
+      float h0, h1, h2, h3;
+      tc::u2(h[2 * q], h0, h1);
+      tc::u2(h[2 * q + 1], h2, h3);
+      s[0] = __fmaf_rn(h0, ww.x, s[0]);
+      s[1] = __fmaf_rn(h1, ww.y, s[1]);
+      s[2] = __fmaf_rn(h2, ww.z, s[2]);
+      s[3] = __fmaf_rn(h3, ww.w, s[3]);
     }
   }
 }
@@ -344,12 +357,23 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl) {
     tl.phase_d ^= 1u;
     tc::fence_after_sync();
     { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
+#ifdef IKR_TC_TRACE
+    long long tr[8]; int ti = 0;
+    const bool tracing = layer == 1 && tl.trace_eval == 300 && blockIdx.x == 0;   // warp-uniform
+    if (tracing) tr[ti++] = clock64();
+#endif
     for (int u = u_begin; u < u_end; ++u) {
       if (2 * u + 1 < g.KSf) {
         uint32_t v[32];
         tc::ld32(tl.taddr + 32 * u, v);
         tc::wait_ld();
+#ifdef IKR_TC_TRACE
+        if (tracing && ti < 7) tr[ti++] = clock64();
+#endif
         tc_unit_finish<2>(g, tl, u, bias, v, last, wl, s);
+#ifdef IKR_TC_TRACE
+        if (tracing && ti < 7) tr[ti++] = clock64();
+#endif
       } else {
         uint32_t v[16];
         tc::ld16(tl.taddr + 32 * u, v);
@@ -363,9 +387,22 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl) {
       tc::wait_ld();
       tc_tail_finish(g, tl, bias, v, last, wl, s);
     }
+#ifdef IKR_TC_TRACE
+    if (tracing) { tr[ti++] = clock64(); tc::wait_st(); tr[ti++] = clock64(); }
+#endif
     if (!last) tc_publish_a(tl);
+#ifdef IKR_TC_TRACE
+    if (tracing && (threadIdx.x & 31) == 0) {
+      const long long te = clock64();
+      printf("[trace] warp %d (group %d): d_ready->ld0 %lld, unit0 %lld, ld1 %lld, unit1 %lld, tail.. %lld, wait_st %lld, publish %lld | abs start %lld end %lld\n",
+             (int)(threadIdx.x >> 5), tl.group, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], te - tr[6], tr[0], te);
+    }
+#endif
     { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
   }
+#ifdef IKR_TC_TRACE
+  ++tl.trace_eval;
+#endif
   tl.part[tl.group * kTcM + tl.lane] = (s[0] + s[1]) + (s[2] + s[3]);
 }
 
@@ -503,7 +540,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    mbar_init(bar_a, kLaneThreads);
+    mbar_init(bar_a, kLaneThreads / 32);
     mbar_init(bar_d, 1);
     mbar_fence_init();
     *stop_flag = 0;
@@ -548,6 +585,9 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
     tl.slope = (float)p.mlp.slope;
     tl.c_l0 = tl.c_wait = tl.c_epi = 0;
+#ifdef IKR_TC_TRACE
+    tl.trace_eval = 0;
+#endif
     const long long c_begin = clock64();
 
     if (tl.group > 0) {
@@ -703,7 +743,8 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
       if (G > 1) lanes_sync<G>();
     }
     // one more a_ready phase wakes the MMA thread, which sees the stop flag
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
+    __syncwarp();
+    if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
   }
 
   tc::fence_before_sync();

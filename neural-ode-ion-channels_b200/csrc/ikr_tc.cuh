@@ -172,6 +172,53 @@ __device__ __forceinline__ void split3(float x0, float x1, uint32_t& w1, uint32_
   w3 = pack_bf16x2(r0, r1);
 }
 
+
+// ---- packed fp32 pairs (FADD2 / FMUL2 on sm_100): halve the issue slots of the epilogues -------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t p2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void u2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// LeakyReLU of a pair for 0 <= slope <= 1: max(z, slope z)
+__device__ __forceinline__ f32x2_t leaky2(f32x2_t z, f32x2_t slope2) {
+  const f32x2_t s = mul2(z, slope2);
+  float z0, z1, s0, s1;
+  u2(z, z0, z1);
+  u2(s, s0, s1);
+  return p2(fmaxf(z0, s0), fmaxf(z1, s1));
+}
+// bf16x3 split of a pair with packed subtractions (same values as split3)
+__device__ __forceinline__ void split3p(f32x2_t h, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+  float a, b;
+  u2(h, a, b);
+  w1 = pack_bf16x2(a, b);
+  f32x2_t r = sub2(h, p2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xFFFF0000u)));
+  u2(r, a, b);
+  w2 = pack_bf16x2(a, b);
+  r = sub2(r, p2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xFFFF0000u)));
+  u2(r, a, b);
+  w3 = pack_bf16x2(a, b);
+}
+
 }  // namespace tc
 }  // namespace ikr
 #endif  // IKR_TC_CUH_
