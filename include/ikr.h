@@ -169,6 +169,34 @@ int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, voi
  * io->weights and the checkpoint fields are ignored.  No workspace.                              */
 int ikr_forward_hh(const ikr_desc* d, const ikr_io* io, const double* hh_params, void* cuda_stream);
 
+/* 6-state Markov ground-truth model of the synthetic-data studies (train-d1.py:134-187 `Lambda`:
+ * states [c1, c2, i, ic1, ic2, o], rate parameters p1..p12) and its data production step
+ * (train-d1.py:539-569): `odeint(true_model, true_y0, t)` then
+ * `true_y[:, 0, -1] * (V(t) + 86) + N(0, noise_sigma^2)`.  Batched: trajectory b has its own
+ * initial state, parameters (nullable: `p` for everyone), conductance and noise stream (Philox,
+ * subsequence b of `seed`).  `desc` supplies method / state dtype / tolerances.  No workspace.     */
+typedef struct ikr_markov_io {
+  int64_t B, T, G;
+  const double* table_t;  /* protocol table, as in ikr_io                                         */
+  const double* table_v;
+  int32_t table_len, table_uniform;
+  double table_t0, table_inv_dt;
+  const void* y0;         /* [B,6] state dtype                                                     */
+  const double* t_out;    /* [T]                                                                   */
+  const double* grid;     /* [G] rk4                                                               */
+  const double* v_out;    /* [T] V(t_out); required with i_out                                     */
+  const double* params;   /* [B,12] per-trajectory p1..p12 (nullable)                              */
+  double p[12];           /* shared p1..p12 when params is null                                    */
+  const void* g;          /* [B] state dtype conductance (nullable => 1)                           */
+  double e_rev;           /* -86 in the reference                                                  */
+  double noise_sigma;     /* 0: noise-free current                                                 */
+  uint64_t seed;
+  void* y_out;            /* [T,B,6] state dtype (nullable)                                        */
+  double* i_out;          /* [T,B] fp64 current (+ noise) (nullable)                               */
+  int32_t* stats_out;     /* [B,4] n_accept, n_reject, nfe, status                                 */
+} ikr_markov_io;
+int ikr_forward_markov(const ikr_desc* d, const ikr_markov_io* io, void* cuda_stream);
+
 /* V(t) of the protocol table at T query times (scipy interp1d linear semantics; out-of-table
  * => -80 like the callers' ValueError branch, train-s1.py:234-237).                             */
 int ikr_interp_protocol(const ikr_io* table, const double* t_query, int64_t T, double* v_out,

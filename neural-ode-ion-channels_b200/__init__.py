@@ -15,6 +15,7 @@ from .models import (ARCHITECTURES, PARAMETER_SETS, ODEFunc, ODEFuncNNd, ODEFunc
 from .solver import IkrResult, describe, integrate, integrate_many, odeint  # noqa: F401
 from .adjoint import loss_and_grad  # noqa: F401
 from .hh import HHPopulationModel, integrate_hh  # noqa: F401
+from .markov import MARKOV_B06, MarkovGroundTruth, integrate_markov  # noqa: F401
 
-__all__ = ['odeint', 'integrate', 'loss_and_grad', 'integrate_hh', 'HHPopulationModel', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
+__all__ = ['odeint', 'integrate', 'loss_and_grad', 'integrate_hh', 'HHPopulationModel', 'integrate_markov', 'MarkovGroundTruth', 'MARKOV_B06', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
            'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols', 'parallel']

@@ -48,6 +48,17 @@ class IkrIO(ctypes.Structure):
     ]
 
 
+class IkrMarkovIO(ctypes.Structure):
+    _fields_ = [
+        ('B', c_i64), ('T', c_i64), ('G', c_i64),
+        ('table_t', c_vp), ('table_v', c_vp), ('table_len', c_i32), ('table_uniform', c_i32),
+        ('table_t0', c_f64), ('table_inv_dt', c_f64),
+        ('y0', c_vp), ('t_out', c_vp), ('grid', c_vp), ('v_out', c_vp), ('params', c_vp),
+        ('p', c_f64 * 12), ('g', c_vp), ('e_rev', c_f64), ('noise_sigma', c_f64),
+        ('seed', ctypes.c_uint64), ('y_out', c_vp), ('i_out', c_vp), ('stats_out', c_vp),
+    ]
+
+
 class IkrBwdIO(ctypes.Structure):
     _fields_ = [
         ('grad_y', c_vp), ('fused_loss', c_i32), ('reserved', c_i32),
@@ -95,6 +106,8 @@ def lib():
                                ctypes.POINTER(IkrBwdIO), c_vp, ctypes.c_size_t, c_vp]
     L.ikr_forward_hh.restype = c_i32
     L.ikr_forward_hh.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(IkrIO), c_vp, c_vp]
+    L.ikr_forward_markov.restype = c_i32
+    L.ikr_forward_markov.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(IkrMarkovIO), c_vp]
     L.ikr_interp_protocol.restype = c_i32
     L.ikr_interp_protocol.argtypes = [ctypes.POINTER(IkrIO), c_vp, c_i64, c_vp, c_vp]
     L.ikr_fma_peak.restype = c_i32
@@ -107,7 +120,8 @@ def lib():
 
 EXPORTS = ('ikr_abi_version', 'ikr_error_string', 'ikr_packed_weight_elems', 'ikr_packed_layout',
            'ikr_param_count', 'ikr_uses_tensor_cores', 'ikr_tile_m', 'ikr_launch_geometry', 'ikr_workspace_bytes',
-           'ikr_forward', 'ikr_backward', 'ikr_forward_hh', 'ikr_interp_protocol', 'ikr_fma_peak')
+           'ikr_forward', 'ikr_backward', 'ikr_forward_hh', 'ikr_forward_markov', 'ikr_interp_protocol',
+           'ikr_fma_peak')
 
 
 def check(code, what):

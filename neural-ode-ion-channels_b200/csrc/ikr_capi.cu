@@ -12,6 +12,7 @@
 #include "ikr_backward.cuh"
 #include "ikr_backward_tc.cuh"
 #include "ikr_hh.cuh"
+#include "ikr_markov.cuh"
 
 using namespace ikr;
 
@@ -928,6 +929,36 @@ int ikr_forward_hh(const ikr_desc* d, const ikr_io* io, const double* hh_params,
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (d->state_dtype == IKR_F32) ikr_hh_kernel<float><<<blocks, threads, 0, st>>>(p);
   else ikr_hh_kernel<double><<<blocks, threads, 0, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
+int ikr_forward_markov(const ikr_desc* d, const ikr_markov_io* io, void* cuda_stream) {
+  if (!d || !io) return IKR_ERR_ARG;
+  if (d->state_dtype != IKR_F32 && d->state_dtype != IKR_F64) return IKR_ERR_ARG;
+  if (d->method != IKR_DOPRI5 && d->method != IKR_RK4) return IKR_ERR_ARG;
+  if (io->B < 1 || io->T < 1 || !io->table_t || !io->table_v || io->table_len < 2 || !io->y0 ||
+      !io->t_out || !io->stats_out)
+    return IKR_ERR_ARG;
+  if (d->method == IKR_RK4 && (!io->grid || io->G < 1)) return IKR_ERR_ARG;
+  if (io->i_out && !io->v_out) return IKR_ERR_ARG;
+  if (io->T > 2147483647LL || io->G > 2147483647LL || !(io->noise_sigma >= 0.0)) return IKR_ERR_ARG;
+  MarkovKernelParams p;
+  p.cfg = make_cfg(d);
+  p.cfg.tab.t = io->table_t; p.cfg.tab.v = io->table_v; p.cfg.tab.len = io->table_len;
+  p.cfg.tab.uniform = io->table_uniform; p.cfg.tab.t0 = io->table_t0; p.cfg.tab.inv_dt = io->table_inv_dt;
+  for (int i = 0; i < 12; ++i) p.p[i] = io->p[i];
+  p.params = io->params;
+  p.B = io->B; p.T = (int)io->T; p.G = (int)io->G;
+  p.y0 = io->y0; p.t_out = io->t_out; p.grid = io->grid; p.v_out = io->v_out;
+  p.y_out = io->y_out; p.i_out = io->i_out; p.g = io->g; p.e_rev = io->e_rev;
+  p.noise_sigma = io->noise_sigma; p.seed = io->seed;
+  p.stats_out = io->stats_out;
+  p.method = d->method; p.time_f32 = d->time_f32; p.rk4_perturb = d->rk4_perturb;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((io->B + threads - 1) / threads);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (d->state_dtype == IKR_F32) ikr_markov_kernel<float><<<blocks, threads, 0, st>>>(p);
+  else ikr_markov_kernel<double><<<blocks, threads, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
 }
 

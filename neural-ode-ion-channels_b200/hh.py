@@ -22,7 +22,8 @@ _HH_KEYS = tuple('p%d' % i for i in range(1, 9))
 
 def is_hh_func(func):
     """A reference-style HH ODE func: scalars p1..p8, a protocol, and no ``net``."""
-    return getattr(func, 'net', None) is None and all(hasattr(func, k) for k in _HH_KEYS)
+    return (getattr(func, 'net', None) is None and all(hasattr(func, k) for k in _HH_KEYS)
+            and not hasattr(func, 'p9'))     # p1..p12 => the 6-state Markov model (markov.py)
 
 
 def hh_params_of(func):

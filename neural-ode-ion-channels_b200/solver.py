@@ -407,9 +407,10 @@ def _prepare_job(dm, desc, method, opts, dev, lib, sptr, job, state_dtype):
     return io, res
 
 
-def _check_job_inputs(y0, t):
-    if not isinstance(y0, torch.Tensor) or y0.dim() != 2 or y0.shape[1] != 2:
-        raise TypeError('odeint: y0 must be a (B, 2) tensor of (a, r) states')
+def _check_job_inputs(y0, t, n_state=2):
+    if not isinstance(y0, torch.Tensor) or y0.dim() != 2 or y0.shape[1] != n_state:
+        raise TypeError('odeint: y0 must be a (B, 2) tensor of (a, r) states' if n_state == 2 else
+                        'odeint: y0 must be a (B, %d) state tensor' % n_state)
     if y0.dtype not in (torch.float32, torch.float64):
         raise TypeError('odeint: y0 must be float32 or float64')
     t = torch.as_tensor(t)
@@ -510,6 +511,14 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         # network-free HH candidate (train-d0.py:321-376): same call, dedicated kernel
         y = integrate_hh(hh_params_of(func), y0, t, _protocol_arrays(func), rtol=rtol, atol=atol,
                          method=method, options=options).y
+        if not y0.is_cuda:
+            y = y.to(y0.device)
+        return y[:, 0, :] if squeeze else y
+    from .markov import integrate_markov, is_markov_func, markov_params_of
+    if is_markov_func(func):
+        # 6-state Markov ground truth (train-d1.py:134-187): same call, dedicated kernel
+        y = integrate_markov(markov_params_of(func), y0, t, _protocol_arrays(func), rtol=rtol,
+                             atol=atol, method=method, options=options).y
         if not y0.is_cuda:
             y = y.to(y0.device)
         return y[:, 0, :] if squeeze else y

@@ -63,6 +63,9 @@ def test_argument_validation_without_gpu(lib):
     assert lib.ikr_forward(None, ctypes.byref(io), 1, None, 0, None) == -1
     assert lib.ikr_forward(ctypes.byref(d), ctypes.byref(io), 1, None, 0, None) == -1   # B = 0
     assert lib.ikr_forward(ctypes.byref(d), ctypes.byref(io), 0, None, 0, None) == -1   # no jobs
+    mio = _cabi.IkrMarkovIO()
+    assert lib.ikr_forward_markov(None, ctypes.byref(mio), None) == -1
+    assert lib.ikr_forward_markov(ctypes.byref(d), ctypes.byref(mio), None) == -1      # B = 0
     bad = _desc()
     bad.n_layers = 0
     assert lib.ikr_packed_weight_elems(ctypes.byref(bad)) == -1
