@@ -169,6 +169,17 @@ int ikr_backward(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, voi
  * io->weights and the checkpoint fields are ignored.  No workspace.                              */
 int ikr_forward_hh(const ikr_desc* d, const ikr_io* io, const double* hh_params, void* cuda_stream);
 
+/* MLP regression stage of the training scripts (train-s1.py:891-909, train-r1.py:917-925): one
+ * full-batch evaluation of  p = net(x) / netscale;  loss = sum (p - y)^2  and d loss / d theta.
+ * x [N,2] fp32 = (V / vrange, a), y [N] fp32 = target da/dt; *loss_out (device) receives the fp64
+ * loss, grad_weights [ikr_param_count] the fp64 gradient in state_dict order.  Tensor-core path
+ * only (fp32 MLP, n_nodes <= 200 with n_nodes % 16 in 1..8): otherwise IKR_ERR_UNSUPPORTED and the
+ * caller keeps its own autograd.  The optimiser step stays with the caller (torch.optim.Adam).   */
+size_t ikr_regression_workspace_bytes(const ikr_desc* d, int64_t N);
+int ikr_regression_loss_grad(const ikr_desc* d, const void* weights, const void* x, const void* y,
+                             int64_t N, double* loss_out, double* grad_weights, void* workspace,
+                             size_t workspace_bytes, void* cuda_stream);
+
 /* 6-state Markov ground-truth model of the synthetic-data studies (train-d1.py:134-187 `Lambda`:
  * states [c1, c2, i, ic1, ic2, o], rate parameters p1..p12) and its data production step
  * (train-d1.py:539-569): `odeint(true_model, true_y0, t)` then

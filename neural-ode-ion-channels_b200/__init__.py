@@ -16,6 +16,8 @@ from .solver import IkrResult, describe, integrate, integrate_many, odeint  # no
 from .adjoint import loss_and_grad  # noqa: F401
 from .hh import HHPopulationModel, integrate_hh  # noqa: F401
 from .markov import MARKOV_B06, MarkovGroundTruth, integrate_markov  # noqa: F401
+from .regression import fit_regression, mse_loss_and_grad, save_checkpoint  # noqa: F401
 
-__all__ = ['odeint', 'integrate', 'loss_and_grad', 'integrate_hh', 'HHPopulationModel', 'integrate_markov', 'MarkovGroundTruth', 'MARKOV_B06', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
+__all__ = ['odeint', 'integrate', 'loss_and_grad', 'integrate_hh', 'HHPopulationModel', 'integrate_markov', 'MarkovGroundTruth', 'MARKOV_B06', 'mse_loss_and_grad', 'fit_regression',
+           'save_checkpoint', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
            'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols', 'parallel']

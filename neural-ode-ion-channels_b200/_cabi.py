@@ -106,6 +106,11 @@ def lib():
                                ctypes.POINTER(IkrBwdIO), c_vp, ctypes.c_size_t, c_vp]
     L.ikr_forward_hh.restype = c_i32
     L.ikr_forward_hh.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(IkrIO), c_vp, c_vp]
+    L.ikr_regression_workspace_bytes.restype = ctypes.c_size_t
+    L.ikr_regression_workspace_bytes.argtypes = [ctypes.POINTER(IkrDesc), c_i64]
+    L.ikr_regression_loss_grad.restype = c_i32
+    L.ikr_regression_loss_grad.argtypes = [ctypes.POINTER(IkrDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp,
+                                           c_vp, ctypes.c_size_t, c_vp]
     L.ikr_forward_markov.restype = c_i32
     L.ikr_forward_markov.argtypes = [ctypes.POINTER(IkrDesc), ctypes.POINTER(IkrMarkovIO), c_vp]
     L.ikr_interp_protocol.restype = c_i32
@@ -120,7 +125,8 @@ def lib():
 
 EXPORTS = ('ikr_abi_version', 'ikr_error_string', 'ikr_packed_weight_elems', 'ikr_packed_layout',
            'ikr_param_count', 'ikr_uses_tensor_cores', 'ikr_tile_m', 'ikr_launch_geometry', 'ikr_workspace_bytes',
-           'ikr_forward', 'ikr_backward', 'ikr_forward_hh', 'ikr_forward_markov', 'ikr_interp_protocol',
+           'ikr_forward', 'ikr_backward', 'ikr_forward_hh', 'ikr_forward_markov', 'ikr_regression_workspace_bytes',
+           'ikr_regression_loss_grad', 'ikr_interp_protocol',
            'ikr_fma_peak')
 
 

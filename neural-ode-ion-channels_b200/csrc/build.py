@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, 'libikr_b200.so')
 SOURCES = ['ikr_capi.cu']
 HEADERS = ['ikr_math.h', 'ikr_device.cuh', 'ikr_forward.cuh', 'ikr_backward.cuh', 'ikr_hh.cuh',
-           'ikr_tc.cuh', 'ikr_forward_tc.cuh', 'ikr_backward_tc.cuh', 'ikr_markov.cuh',
+           'ikr_tc.cuh', 'ikr_forward_tc.cuh', 'ikr_backward_tc.cuh', 'ikr_markov.cuh', 'ikr_regress_tc.cuh',
            os.path.join('..', '..', 'include', 'ikr.h')]
 
 NVCC_FLAGS = [

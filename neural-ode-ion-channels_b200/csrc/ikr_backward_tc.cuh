@@ -655,7 +655,8 @@ struct TcWgradParams {
   TcGeom g;
   TcStashGeom sg;
   const unsigned char* stash;
-  const unsigned long long* counters;   // [1] = slots used this round
+  const unsigned long long* counters;   // [1] = slots used this round (when slots_fixed < 0)
+  long long slots_fixed;                // >= 0: number of slots, known to the host
   int S;                                // splits per pseudo-layer; grid = (L + 2) * S
   int stages;
   double* partial;                      // [(L + 2)][S][NP rows][NP cols] fp64, accumulated (+=)
@@ -702,7 +703,7 @@ __global__ void __launch_bounds__(kWgTcThreads, 1) ikr_wgrad_tc_kernel(const TcW
   tc::fence_after_sync();
   const uint32_t tbase = *tmem_slot;
 
-  const long long slots = (long long)p.counters[1];
+  const long long slots = p.slots_fixed >= 0 ? p.slots_fixed : (long long)p.counters[1];
   const long long my_slots = slots > split ? (slots - split + p.S - 1) / p.S : 0;
   const long long n_steps = my_slots * 8;      // K = 16 steps (8 per slot)
 

@@ -10,7 +10,7 @@
 
 #include "../../include/ikr.h"
 #include "ikr_backward.cuh"
-#include "ikr_backward_tc.cuh"
+#include "ikr_regress_tc.cuh"
 #include "ikr_hh.cuh"
 #include "ikr_markov.cuh"
 
@@ -568,6 +568,7 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
   wp.g = pl.g; wp.sg = pl.sg;
   wp.stash = tp.stash;
   wp.counters = p.counters;
+  wp.slots_fixed = -1;
   wp.S = pl.wg_S;
   wp.stages = pl.wg_stages;
   wp.partial = reinterpret_cast<double*>(ws + pl.off_partial);
@@ -685,6 +686,48 @@ int bwd_dispatch(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, voi
   const int threads = 256;
   const unsigned blocks = (unsigned)((rp.n_params + threads - 1) / threads);
   ikr_grad_reduce_kernel<<<blocks, threads, 0, st>>>(rp);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MLP regression stage (ikr_regress_tc.cuh): plan + launch
+// ---------------------------------------------------------------------------------------------
+struct TcRegPlan {
+  bool ok;
+  TcBwdPlan b;          // geometry / smem / wgrad configuration shared with the ODE backward
+  long long n_tiles;
+  size_t off_loss, off_partial, off_img, fixed_bytes, img_bytes;
+};
+
+TcRegPlan make_tc_reg_plan(const ikr_desc* d, long long N) {
+  TcRegPlan r;
+  r.ok = false;
+  ikr_desc dd = *d;
+  dd.method = IKR_DOPRI5;
+  dd.state_dtype = IKR_F32;
+  r.b = make_tc_bwd_plan(&dd, N);
+  if (!r.b.ok) return r;
+  r.n_tiles = (N + kTcM - 1) / kTcM;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
+  r.off_loss = take(256);
+  r.off_partial = take(r.b.partial_bytes);
+  r.img_bytes = (size_t)3 * d->n_layers * r.b.g.KST * r.b.g.stage_bytes;
+  r.off_img = take(r.img_bytes);
+  r.fixed_bytes = o;
+  r.ok = true;
+  return r;
+}
+
+template <int G>
+int launch_regress_g(const TcRegParams& tp, const TcBwdPlan& pl, int grid, cudaStream_t st) {
+  auto kern = ikr_regress_tc_kernel<G>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return IKR_ERR_LAUNCH;
+  }
+  kern<<<grid, tc_threads(G), pl.smem, st>>>(tp);
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
 }
 
@@ -930,6 +973,98 @@ int ikr_forward_hh(const ikr_desc* d, const ikr_io* io, const double* hh_params,
   if (d->state_dtype == IKR_F32) ikr_hh_kernel<float><<<blocks, threads, 0, st>>>(p);
   else ikr_hh_kernel<double><<<blocks, threads, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
+}
+
+size_t ikr_regression_workspace_bytes(const ikr_desc* d, int64_t N) {
+  if (!valid_desc(d) || N < 1) return 0;
+  const TcRegPlan r = make_tc_reg_plan(d, N);
+  if (!r.ok) return 0;
+  // stash: every tile of the batch when that stays below ~4 GiB, else rounds of tiles
+  long long tiles = r.n_tiles;
+  const long long cap = (long long)(4.0 * 1024 * 1024 * 1024 / (double)r.b.sg.slot);
+  if (tiles > cap) tiles = cap;
+  if (tiles < 1) tiles = 1;
+  return r.fixed_bytes + 512 + (size_t)tiles * (size_t)r.b.sg.slot;
+}
+
+int ikr_regression_loss_grad(const ikr_desc* d, const void* weights, const void* x, const void* y,
+                             int64_t N, double* loss_out, double* grad_weights, void* workspace,
+                             size_t workspace_bytes, void* cuda_stream) {
+  if (!valid_desc(d) || !weights || !x || !y || N < 1 || !loss_out || !grad_weights) return IKR_ERR_ARG;
+  const TcRegPlan r = make_tc_reg_plan(d, N);
+  if (!r.ok) return IKR_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes <= r.fixed_bytes + 512) return IKR_ERR_WORKSPACE;
+  const TcBwdPlan& pl = r.b;
+  unsigned char* ws = (unsigned char*)workspace;
+  const size_t off_stash = (r.fixed_bytes + 255) & ~(size_t)255;
+  const long long slots_cap = (long long)((workspace_bytes - off_stash) / (size_t)pl.sg.slot);
+  if (slots_cap < 1) return IKR_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (cudaMemsetAsync(ws + r.off_loss, 0, 256, st) != cudaSuccess) return IKR_ERR_DEVICE;
+  if (cudaMemsetAsync(ws + r.off_partial, 0, pl.partial_bytes, st) != cudaSuccess) return IKR_ERR_DEVICE;
+
+  const MlpView mv = make_view(d, weights);
+  TcPackParams pk;
+  pk.wn = reinterpret_cast<const float*>(weights) + mv.off_wn;
+  pk.wt = reinterpret_cast<const float*>(weights) + mv.off_wt;
+  pk.npad = mv.npad;
+  pk.n_seq = 3 * d->n_layers;
+  pk.g = pl.g;
+  pk.img = reinterpret_cast<uint16_t*>(ws + r.off_img);
+  ikr_tc_pack_kernel<<<pl.sms, 256, 0, st>>>(pk);
+  if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
+
+  TcRegParams tp;
+  tp.mlp = mv;
+  tp.g = pl.g;
+  tp.sg = pl.sg;
+  tp.img = ws + r.off_img;
+  tp.stash = ws + off_stash;
+  tp.x = reinterpret_cast<const float*>(x);
+  tp.y = reinterpret_cast<const float*>(y);
+  tp.N = N;
+  tp.netscale = (float)d->netscale;
+  tp.loss_out = reinterpret_cast<double*>(ws + r.off_loss);
+  tp.mask_words = pl.mask_words;
+
+  TcWgradParams wp;
+  wp.g = pl.g; wp.sg = pl.sg;
+  wp.stash = tp.stash;
+  wp.counters = nullptr;
+  wp.S = pl.wg_S;
+  wp.stages = pl.wg_stages;
+  wp.partial = reinterpret_cast<double*>(ws + r.off_partial);
+  if (cudaFuncSetAttribute(ikr_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)pl.wg_smem) != cudaSuccess) {
+    cudaGetLastError();
+    return IKR_ERR_LAUNCH;
+  }
+  for (long long t0 = 0; t0 < r.n_tiles; t0 += slots_cap) {
+    const long long t1 = t0 + slots_cap < r.n_tiles ? t0 + slots_cap : r.n_tiles;
+    tp.tile_begin = t0; tp.tile_end = t1;
+    const int grid = (int)((t1 - t0) < pl.sms ? (t1 - t0) : pl.sms);
+    int rc;
+    if (pl.groups == 1) rc = launch_regress_g<1>(tp, pl, grid, st);
+    else if (pl.groups == 2) rc = launch_regress_g<2>(tp, pl, grid, st);
+    else rc = launch_regress_g<3>(tp, pl, grid, st);
+    if (rc != 0) return rc;
+    wp.slots_fixed = t1 - t0;
+    ikr_wgrad_tc_kernel<<<(d->n_layers + 2) * pl.wg_S, kWgTcThreads, pl.wg_smem, st>>>(wp);
+    if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
+  }
+  TcReduceParams rp;
+  rp.L = d->n_layers; rp.n = d->n_nodes; rp.NP = pl.g.NP; rp.S = pl.wg_S;
+  rp.partial = wp.partial;
+  rp.out = grad_weights;
+  const long long n = d->n_nodes, Ln = d->n_layers;
+  rp.n_params = 3 * n + Ln * (n * n + n) + n + 1;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((rp.n_params + threads - 1) / threads);
+  ikr_grad_reduce_tc_kernel<<<blocks, threads, 0, st>>>(rp);
+  if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
+  if (cudaMemcpyAsync(loss_out, ws + r.off_loss, sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return IKR_ERR_DEVICE;
+  return 0;
 }
 
 int ikr_forward_markov(const ikr_desc* d, const ikr_markov_io* io, void* cuda_stream) {

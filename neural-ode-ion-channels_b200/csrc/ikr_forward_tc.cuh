@@ -93,7 +93,8 @@ struct TcPackParams {
   const float* wn;   // [L][n][npad] rows = output features (packed-parameter section off_wn)
   const float* wt;   // [L][n][npad] rows = input features  (section off_wt = W^T), backward images
   int npad;
-  int n_seq;         // L: forward images W_1..W_L; 2L: followed by the transposed W_L..W_1
+  int n_seq;         // L: forward images W_1..W_L; 2L: followed by the transposed W_L..W_1;
+                     // 3L (regression): forward images twice, then the transposed ones
   TcGeom g;
   uint16_t* img;
 };
@@ -122,8 +123,9 @@ __global__ void ikr_tc_pack_kernel(const TcPackParams p) {
     const int c = (int)(blk % 3);
     const int step = (int)((blk / 3) % g.KST);
     const int seq = (int)(blk / (3LL * g.KST));
-    const float* src = seq < g.L ? p.wn + (long long)seq * g.n * p.npad
-                                 : p.wt + (long long)(2 * g.L - 1 - seq) * g.n * p.npad;
+    const int n_fwd = p.n_seq == 3 * g.L ? 2 * g.L : g.L;
+    const float* src = seq < n_fwd ? p.wn + (long long)(seq % g.L) * g.n * p.npad
+                                   : p.wt + (long long)(p.n_seq - 1 - seq) * g.n * p.npad;
     int k, term;
     if (step < g.KSf) {
       k = 16 * step + kk;
