@@ -9,7 +9,7 @@ Public surface (mirrors what the reference scripts use on this path):
 * ``ARCHITECTURES`` / ``build_net``                    -- architectures/s00..s11
 * ``protocols``                                        -- voltage-clamp protocol tables
 """
-from . import parallel, protocols  # noqa: F401
+from . import parallel, protocols, reporting  # noqa: F401
 from .models import (ARCHITECTURES, PARAMETER_SETS, ODEFunc, ODEFuncNNd, ODEFuncNNf,  # noqa: F401
                      build_net, load_weights)
 from .solver import IkrResult, describe, integrate, integrate_many, odeint  # noqa: F401
@@ -20,4 +20,4 @@ from .regression import fit_regression, mse_loss_and_grad, save_checkpoint  # no
 
 __all__ = ['odeint', 'integrate', 'loss_and_grad', 'integrate_hh', 'HHPopulationModel', 'integrate_markov', 'MarkovGroundTruth', 'MARKOV_B06', 'mse_loss_and_grad', 'fit_regression',
            'save_checkpoint', 'integrate_many', 'describe', 'IkrResult', 'ODEFunc', 'ODEFuncNNf', 'ODEFuncNNd',
-           'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols', 'parallel']
+           'ARCHITECTURES', 'PARAMETER_SETS', 'build_net', 'load_weights', 'protocols', 'parallel', 'reporting']

@@ -161,6 +161,32 @@ def make_hh_fit_vectors():
     print('hh_fit_vectors.npz: %d probes x %d parameter vectors' % (n, len(X)))
 
 
+def make_table1_cache_fixture():
+    """Formats and losses of the reference's own cached predictions (`table-1/*.pt`, written by
+    table-1.py:468-523) and its LaTeX table -> ``table1_cache.json`` (the tensors themselves stay in
+    the reference checkout: only shapes, dtypes and the derived losses are committed)."""
+    from neural_ode_ion_channels_b200 import reporting as rp
+    out = {'source': 'derived from /root/reference/table-1/*.pt and table-1.txt by '
+                     'tests/golden/make_golden.py'}
+    losses = {}
+    for proto in ('pr4', 'sinewave', 'aps'):
+        c = {}
+        p = os.path.join(REF, 'table-1', 'yc-%s.pt' % proto)
+        if os.path.exists(p):
+            c['c'] = torch.from_numpy(torch.load(p, weights_only=False))
+        for k in ('o', '1', '2'):
+            c[k] = torch.load(os.path.join(REF, 'table-1', 'y%s-%s.pt' % (k, proto)), weights_only=False)
+        out.setdefault('shapes', {})[proto] = {k: [list(c[k].shape), str(c[k].dtype)] for k in c}
+        if 'c' in c:
+            losses[proto] = {k: rp.mean_abs_loss(c[k], c['c']) for k in ('o', '1', '2')}
+    out['losses'] = losses
+    with open(os.path.join(REF, 'table-1', 'table-1.txt')) as fh:
+        out['table_txt'] = fh.read()
+    with open(os.path.join(HERE, 'table1_cache.json'), 'w') as fh:
+        json.dump(out, fh, indent=1)
+    print('table1_cache.json: %d protocols with data traces' % len(losses))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--traces', action='store_true')
@@ -169,6 +195,7 @@ def main():
     make_kat()
     make_rhs_vectors()
     make_hh_fit_vectors()
+    make_table1_cache_fixture()
     if args.traces:
         from tests.golden import make_traces
         make_traces.main()
