@@ -377,7 +377,8 @@ def run_b200(args):
     _cabi.check(_cabi.lib().ikr_fma_peak(_cabi.F32, 200000, ctypes.byref(peak), None), 'fma_peak')
     fma_peak_tflops = peak.value
 
-    opts = {'check_status': False, 'lane_pool': bool(os.environ.get('IKR_LANE_POOL')),
+    lane_pool = {'1': True, '0': False}.get(os.environ.get('IKR_LANE_POOL', ''), None)
+    opts = {'check_status': False, 'lane_pool': lane_pool,
             'tensor_cores': not os.environ.get('IKR_NO_TC')}
 
     def step_device():

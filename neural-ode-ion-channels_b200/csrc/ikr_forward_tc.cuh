@@ -144,14 +144,15 @@ __global__ void ikr_tc_pack_kernel(const TcPackParams p) {
 // ---- shared memory carve-up --------------------------------------------------------------------------
 template <typename S>
 struct TcSmemLayout {
-  size_t off_bar, off_misc, off_job, off_lanes, off_obs, off_xin, off_part, off_sp, off_ring, total;
+  size_t off_bar, off_misc, off_job, off_lanes, off_obs, off_aux, off_xin, off_part, off_sp, off_ring, total;
   __host__ __device__ TcSmemLayout(const TcGeom& g, int stages, int G) {
     size_t o = 0;
     off_bar = o; o += (size_t)(2 * kTcMaxStages + 2) * 8;          // full[], empty[], a_ready, d_ready
     off_misc = o; o += 32;                                          // tmem base, stop flag, tile slot
-    off_job = o; o += (sizeof(FwdJob) + 15) & ~(size_t)15;
+    off_job = o; o += (size_t)kInlineJobs * ((sizeof(FwdJob) + 15) & ~(size_t)15);   // pool: job table
     off_lanes = o; o += (size_t)kTcM * sizeof(Lane<S>); o = (o + 15) & ~(size_t)15;
     off_obs = o; o += (size_t)kTcM * 2 * sizeof(double);
+    off_aux = o; o += (size_t)kTcM * 32;                               // LaneAux (lane-pool kernel)
     off_xin = o; o += (size_t)kTcM * 2 * sizeof(float);
     off_part = o; o += (size_t)G * kTcM * sizeof(float);
     off_sp = o; o += (size_t)g.small_elems * sizeof(float); o = (o + 127) & ~(size_t)127;
@@ -745,6 +746,259 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
       if (G > 1) lanes_sync<G>();
     }
     // one more a_ready phase wakes the MMA thread, which sees the stop flag
+    __syncwarp();
+    if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) tc::tmem_dealloc(tbase, tc::kTmemCols);
+}
+
+// =============================================================================================
+// Lane-pool variant (dopri5): every CTA owns 128 lane SLOTS; a slot whose trajectory has finished
+// pulls the next trajectory -- of whatever job -- from one global queue (jobs longest first), so no
+// TMEM lane idles while its neighbours finish and there is no tile / wave quantisation.  Lanes stay
+// in lock-step by ROUND of six RHS evaluations: a lane attempts one dopri5 step, or, right after a
+// refill, runs its two start-up evaluations.  Every lane's arithmetic is independent of its slot,
+// so results are bit-identical to the tile-scheduled kernel.
+// =============================================================================================
+template <typename S, int G>
+__global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(const TcFwdParams tp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const FwdParams& p = tp.f;
+  const TcGeom g = tp.g;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  constexpr int kLaneThreads = 128 * G;
+  constexpr int kMmaWarp = 4 * G, kLoadWarp = 4 * G + 1;
+  const TcSmemLayout<S> lay(g, g.stages, G);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + lay.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + lay.off_misc);
+  volatile int* stop_flag = reinterpret_cast<volatile int*>(smem_raw + lay.off_misc + 4);
+  volatile int* cmd_exit = reinterpret_cast<volatile int*>(smem_raw + lay.off_misc + 16);
+  Lane<S>* lanes = reinterpret_cast<Lane<S>*>(smem_raw + lay.off_lanes);
+  double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);
+  LaneAux<S>* aux = reinterpret_cast<LaneAux<S>*>(smem_raw + lay.off_aux);
+  float* sp = reinterpret_cast<float*>(smem_raw + lay.off_sp);
+  TcEngineCtx eng;
+  eng.bar_full = bars; eng.bar_empty = bars + kTcMaxStages;
+  eng.bar_a = bars + 2 * kTcMaxStages; eng.bar_d = eng.bar_a + 1;
+  eng.stop_flag = stop_flag; eng.ring = smem_raw + lay.off_ring;
+
+  if (tid == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&eng.bar_full[s], 1);
+      mbar_init(&eng.bar_empty[s], 1);
+    }
+    mbar_init(eng.bar_a, kLaneThreads / 32);
+    mbar_init(eng.bar_d, 1);
+    mbar_fence_init();
+    *stop_flag = 0;
+    *cmd_exit = 0;
+  }
+  if (warp == kMmaWarp) tc::tmem_alloc(smem_u32(tmem_slot), tc::kTmemCols);
+  {
+    const float* P = reinterpret_cast<const float*>(p.mlp.base);
+    const int NP = g.NP, npad = p.mlp.npad, n = g.n;
+    for (int i = tid; i < g.small_elems; i += tc_threads(G)) {
+      const int row = i / NP, c = i - row * NP;
+      float v = 0.0f;
+      if (row < 3) { if (c < n) v = P[p.mlp.off_w0 + (long long)row * npad + c]; }
+      else if (row < 3 + g.L) { if (c < n) v = P[p.mlp.off_bh + (long long)(row - 3) * npad + c]; }
+      else if (row == 3 + g.L) { if (c < n) v = P[p.mlp.off_wl + c]; }
+      else if (i == (4 + g.L) * NP) v = P[p.mlp.off_wl + npad];
+      sp[i] = v;
+    }
+  }
+  // job descriptors: shared-memory copy of the inline table (every lane reads its job every round)
+  constexpr size_t kJobStride = (sizeof(FwdJob) + 15) & ~(size_t)15;
+  unsigned char* sjobs = smem_raw + lay.off_job;
+  if (p.jobs_are_inline) {
+    const int words = (int)(sizeof(FwdJob) / 4);
+    for (int i = tid; i < p.n_jobs * words; i += tc_threads(G)) {
+      const int j = i / words, w = i - j * words;
+      reinterpret_cast<uint32_t*>(sjobs + (size_t)j * kJobStride)[w] =
+          reinterpret_cast<const uint32_t*>(&p.jobs_inline[j])[w];
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == kMmaWarp) {
+    tc_mma_warp(g, eng, tbase, tp.timing && blockIdx.x == 0);
+  } else if (warp == kLoadWarp) {
+    if ((tid & 31) == 0) tc_producer_thread(g, eng, reinterpret_cast<const unsigned char*>(tp.img),
+                                            (unsigned)(g.L * g.KST));
+  } else {
+    TcLane tl;
+    tl.group = warp >> 2;
+    tl.lane = tid & 127;
+    tl.taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    tl.bar_a = smem_u32(eng.bar_a);
+    tl.bar_d = eng.bar_d;
+    tl.phase_d = 0;
+    tl.sp = sp;
+    tl.xin = reinterpret_cast<float*>(smem_raw + lay.off_xin);
+    tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
+    tl.slope = (float)p.mlp.slope;
+    tl.c_l0 = tl.c_wait = tl.c_epi = 0;
+#ifdef IKR_TC_TRACE
+    tl.trace_eval = 0;
+#endif
+
+    if (tl.group > 0) {
+      while (true) {
+        lanes_sync<G>();
+        if (*cmd_exit) break;
+        tc_mlp_eval<G>(g, tl);
+        lanes_sync<G>();
+      }
+    } else {
+      const bool heuristic = !(p.cfg.first_step > 0);
+      Lane<S>& L = lanes[tid];
+      LaneAux<S>& A = aux[tid];
+      SolverCfg c = p.cfg;                      // per-thread copy; c.tab follows the lane's job
+      auto job_of = [&](int j) -> const FwdJob* {
+        return p.jobs_are_inline ? reinterpret_cast<const FwdJob*>(sjobs + (size_t)j * kJobStride) : p.jobs + j;
+      };
+      const FwdJob* jobp = job_of(0);
+      lane_reset<S>(L, (S)0, (S)1, 0.0, false);
+      A.mode = POOL_EMPTY; A.job = 0; A.b = 0; A.g = (S)1; A.e = (S)0;
+      bool queue_dry = false;
+
+      while (true) {
+        // ---- round boundary: retire finished trajectories, refill free slots ----------------------
+        if (A.mode == POOL_STEP) dp_check_before_step<S>(L, c);
+        if (A.mode != POOL_EMPTY && !lane_active(L)) {
+          const FwdJob& job = *jobp;
+          int* st = job.stats_out + 4 * A.b;
+          st[0] = L.n_acc; st[1] = L.n_rej; st[2] = L.nfe;
+          st[3] = L.status == LANE_DONE ? 0 : L.status;
+          if (job.loss_out) {
+            job.loss_out[2 * A.b] = obs[2 * tid];
+            job.loss_out[2 * A.b + 1] = obs[2 * tid + 1];
+          }
+          A.mode = POOL_EMPTY;
+        }
+        if (A.mode == POOL_EMPTY && !queue_dry) {
+          const long long gidx = (long long)atomicAdd(p.queue, 1ULL);
+          if (gidx < p.n_traj) {
+            int j = 0;
+            while (j + 1 < p.n_jobs && job_of(j + 1)->traj_begin <= gidx) ++j;
+            jobp = job_of(j);
+            const FwdJob& job = *jobp;
+            c.tab = job.tab;
+            const long long b = gidx - job.traj_begin;
+            const S* y0 = reinterpret_cast<const S*>(job.y0);
+            A.job = j; A.b = b; A.mode = POOL_INIT;
+            A.g = job.g ? reinterpret_cast<const S*>(job.g)[b] : (S)1;
+            A.e = job.e_rev ? reinterpret_cast<const S*>(job.e_rev)[b] : (S)job.e_scalar;
+            lane_reset<S>(L, y0[2 * b], y0[2 * b + 1], job.t_out[0], true);
+            obs[2 * tid] = 0.0; obs[2 * tid + 1] = 0.0;
+          } else {
+            queue_dry = true;
+          }
+        }
+        if (!owners_or(A.mode != POOL_EMPTY ? 1 : 0)) break;
+
+        // ---- one round = six RHS evaluations ---------------------------------------------------------
+#pragma unroll 1
+        for (int s = 0; s < 6; ++s) {
+          int what = 0;   // 0 masked, 1 dopri5 stage, 2 f0, 3 initial-step probe
+          double nv = 0, ain = 0;
+          if (A.mode == POOL_STEP) what = 1;
+          else if (A.mode == POOL_INIT && s == 0) what = 2;
+          else if (A.mode == POOL_INIT && s == 1 && heuristic) what = 3;
+          if (what) {
+            if (what == 1) dp_prepare_stage<S>(L, c, s, &nv, &ain);
+            else if (what == 2) init_prepare_f0<S>(L, c, &nv, &ain);
+            else init_prepare_f1<S>(L, c, &nv, &ain);
+          }
+          const float out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+          if (what == 1) dp_store_stage<S>(L, c, s, (double)out);
+          else if (what == 2) {
+            init_store_f0<S>(L, c, (double)out);
+            if (!heuristic) L.dt = c.first_step;
+          } else if (what == 3) init_store_f1<S>(L, c, (double)out);
+        }
+
+        // ---- end of round: finish the attempted step / leave start-up ----------------------------------
+        if (A.mode == POOL_STEP) {
+          const FwdJob& job = *jobp;
+          const long long jB = job.B, b = A.b;
+          S* y_out = reinterpret_cast<S*>(job.y_out);
+          S* i_out = reinterpret_cast<S*>(job.i_out);
+          S* ckpt_y = reinterpret_cast<S*>(job.ckpt_y);
+          const S* dptr = reinterpret_cast<const S*>(job.data);
+          const bool observe = (job.v_out != nullptr) && (job.i_out != nullptr || job.loss_out != nullptr);
+          const S g_b = A.g, e_b = A.e;
+          auto emit = [&](int idx, S a, S r) {
+            if (y_out) {
+              typename Vec2<S>::type v;
+              v.x = a; v.y = r;
+              *reinterpret_cast<typename Vec2<S>::type*>(y_out + ((size_t)idx * jB + b) * 2) = v;
+            }
+            if (observe) {
+              double cur = (double)(g_b * a * r) * (job.v_out[idx] - (double)e_b);
+              if (i_out) i_out[(size_t)idx * jB + b] = (S)cur;
+              if (dptr) {
+                double d = (double)dptr[(size_t)idx * job.data_B + (job.data_B == 1 ? 0 : b)];
+                double diff = cur - d;
+                obs[2 * tid] += diff * diff;
+                obs[2 * tid + 1] += fabs(diff);
+              }
+            }
+          };
+          auto ckpt = [&](int step, const Lane<S>& lane) -> bool {
+            if (!job.ckpt_t) return true;
+            if (step >= job.ckpt_cap) return false;
+            size_t o = (size_t)step * jB + b;
+            double2 tt;
+            tt.x = lane.t0; tt.y = lane.dt;
+            *reinterpret_cast<double2*>(job.ckpt_t + 2 * o) = tt;
+            S buf[kCkptVals];
+            ckpt_pack<S>(lane, buf);
+            typedef typename Vec2<S>::type V2;
+            V2* dst = reinterpret_cast<V2*>(ckpt_y + (size_t)kCkptVals * o);
+#pragma unroll
+            for (int i = 0; i < kCkptVals / 2; ++i) {
+              V2 v;
+              v.x = buf[2 * i]; v.y = buf[2 * i + 1];
+              dst[i] = v;
+            }
+            return true;
+          };
+          dp_finish_step<S>(L, c, job.t_out, job.T, emit, ckpt);
+        } else if (A.mode == POOL_INIT) {
+          // start-up done: emit y(t[0]) = y0 and start stepping (or finish if there is one output)
+          const FwdJob& job = *jobp;
+          const long long b = A.b;
+          if (job.y_out) {
+            typename Vec2<S>::type v;
+            v.x = L.ya; v.y = L.yr;
+            reinterpret_cast<typename Vec2<S>::type*>(job.y_out)[b] = v;
+          }
+          if (job.v_out && (job.i_out || job.loss_out)) {
+            double cur = (double)(A.g * L.ya * L.yr) * (job.v_out[0] - (double)A.e);
+            if (job.i_out) reinterpret_cast<S*>(job.i_out)[b] = (S)cur;
+            if (job.data) {
+              const S* dptr = reinterpret_cast<const S*>(job.data);
+              double diff = cur - (double)dptr[job.data_B == 1 ? 0 : b];
+              obs[2 * tid] += diff * diff;
+              obs[2 * tid + 1] += fabs(diff);
+            }
+          }
+          A.mode = POOL_STEP;
+          if (job.T <= 1 && lane_active(L)) L.status = LANE_DONE;
+        }
+      }
+      if (tid == 0) { *cmd_exit = 1; *stop_flag = 1; }
+      owners_sync();
+      if (G > 1) lanes_sync<G>();
+    }
     __syncwarp();
     if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
   }

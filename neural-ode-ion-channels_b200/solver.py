@@ -150,8 +150,11 @@ def _make_desc(spec: ModelSpec, state_dtype, method, rtol, atol, opts, time_f32=
     d.dfactor = float(opts.get('dfactor', 0.2))
     d.max_num_steps = int(opts.get('max_num_steps', 2 ** 31 - 1))
     d.tile_m = int(opts.get('tile_m', 0))
-    # bit 0: lane-pool kernel; bit 1: keep the fp32 MLP on the FFMA2 kernel (no tcgen05 path)
-    d.reserved = (1 if opts.get('lane_pool', False) else 0) | (0 if opts.get('tensor_cores', True) else 2)
+    # bit 0: force the lane-pool kernel; bit 2: forbid it (lane_pool=None: library decides);
+    # bit 1: keep the fp32 MLP on the FFMA2 kernel (no tcgen05 path)
+    lp = opts.get('lane_pool', None)
+    d.reserved = ((1 if lp else 0) | (4 if lp is False else 0) |
+                  (0 if opts.get('tensor_cores', True) else 2))
     return d
 
 

@@ -28,7 +28,7 @@ with torch.no_grad():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         r = ikr.integrate(f, y0, t, want_y=False, want_current=False, data=torch.zeros(len(t)),
-                          options={'lane_pool': bool(os.environ.get('POOL')),
+                          options={'lane_pool': {'1': True, '0': False}.get(os.environ.get('POOL', ''), None),
                                    'tensor_cores': not os.environ.get('NO_TC')})
         e1.record()
         torch.cuda.synchronize()

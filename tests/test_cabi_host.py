@@ -88,7 +88,9 @@ def test_packed_layout_and_param_count(lib):
         assert geo['smem'] <= 227 * 1024 and geo['threads'] <= 512 and geo['tile_m'] % 8 == 0
         assert geo['n_tiles'] * geo['tile_m'] >= 65536
         multi = _cabi.launch_geometry(d, [13107] * 4 + [13108])
-        assert multi['n_tiles'] >= sum(-(-b // multi['tile_m']) for b in [13107] * 4 + [13108])
+        # tile-scheduled: whole tiles per job; lane-pool (large tensor-core launches): one pool
+        assert multi['n_tiles'] * multi['tile_m'] >= 65536
+        assert multi['n_tiles'] <= sum(-(-b // multi['tile_m']) for b in [13107] * 4 + [13108])
     # the default network (fp32 MLP, n = 200) runs on the tcgen05 kernel: 128-trajectory tiles (one
     # per TMEM lane), 3 x 128 lane threads + MMA warp + weight-producer warp
     d = _desc()

@@ -172,3 +172,31 @@ def test_tc_backward_round_and_shard_invariance():
         tb, pb, gb, _ = ikr.loss_and_grad(func, y0[h:], t, data[:, h:], options=opts)
         assert torch.equal(torch.cat([pa, pb]), per)
         assert np.abs(_flat(ga) + _flat(gb) - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+def test_tc_lane_pool_kernel_equals_tile_scheduled_kernel():
+    """The tensor-core lane-pool kernel (slots refill from one trajectory queue, jobs mixed inside a
+    CTA) reproduces the tile-scheduled tensor-core kernel bit for bit, checkpoints included."""
+    func, _ = _pair('d1')
+    rng = np.random.RandomState(11)
+    jobs = []
+    for k, (tt, vv, T) in enumerate([(*protocols.ap2hz(), 101), (*protocols.pr3_activation(20), 81),
+                                     (*protocols.pr5_deactivation(-60), 41)]):
+        B = (37, 300, 5)[k]
+        y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1),
+                          dtype=torch.float32).cuda()
+        t = torch.linspace(0., 2. * (T - 1), T)
+        g = torch.tensor(rng.lognormal(0, 0.2, B), dtype=torch.float32)
+        jobs.append(dict(protocol=(tt, vv), y0=y0, t=t, g=g, data=torch.zeros(T),
+                         want_current=True, want_ckpt=True))
+    a = ikr.integrate_many(func, jobs)
+    b = ikr.integrate_many(func, jobs, options={'lane_pool': True})
+    assert a[0].geometry['tensor_cores'] and b[0].geometry['tensor_cores']
+    for ra, rb in zip(a, b):
+        assert torch.equal(ra.stats, rb.stats)
+        assert torch.equal(ra.y, rb.y) and torch.equal(ra.current, rb.current)
+        assert torch.equal(ra.sse, rb.sse) and torch.equal(ra.sae, rb.sae)
+        for bb in range(ra.stats.shape[0]):
+            k = int(ra.stats[bb, 0])
+            assert torch.equal(ra.ckpt[1][:k, bb], rb.ckpt[1][:k, bb])
+            assert torch.equal(ra.ckpt[0][:k, bb], rb.ckpt[0][:k, bb])
