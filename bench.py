@@ -454,7 +454,8 @@ def run_b200(args):
     h2d = sum(j['y0'].numel() * 4 + j['g'].numel() * 4 for j in jobs_host) + \
         sum(t.numel() * 8 for t in tgrids)
     d2h = sum(nb * 8 + nb * 16 for nb in sizes)
-    n_launch_fwd = (len(jobs_dev) + 1) * args.steps   # forward kernel + one V(t_out) kernel per job
+    # per step: weight-image pack kernel + forward kernel + one V(t_out) kernel per job
+    n_launch_fwd = (len(jobs_dev) + (2 if geo.get('tensor_cores') else 1)) * args.steps
     train = None
     if args.train_batch > 0:
         del jobs_dev, jobs_host, outs
@@ -482,7 +483,10 @@ def run_b200(args):
                 'cache': 'working set (weights 0.8 MB, tables, per-lane state) is L2/SMEM '
                          'resident by design; y0/g/stat buffers are rewritten every step',
                 'tile_m': geo['tile_m'], 'threads_per_cta': geo['threads'], 'grid': geo['grid'],
-                'n_tiles': geo['n_tiles'],
+                'n_tiles': geo['n_tiles'], 'tensor_cores': bool(geo.get('tensor_cores')),
+                'scheduling': 'lane pool (slots refill from one trajectory queue)'
+                if geo['n_tiles'] * geo['tile_m'] < sum(-(-nb // geo['tile_m']) for nb in sizes) * geo['tile_m']
+                else 'tile queue (longest job first)',
                 'step_attempts_per_trajectory': dict(zip([w[0] for w in wl], steps_per_lane)),
             },
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': h2d,

@@ -318,8 +318,13 @@ __device__ __forceinline__ void tc_layer0_sums(const TcLane& tl, int NP, int c0,
 // lanes included: the a_ready barrier counts 128 G arrivals).  The caller has published (nv, a) in
 // tl.xin and passed the lanes barrier; the partial output sums land in tl.part (caller syncs).
 // Group c works on the contiguous unit range [c upg, (c + 1) upg); the last group adds the tail.
-template <int G>
-__device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl) {
+struct TcNoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// `hook` runs right after this thread's layer-0 part is published, i.e. while the MMAs of layer 1
+// execute: the owners use it to compute time-only RHS terms of the next stage ahead.
+template <int G, typename Hook = TcNoHook>
+__device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook hook = Hook()) {
   const int NP = g.NP;
   const float2 in = *reinterpret_cast<const float2*>(tl.xin + 2 * tl.lane);
   const float nv = in.x, a = in.y;
@@ -352,6 +357,7 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl) {
     tc_publish_a(tl);
   }
   { const long long c1 = clock64(); tl.c_l0 += c1 - c0; c0 = c1; }
+  hook();
   // ---- hidden layers: read D, bias + LeakyReLU, write the next A (or reduce the output) -----------
   for (int layer = 0; layer < g.L; ++layer) {
     const float* bias = tl.sp + (size_t)(3 + layer) * NP;
@@ -410,11 +416,12 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl) {
 }
 
 // Owner-side wrapper: publish the inputs, run the evaluation with the helper groups, collect.
-template <int G>
-__device__ __forceinline__ float tc_owner_eval(const TcGeom& g, TcLane& tl, float nv, float a) {
+template <int G, typename Hook = TcNoHook>
+__device__ __forceinline__ float tc_owner_eval(const TcGeom& g, TcLane& tl, float nv, float a,
+                                               Hook hook = Hook()) {
   *reinterpret_cast<float2*>(tl.xin + 2 * tl.lane) = make_float2(nv, a);
   if (G > 1) lanes_sync<G>();        // inputs visible to the helper groups (cmd word = run)
-  tc_mlp_eval<G>(g, tl);
+  tc_mlp_eval<G, Hook>(g, tl, hook);
   if (G > 1) lanes_sync<G>();        // partial sums visible
   float out = tl.part[tl.lane];
 #pragma unroll
@@ -697,13 +704,18 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
           }
           if (T <= 1 && lane_active(L)) L.status = LANE_DONE;
 
+          TimeCache tcache;
+          tcache.valid = 0;
           while (true) {
             dp_check_before_step<S>(L, cfg);
             if (!owners_or(lane_active(L) ? 1 : 0)) break;
 #pragma unroll 1
             for (int s = 0; s < 6; ++s) {
-              dp_prepare_stage<S>(L, cfg, s, &nv, &ain);
-              out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+              dp_prepare_stage_cached<S>(L, cfg, s, &nv, &ain, tcache);
+              // while the MMAs of this stage run: V(t) and the HH rates of the next stage
+              out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain, [&]() {
+                if (s < 5 && lane_active(L)) dp_prefetch_stage_time<S>(L, cfg, s + 1, tcache);
+              });
               dp_store_stage<S>(L, cfg, s, (double)out);
             }
             dp_finish_step<S>(L, cfg, job.t_out, T, emit, ckpt);
@@ -865,6 +877,8 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
         return p.jobs_are_inline ? reinterpret_cast<const FwdJob*>(sjobs + (size_t)j * kJobStride) : p.jobs + j;
       };
       const FwdJob* jobp = job_of(0);
+      TimeCache tcache;
+      tcache.valid = 0;
       lane_reset<S>(L, (S)0, (S)1, 0.0, false);
       A.mode = POOL_EMPTY; A.job = 0; A.b = 0; A.g = (S)1; A.e = (S)0;
       bool queue_dry = false;
@@ -913,11 +927,13 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
           else if (A.mode == POOL_INIT && s == 0) what = 2;
           else if (A.mode == POOL_INIT && s == 1 && heuristic) what = 3;
           if (what) {
-            if (what == 1) dp_prepare_stage<S>(L, c, s, &nv, &ain);
+            if (what == 1) dp_prepare_stage_cached<S>(L, c, s, &nv, &ain, tcache);
             else if (what == 2) init_prepare_f0<S>(L, c, &nv, &ain);
             else init_prepare_f1<S>(L, c, &nv, &ain);
           }
-          const float out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+          const float out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain, [&]() {
+            if (what == 1 && s < 5) dp_prefetch_stage_time<S>(L, c, s + 1, tcache);
+          });
           if (what == 1) dp_store_stage<S>(L, c, s, (double)out);
           else if (what == 2) {
             init_store_f0<S>(L, c, (double)out);

@@ -460,7 +460,64 @@ IKR_HD void rhs_finish(const Lane<S>& L, const SolverCfg& c, double net_out, dou
   *fr = L.hh_r;
 }
 
+// ---- time-only part of the RHS, computed ahead --------------------------------------------------
+// V(t) and the HH rate constants depend on the stage TIME only, and the times of stages 1..5 of a
+// dopri5 step are known when the step starts.  The tensor-core kernels fill this cache for stage
+// s + 1 while the MMAs of stage s run (the owner thread is idle then), which takes the table
+// search (dependent global loads) and the fp64 `exp`s off the serial part of an evaluation.
+// Same expressions as hh_drdt / hh_rate_pair (in-table branch) => bit-identical results; anything
+// else (time mismatch, out-of-table fallback) takes the uncached path.
+struct TimeCache {
+  double t, v, k1, k2, k3, k4;
+  int valid, in_table;
+};
+IKR_HD void time_cache_fill(TimeCache& tcx, const SolverCfg& c, double t_eval) {
+  tcx.t = t_eval;
+  tcx.in_table = table_voltage(c.tab, t_eval, &tcx.v) ? 1 : 0;
+  if (tcx.in_table) {
+    tcx.k3 = c.hp.p[4] * exp(c.hp.p[5] * tcx.v);
+    tcx.k4 = c.hp.p[6] * exp(-c.hp.p[7] * tcx.v);
+    if (c.nn_d) {
+      tcx.k1 = c.hp.p[0] * exp(c.hp.p[1] * tcx.v);
+      tcx.k2 = c.hp.p[2] * exp(-c.hp.p[3] * tcx.v);
+    }
+  }
+  tcx.valid = 1;
+}
+template <typename SS, typename S>
+IKR_HD void rhs_prepare_cached(Lane<S>& L, const SolverCfg& c, double t_eval, SS a, SS r, double* nv,
+                               double* a_in, const TimeCache& tcx) {
+  if (!(tcx.valid && tcx.in_table && tcx.t == t_eval)) {
+    rhs_prepare<SS, S>(L, c, t_eval, a, r, nv, a_in);
+    return;
+  }
+  const SS one_minus_r = (SS)1 - r;
+  L.hh_r = -tcx.k3 * (double)r + tcx.k4 * (double)one_minus_r;
+  if (c.nn_d) {
+    const SS one_minus_a = (SS)1 - a;
+    L.hh_a = tcx.k1 * (double)one_minus_a - tcx.k2 * (double)a;
+  } else {
+    L.hh_a = 0.0;
+  }
+  *nv = mlp_input_nv(tcx.v, true, c.vrange, c.mlp_is_f64 != 0);
+  *a_in = (double)a;
+}
+
 // ---- dopri5 --------------------------------------------------------------------------------
+template <typename S>
+IKR_HD void dp_prepare_stage_cached(Lane<S>& L, const SolverCfg& c, int stage, double* nv, double* a_in,
+                                    const TimeCache& tcx) {
+  S ti = dp_stage_time<S>(stage, L.t0, L.dt);
+  L.sa = dp_stage_state<S>(stage, L.ya, L.ka, L.dt);
+  L.sr = dp_stage_state<S>(stage, L.yr, L.kr, L.dt);
+  rhs_prepare_cached<S, S>(L, c, (double)ti, L.sa, L.sr, nv, a_in, tcx);
+}
+// fill the cache for stage `stage` of the step the lane is attempting
+template <typename S>
+IKR_HD void dp_prefetch_stage_time(const Lane<S>& L, const SolverCfg& c, int stage, TimeCache& tcx) {
+  time_cache_fill(tcx, c, (double)dp_stage_time<S>(stage, L.t0, L.dt));
+}
+
 template <typename S>
 IKR_HD void dp_prepare_stage(Lane<S>& L, const SolverCfg& c, int stage, double* nv, double* a_in) {
   S ti = dp_stage_time<S>(stage, L.t0, L.dt);
