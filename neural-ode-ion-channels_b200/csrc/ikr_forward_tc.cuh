@@ -239,9 +239,20 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
 #pragma unroll
     for (int q = 0; q < 8 * NK; ++q) tc::split3p(h[q], w12[q], w12[8 * NK + q], w3[q]);
     const uint32_t dst = tl.taddr + g.col_a + 48 * u;
+#ifdef IKR_TC_TRACE
+    const long long ts0 = clock64();
+#endif
     if (NK == 2) {
       tc::st32(dst, reinterpret_cast<uint32_t(&)[32]>(w12));
+#ifdef IKR_TC_TRACE
+      const long long ts1 = clock64();
+#endif
       tc::st16(dst + 32, reinterpret_cast<uint32_t(&)[16]>(w3));
+#ifdef IKR_TC_TRACE
+      const long long ts2 = clock64();
+      if (tl.trace_eval == 300 && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && u == 0 && bias == tl.sp + 4 * g.NP)
+        printf("[trace-st] warp %d: st32 issue %lld, st16 issue %lld cycles\n", (int)(threadIdx.x >> 5), ts1 - ts0, ts2 - ts1);
+#endif
     } else {
       tc::st16(dst, reinterpret_cast<uint32_t(&)[16]>(w12));
       tc::st8(dst + 16, reinterpret_cast<uint32_t(&)[8]>(w3));
