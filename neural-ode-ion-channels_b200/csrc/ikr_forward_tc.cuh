@@ -237,7 +237,7 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
   if (!last) {
     uint32_t w12[16 * NK], w3[8 * NK];
 #pragma unroll
-    for (int q = 0; q < 8 * NK; ++q) tc::split3p(h[q], w12[q], w12[8 * NK + q], w3[q]);
+    for (int q = 0; q < 8 * NK; ++q) tc::split3t(h[q], w12[q], w12[8 * NK + q], w3[q]);
     const uint32_t dst = tl.taddr + g.col_a + 48 * u;
 #ifdef IKR_TC_TRACE
     const long long ts0 = clock64();
@@ -289,7 +289,7 @@ __device__ __forceinline__ void tc_tail_finish(const TcGeom& g, const TcLane& tl
     uint32_t t[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      tc::split3p(h[q], t[q], t[4 + q], t[12 + q]);
+      tc::split3t(h[q], t[q], t[4 + q], t[12 + q]);
       t[8 + q] = t[q];
     }
     tc::st16(tl.taddr + g.col_t1, t);

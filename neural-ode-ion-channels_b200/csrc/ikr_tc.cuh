@@ -219,6 +219,25 @@ __device__ __forceinline__ void split3p(f32x2_t h, uint32_t& w1, uint32_t& w2, u
   w3 = pack_bf16x2(a, b);
 }
 
+// Cheaper exact split for the forward epilogues: first term rounded (cvt.rn), second and third
+// TRUNCATED to bf16 with a byte permute.  r1 = x - t1 has <= 16 significant bits, t2 takes its top 8,
+// r2 = r1 - t2 has <= 8 and is a bf16 number itself, so x = t1 + t2 + t3 exactly and |t2|, |t3| obey
+// the same 2^-8 / 2^-16 bounds as the rounded split: 11 instead of 14 pipe cycles per pair.  (The
+// adjoint keeps the rounded split: its first two terms feed the weight-gradient GEMM, where a
+// truncation bias would add up over the samples.)
+__device__ __forceinline__ void split3t(f32x2_t h, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+  float a, b;
+  u2(h, a, b);
+  w1 = pack_bf16x2(a, b);
+  f32x2_t r = sub2(h, p2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xFFFF0000u)));
+  u2(r, a, b);
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  w2 = __byte_perm(ua, ub, 0x7632);
+  r = sub2(r, p2(__uint_as_float(ua & 0xFFFF0000u), __uint_as_float(ub & 0xFFFF0000u)));
+  u2(r, a, b);
+  w3 = __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
+}
+
 }  // namespace tc
 }  // namespace ikr
 #endif  // IKR_TC_CUH_
