@@ -283,9 +283,9 @@ __device__ __forceinline__ void tc_adj_tail(const TcGeom& g, const TcStashGeom& 
 
 // One forward + backward MLP evaluation of the tile (every lane thread of every group).
 // xin[lane] = (nv, a, up, -); result: partial sums of up * d net / d a in tl.part.
-template <int G>
+template <int G, typename Hook = TcNoHook>
 __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& sg, TcLane& tl,
-                                            const TcAdjLane& al) {
+                                            const TcAdjLane& al, Hook hook = Hook()) {
   const int NP = g.NP;
   const float4 in = *reinterpret_cast<const float4*>(tl.xin + 4 * tl.lane);
   const float nv = in.x, a = in.y, up = in.z;
@@ -334,6 +334,7 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
       tc_adj_tail<0>(g, sg, tl, al, w_tail, 0, b0, v, up, acc);
     }
     tc_publish_a(tl);
+    hook();      // owners: time-only terms of the next reversed stage, under the first layer's MMAs
   }
   // ---- hidden layers forward (l = 1..L; H_l has sign-bit row l, the last one is consumed at once) ----
   for (int l = 1; l <= g.L; ++l) {
@@ -405,19 +406,19 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
 }
 
 // Owner-side wrapper of one adjoint evaluation: publish (nv, a, up), take a stash slot, run, collect.
-template <int G>
+template <int G, typename Hook = TcNoHook>
 __device__ __forceinline__ float tc_adj_owner_eval(const TcGeom& g, const TcStashGeom& sg, TcLane& tl,
                                                    TcAdjLane& al, unsigned char* stash,
                                                    volatile long long* stash_slot,
                                                    unsigned long long* counters, bool act, double nv,
-                                                   double ain, double up) {
+                                                   double ain, double up, Hook hook = Hook()) {
   const int tid = tl.lane;
   *reinterpret_cast<float4*>(tl.xin + 4 * tid) =
       make_float4(act ? (float)nv : 0.0f, act ? (float)ain : 0.0f, act ? (float)up : 0.0f, 0.0f);
   if (tid == 0) *stash_slot = (long long)atomicAdd(&counters[1], 1ULL);
   if (G > 1) lanes_sync<G>(); else owners_sync();
   al.slot = stash + (size_t)(*stash_slot) * sg.slot;
-  tc_adj_eval<G>(g, sg, tl, al);
+  tc_adj_eval<G, Hook>(g, sg, tl, al, hook);
   if (G > 1) lanes_sync<G>(); else owners_sync();
   float da = tl.part[tid];
 #pragma unroll
@@ -567,6 +568,8 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
             L.gsum = L.gsum + (S)(w * vm * (double)(y.x * y.y));
           }
         };
+        TimeCache tcache;
+        tcache.valid = 0;
         for (int r = 0; r < p.steps_per_round; ++r) {
           const bool act = L.phase == 0;
           if (!owners_or(act ? 1 : 0)) break;
@@ -586,9 +589,11 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
 #pragma unroll 1
           for (int s = 5; s >= 0; --s) {
             double nv = 0, ain = 0, up = 0;
-            if (act) bdp_stage_inputs<S>(L, cfg, s, &nv, &ain, &up);
+            if (act) bdp_stage_inputs_cached<S>(L, cfg, s, &nv, &ain, &up, tcache);
             const float da = tc_adj_owner_eval<G>(g, sg, tl, al, tp.stash, stash_slot, p.counters, act, nv,
-                                                  ain, up);
+                                                  ain, up, [&]() {
+                                                    if (act && s > 0) bdp_prefetch_stage_time<S>(L, cfg, s - 1, tcache);
+                                                  });
             if (act) bdp_reverse_stage<S>(L, s, (S)da);
           }
           if (act) bdp_finish_step<S>(L);

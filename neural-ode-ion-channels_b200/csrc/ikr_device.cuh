@@ -48,6 +48,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// wait that yields the issue slots between polls (long waits of many threads on one barrier)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
                                          uint64_t* bar) {

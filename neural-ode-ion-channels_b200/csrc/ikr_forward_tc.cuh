@@ -373,7 +373,11 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
   for (int layer = 0; layer < g.L; ++layer) {
     const float* bias = tl.sp + (size_t)(3 + layer) * NP;
     const bool last = layer + 1 == g.L;
+#ifdef IKR_TC_BACKOFF
+    mbar_wait_backoff(tl.bar_d, tl.phase_d, IKR_TC_BACKOFF);
+#else
     mbar_wait(tl.bar_d, tl.phase_d);
+#endif
     tl.phase_d ^= 1u;
     tc::fence_after_sync();
     { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }

@@ -841,6 +841,27 @@ IKR_HD void bdp_stage_inputs(BLane<S>& B, const SolverCfg& c, int s, double* nv,
   *up = adj_mlp_upstream((double)B.lka[s + 1], c);
 }
 
+// Same with the time-only terms (V, rate constants) taken from a TimeCache filled ahead
+template <typename S>
+IKR_HD void bdp_stage_inputs_cached(BLane<S>& B, const SolverCfg& c, int s, double* nv, double* a_in,
+                                    double* up, const TimeCache& tcx) {
+  S ti = dp_stage_time<S>(s, B.t0, B.dt);
+  if (!(tcx.valid && tcx.in_table && tcx.t == (double)ti)) {
+    bdp_stage_inputs<S>(B, c, s, nv, a_in, up);
+    return;
+  }
+  S Ya = dp_stage_state<S>(s, B.ya, B.ka, B.dt);
+  B.jr = (S)(-(tcx.k3 + tcx.k4));
+  B.ja = c.nn_d ? (S)(-(tcx.k1 + tcx.k2)) : (S)0;
+  *nv = mlp_input_nv(tcx.v, true, c.vrange, c.mlp_is_f64 != 0);
+  *a_in = (double)Ya;
+  *up = adj_mlp_upstream((double)B.lka[s + 1], c);
+}
+template <typename S>
+IKR_HD void bdp_prefetch_stage_time(const BLane<S>& B, const SolverCfg& c, int stage, TimeCache& tcx) {
+  time_cache_fill(tcx, c, (double)dp_stage_time<S>(stage, B.t0, B.dt));
+}
+
 // Reverse stage s.  Before: B.lka/lkr[s+1] complete.  `mlp_grad_a` = up * d(net)/d(a_in) (the
 // MLP backward result for this lane).
 //   lambda_Y_s = J^T lambda_k_{s+1} (+ lambda_y1 for s = 5, carried in B.la/lr)
