@@ -68,7 +68,7 @@ struct TcAdjSmemLayout {
   size_t off_bar, off_misc, off_lanes, off_xin, off_part, off_mask, off_sp, off_ring, total;
   __host__ __device__ TcAdjSmemLayout(const TcGeom& g, int stages, int G, int mask_words) {
     size_t o = 0;
-    off_bar = o; o += (size_t)(2 * kTcMaxStages + 2) * 8;
+    off_bar = o; o += (size_t)(2 * kTcMaxStages + 2 * 8 + 2) * 8;
     off_misc = o; o += 48;                                     // tmem base, stop, tile, slot, cmd
     off_lanes = o; o += (size_t)kTcM * sizeof(BLane<S>); o = (o + 15) & ~(size_t)15;
     off_xin = o; o += (size_t)kTcM * 4 * sizeof(float);
@@ -121,7 +121,7 @@ __device__ __forceinline__ tc::f32x2_t tc_leaky_grad2(uint32_t bits, int q, floa
 // MODE 3: backward FIRST layer (dz_0): stash dz_0, reduce dz_0 . w0b
 template <int NK, int MODE>
 __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& sg, const TcLane& tl,
-                                            const TcAdjLane& al, int u, int w_idx, int layer,
+                                            const TcAdjLane& al, int u, unsigned gi, int w_idx, int layer,
                                             const float* bias, uint32_t (&v)[16 * NK], float up,
                                             float& acc) {
   constexpr int NP2 = 8 * NK;       // pairs
@@ -172,7 +172,8 @@ __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& 
     }
   }
   if (MODE != 3) {
-    const uint32_t dst = tl.taddr + g.col_a + 48 * u;
+    tc_unit_acquire(g, tl, gi);
+    const uint32_t dst = tl.taddr + tc_unit_slot_col(g, gi);
     if (NK == 2) {
       tc::st32(dst, reinterpret_cast<uint32_t(&)[32]>(w12));
       tc::st16(dst + 32, reinterpret_cast<uint32_t(&)[16]>(w3));
@@ -180,6 +181,7 @@ __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& 
       tc::st16(dst, reinterpret_cast<uint32_t(&)[16]>(w12));
       tc::st8(dst + 16, reinterpret_cast<uint32_t(&)[8]>(w3));
     }
+    tc_unit_publish(g, tl, gi);
   } else {
     const float* w0b = tl.sp + g.NP + c0;
 #pragma unroll
@@ -199,8 +201,8 @@ __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& 
 // the 8 tail features (feature group 2 KSf) -- same four modes; also writes the constant-1 feature of Hc
 template <int MODE>
 __device__ __forceinline__ void tc_adj_tail(const TcGeom& g, const TcStashGeom& sg, const TcLane& tl,
-                                            const TcAdjLane& al, int w_idx, int layer, const float* bias,
-                                            uint32_t (&v)[8], float up, float& acc) {
+                                            const TcAdjLane& al, unsigned gi, int w_idx, int layer,
+                                            const float* bias, uint32_t (&v)[8], float up, float& acc) {
   const int c0 = 16 * g.KSf;
   const int grp = 2 * g.KSf;
   const float slope = tl.slope;
@@ -266,7 +268,9 @@ __device__ __forceinline__ void tc_adj_tail(const TcGeom& g, const TcStashGeom& 
   if (MODE != 3) {
     const uint32_t t[16] = {t1[0], t1[1], t1[2], t1[3], t2[0], t2[1], t2[2], t2[3],
                             t1[0], t1[1], t1[2], t1[3], t3[0], t3[1], t3[2], t3[3]};
-    tc::st16(tl.taddr + g.col_t1, t);
+    tc_unit_acquire(g, tl, gi);
+    tc::st16(tl.taddr + tc_unit_slot_col(g, gi), t);
+    tc_unit_publish(g, tl, gi);
   } else {
     const float* w0b = tl.sp + g.NP + c0;
 #pragma unroll
@@ -289,10 +293,7 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
   const int NP = g.NP;
   const float4 in = *reinterpret_cast<const float4*>(tl.xin + 4 * tl.lane);
   const float nv = in.x, a = in.y, up = in.z;
-  const int upg = (g.units + G - 1) / G;
-  const int u_begin = tl.group * upg;
-  const int u_end = min(g.units, u_begin + upg);
-  const bool tail_mine = tl.group == G - 1;     // tc_backward_ok: there is a tail
+  const int UT = g.units + g.tail;                 // tc_backward_ok: there is a tail unit
   const int w_tail = al.mask_words - 1;
   float acc = 0.0f;
   long long c0 = clock64();
@@ -317,23 +318,26 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
   // ---- layer 0 forward ------------------------------------------------------------------------------
   {
     const float* b0 = tl.sp + 2 * NP;
-    for (int u = u_begin; u < u_end; ++u) {
-      if (2 * u + 1 < g.KSf) {
-        uint32_t v[32];
-        tc_layer0_sums<32>(tl, NP, 32 * u, nv, a, v);
-        tc_adj_unit<2, 0>(g, sg, tl, al, u, u - u_begin, 0, b0, v, up, acc);
+    for (int u = tl.group; u < UT; u += G) {
+      const unsigned gi = tl.unit_idx + (unsigned)u;
+      const int w = (u - tl.group) / G;
+      if (u < g.units) {
+        if (2 * u + 1 < g.KSf) {
+          uint32_t v[32];
+          tc_layer0_sums<32>(tl, NP, 32 * u, nv, a, v);
+          tc_adj_unit<2, 0>(g, sg, tl, al, u, gi, w, 0, b0, v, up, acc);
+        } else {
+          uint32_t v[16];
+          tc_layer0_sums<16>(tl, NP, 32 * u, nv, a, v);
+          tc_adj_unit<1, 0>(g, sg, tl, al, u, gi, w, 0, b0, v, up, acc);
+        }
       } else {
-        uint32_t v[16];
-        tc_layer0_sums<16>(tl, NP, 32 * u, nv, a, v);
-        tc_adj_unit<1, 0>(g, sg, tl, al, u, u - u_begin, 0, b0, v, up, acc);
+        uint32_t v[8];
+        tc_layer0_sums<8>(tl, NP, 16 * g.KSf, nv, a, v);
+        tc_adj_tail<0>(g, sg, tl, al, gi, w_tail, 0, b0, v, up, acc);
       }
     }
-    if (tail_mine) {
-      uint32_t v[8];
-      tc_layer0_sums<8>(tl, NP, 16 * g.KSf, nv, a, v);
-      tc_adj_tail<0>(g, sg, tl, al, w_tail, 0, b0, v, up, acc);
-    }
-    tc_publish_a(tl);
+    tl.unit_idx += (unsigned)UT;
     hook();      // owners: time-only terms of the next reversed stage, under the first layer's MMAs
   }
   // ---- hidden layers forward (l = 1..L; H_l has sign-bit row l, the last one is consumed at once) ----
@@ -341,65 +345,67 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
     const float* bias = tl.sp + (size_t)(2 + l) * NP;
     const bool last = l == g.L;
     { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
-    mbar_wait(tl.bar_d, tl.phase_d);
-    tl.phase_d ^= 1u;
-    tc::fence_after_sync();
+    const uint32_t dcol = tc_wait_d(g, tl);
     { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
-    for (int u = u_begin; u < u_end; ++u) {
-      if (2 * u + 1 < g.KSf) {
-        uint32_t v[32];
-        tc::ld32(tl.taddr + 32 * u, v);
-        tc::wait_ld();
-        if (!last) tc_adj_unit<2, 0>(g, sg, tl, al, u, u - u_begin, l, bias, v, up, acc);
-        else tc_adj_unit<2, 1>(g, sg, tl, al, u, u - u_begin, l, bias, v, up, acc);
+    for (int u = tl.group; u < UT; u += G) {
+      const unsigned gi = tl.unit_idx + (unsigned)u;
+      const int w = (u - tl.group) / G;
+      if (u < g.units) {
+        if (2 * u + 1 < g.KSf) {
+          uint32_t v[32];
+          tc::ld32(tl.taddr + dcol + 32 * u, v);
+          tc::wait_ld();
+          if (!last) tc_adj_unit<2, 0>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
+          else tc_adj_unit<2, 1>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
+        } else {
+          uint32_t v[16];
+          tc::ld16(tl.taddr + dcol + 32 * u, v);
+          tc::wait_ld();
+          if (!last) tc_adj_unit<1, 0>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
+          else tc_adj_unit<1, 1>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
+        }
       } else {
-        uint32_t v[16];
-        tc::ld16(tl.taddr + 32 * u, v);
+        uint32_t v[8];
+        tc::ld8(tl.taddr + dcol + 16 * g.KSf, v);
         tc::wait_ld();
-        if (!last) tc_adj_unit<1, 0>(g, sg, tl, al, u, u - u_begin, l, bias, v, up, acc);
-        else tc_adj_unit<1, 1>(g, sg, tl, al, u, u - u_begin, l, bias, v, up, acc);
+        if (!last) tc_adj_tail<0>(g, sg, tl, al, gi, w_tail, l, bias, v, up, acc);
+        else tc_adj_tail<1>(g, sg, tl, al, gi, w_tail, l, bias, v, up, acc);
       }
     }
-    if (tail_mine) {
-      uint32_t v[8];
-      tc::ld8(tl.taddr + 16 * g.KSf, v);
-      tc::wait_ld();
-      if (!last) tc_adj_tail<0>(g, sg, tl, al, w_tail, l, bias, v, up, acc);
-      else tc_adj_tail<1>(g, sg, tl, al, w_tail, l, bias, v, up, acc);
-    }
-    tc_publish_a(tl);
+    tl.unit_idx += (unsigned)UT;
   }
   // ---- backward: D = dz_l W_l  ->  dz_{l-1} = D * leaky'(H_{l-1}) ---------------------------------------
   for (int l = g.L; l >= 1; --l) {
     { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
-    mbar_wait(tl.bar_d, tl.phase_d);
-    tl.phase_d ^= 1u;
-    tc::fence_after_sync();
+    const uint32_t dcol = tc_wait_d(g, tl);
     { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
     const bool first = l == 1;
-    for (int u = u_begin; u < u_end; ++u) {
-      if (2 * u + 1 < g.KSf) {
-        uint32_t v[32];
-        tc::ld32(tl.taddr + 32 * u, v);
-        tc::wait_ld();
-        if (!first) tc_adj_unit<2, 2>(g, sg, tl, al, u, u - u_begin, l - 1, nullptr, v, up, acc);
-        else tc_adj_unit<2, 3>(g, sg, tl, al, u, u - u_begin, 0, nullptr, v, up, acc);
+    for (int u = tl.group; u < UT; u += G) {
+      const unsigned gi = tl.unit_idx + (unsigned)u;
+      const int w = (u - tl.group) / G;
+      if (u < g.units) {
+        if (2 * u + 1 < g.KSf) {
+          uint32_t v[32];
+          tc::ld32(tl.taddr + dcol + 32 * u, v);
+          tc::wait_ld();
+          if (!first) tc_adj_unit<2, 2>(g, sg, tl, al, u, gi, w, l - 1, nullptr, v, up, acc);
+          else tc_adj_unit<2, 3>(g, sg, tl, al, u, gi, w, 0, nullptr, v, up, acc);
+        } else {
+          uint32_t v[16];
+          tc::ld16(tl.taddr + dcol + 32 * u, v);
+          tc::wait_ld();
+          if (!first) tc_adj_unit<1, 2>(g, sg, tl, al, u, gi, w, l - 1, nullptr, v, up, acc);
+          else tc_adj_unit<1, 3>(g, sg, tl, al, u, gi, w, 0, nullptr, v, up, acc);
+        }
       } else {
-        uint32_t v[16];
-        tc::ld16(tl.taddr + 32 * u, v);
+        uint32_t v[8];
+        tc::ld8(tl.taddr + dcol + 16 * g.KSf, v);
         tc::wait_ld();
-        if (!first) tc_adj_unit<1, 2>(g, sg, tl, al, u, u - u_begin, l - 1, nullptr, v, up, acc);
-        else tc_adj_unit<1, 3>(g, sg, tl, al, u, u - u_begin, 0, nullptr, v, up, acc);
+        if (!first) tc_adj_tail<2>(g, sg, tl, al, gi, w_tail, l - 1, nullptr, v, up, acc);
+        else tc_adj_tail<3>(g, sg, tl, al, gi, w_tail, 0, nullptr, v, up, acc);
       }
     }
-    if (tail_mine) {
-      uint32_t v[8];
-      tc::ld8(tl.taddr + 16 * g.KSf, v);
-      tc::wait_ld();
-      if (!first) tc_adj_tail<2>(g, sg, tl, al, w_tail, l - 1, nullptr, v, up, acc);
-      else tc_adj_tail<3>(g, sg, tl, al, w_tail, 0, nullptr, v, up, acc);
-    }
-    if (!first) tc_publish_a(tl);
+    if (!first) tl.unit_idx += (unsigned)UT;
   }
   tl.part[tl.group * kTcM + tl.lane] = acc;
   { const long long c1 = clock64(); tl.c_epi += c1 - c0; }
@@ -446,20 +452,10 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
   volatile int* cmd_exit = reinterpret_cast<volatile int*>(smem_raw + lay.off_misc + 24);
   BLane<S>* lanes = reinterpret_cast<BLane<S>*>(smem_raw + lay.off_lanes);
   float* sp = reinterpret_cast<float*>(smem_raw + lay.off_sp);
-  TcEngineCtx eng;
-  eng.bar_full = bars; eng.bar_empty = bars + kTcMaxStages;
-  eng.bar_a = bars + 2 * kTcMaxStages; eng.bar_d = eng.bar_a + 1;
-  eng.stop_flag = stop_flag; eng.ring = smem_raw + lay.off_ring;
+  const TcEngineCtx eng = tc_engine_ctx(bars, stop_flag, smem_raw + lay.off_ring);
 
   if (tid == 0) {
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&eng.bar_full[s], 1);
-      mbar_init(&eng.bar_empty[s], 1);
-    }
-    mbar_init(eng.bar_a, kLaneThreads / 32);
-    mbar_init(eng.bar_d, 1);
-    mbar_fence_init();
-    *stop_flag = 0;
+    tc_engine_init(eng, g.stages);
     *cmd_exit = 0;
   }
   if (warp == kMmaWarp) tc::tmem_alloc(smem_u32(tmem_slot), tc::kTmemCols);
@@ -491,9 +487,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
     tl.group = warp >> 2;
     tl.lane = tid & 127;
     tl.taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    tl.bar_a = smem_u32(eng.bar_a);
-    tl.bar_d = eng.bar_d;
-    tl.phase_d = 0;
+    tc_lane_attach(tl, eng);
     tl.sp = sp;
     tl.xin = reinterpret_cast<float*>(smem_raw + lay.off_xin);
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
@@ -644,8 +638,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
       owners_sync();
       if (G > 1) lanes_sync<G>();
     }
-    __syncwarp();
-    if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
+    tc_release_engines(tl);
   }
 
   tc::fence_before_sync();

@@ -232,6 +232,9 @@ TcPlan make_tc_plan(const ikr_desc* d) {
     const int v = atoi(e);
     if (v >= 1 && v <= 3) t.groups = v;
   }
+  // every column group must produce at least one unit per layer pass (it then consumes every phase
+  // of the pass barriers in order)
+  if (t.groups > t.g.units + t.g.tail) t.groups = t.g.units + t.g.tail;
   const size_t fixed = d->state_dtype == IKR_F32 ? TcSmemLayout<float>(t.g, 0, t.groups).total
                                                   : TcSmemLayout<double>(t.g, 0, t.groups).total;
   if (fixed + (size_t)kTcMinStages * t.g.stage_bytes > kSmemLimit) return t;

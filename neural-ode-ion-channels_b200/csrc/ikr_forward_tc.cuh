@@ -49,9 +49,10 @@ struct TcGeom {
   int tail;          // 1: a final tail step covers the last n % 16 <= 8 features
   int KST;           // steps per layer = KSf + tail = ring stages consumed per layer
   int units;         // epilogue work units: pairs of k-steps (the last one may hold a single k-step)
-  int col_a;         // TMEM column of the A operand: unit u at col_a + 48 u as [a1 | a2 | a3], each
-                     // 16 columns (two k-steps) -- or 8 columns each for a single-k-step unit
-  int col_t1, col_t2;  // tail blocks [a1t | a2t], [a1t | a3t] (adjacent: one 16-column store)
+  int col_ring;      // TMEM column of the A-operand unit ring: two slots of 48 columns, a unit as
+                     // [a1 | a2 | a3] of 16 columns each (two k-steps) -- 8 each for a single k-step;
+                     // the tail as [a1t | a2t | a1t | a3t] in the first 16 columns of its slot.
+                     // Columns [0, NP) and [NP, 2 NP) are the two D accumulators.
   int cols;          // TMEM columns used
   int block_bytes;   // one B block: NP x 16 bf16 = NP * 32 bytes
   int stage_bytes;   // one k-step: 3 blocks
@@ -68,10 +69,8 @@ __host__ __device__ inline TcGeom tc_geometry(int n, int L) {
   g.tail = (rem > 0 && rem <= 8) ? 1 : 0;
   g.KST = g.KSf + g.tail;
   g.units = (g.KSf + 1) / 2;
-  g.col_a = g.NP;
-  g.col_t1 = g.col_a + 24 * g.KSf;
-  g.col_t2 = g.col_t1 + 8;
-  g.cols = g.col_t1 + (g.tail ? 16 : 0);
+  g.col_ring = 2 * g.NP;
+  g.cols = g.col_ring + 96;
   g.block_bytes = g.NP * 32;
   g.stage_bytes = 3 * g.block_bytes;
   g.stages = 0;
@@ -81,13 +80,6 @@ __host__ __device__ inline TcGeom tc_geometry(int n, int L) {
 __host__ __device__ inline bool tc_geometry_ok(const TcGeom& g) {
   return g.n >= 16 && g.NP <= 256 && g.cols <= (int)tc::kTmemCols && g.KST >= 1;
 }
-// TMEM column (relative to the allocation) of bf16 term t of k-step j
-__host__ __device__ inline int tc_a_col(const TcGeom& g, int t, int j) {
-  const int u = j >> 1;
-  const bool full = 2 * u + 1 < g.KSf;
-  return g.col_a + 48 * u + (full ? 16 * t + 8 * (j & 1) : 8 * t);
-}
-
 // ---- weight image: [layer][k-step][block 0..2][NP x 16 bf16 in core-matrix order] -----------------
 struct TcPackParams {
   const float* wn;   // [L][n][npad] rows = output features (packed-parameter section off_wn)
@@ -147,7 +139,7 @@ struct TcSmemLayout {
   size_t off_bar, off_misc, off_job, off_lanes, off_obs, off_aux, off_xin, off_part, off_sp, off_ring, total;
   __host__ __device__ TcSmemLayout(const TcGeom& g, int stages, int G) {
     size_t o = 0;
-    off_bar = o; o += (size_t)(2 * kTcMaxStages + 2) * 8;          // full[], empty[], a_ready, d_ready
+    off_bar = o; o += (size_t)(2 * kTcMaxStages + 2 * 8 + 2) * 8;  // full[], empty[], unit_ready[8], unit_done[8], d_ready
     off_misc = o; o += 32;                                          // tmem base, stop flag, tile slot
     off_job = o; o += (size_t)kInlineJobs * ((sizeof(FwdJob) + 15) & ~(size_t)15);   // pool: job table
     off_lanes = o; o += (size_t)kTcM * sizeof(Lane<S>); o = (o + 15) & ~(size_t)15;
@@ -189,13 +181,16 @@ __device__ __forceinline__ int owners_or(int pred) {
 // Per-thread view of the tensor-core MLP
 struct TcLane {
   uint32_t taddr;        // TMEM address of this thread's lane, column 0 of the allocation
-  uint32_t bar_a;        // shared-memory address of the a_ready mbarrier
-  uint64_t* bar_d;       // d_ready mbarrier
+  uint64_t* unit_ready;  // [kTcMaxUnits] unit u of the pass is in its slot (4 warp arrivals: its group)
+  uint64_t* unit_done;   // [kTcMaxUnits] tcgen05.commit: the MMAs of unit u of the pass are done
+  uint64_t* bar_d;       // tcgen05.commit: the layer's D is complete
   unsigned phase_d;      // parity of the next d_ready completion
+  unsigned n_pass;       // layer passes whose D this thread has consumed: D of the next one is in buffer n_pass & 1
+  unsigned unit_idx;     // global sequence number of the first unit of the pass being produced
   int group;             // column group 0..G-1
   int lane;              // TMEM lane 0..127
   const float* sp;       // small parameters (stride NP): w0a | w0b | b0 | L x bias | w_last, b_last
-  float* xin;            // [128][2] (nv, a) broadcast by the owner
+  float* xin;            // [128][2] (nv, a) broadcast by the owner ([128][4] in the adjoint kernel)
   float* part;           // [G][128] partial output sums
   float slope;
   long long c_l0, c_wait, c_epi;   // phase clocks (timing runs)
@@ -206,23 +201,47 @@ struct TcLane {
 
 __device__ __forceinline__ float tc_leaky(float x, float slope) { return x > 0.0f ? x : x * slope; }
 
-// A operand of this thread is in TMEM: one arrival per WARP on a_ready (every lane orders its stores
-// before the warp barrier; 12 arrivals instead of 384 keep the mbarrier off the critical path)
-__device__ __forceinline__ void tc_publish_a(const TcLane& tl) {
+// ---- A-operand unit ring ---------------------------------------------------------------------------
+// The activations of the next layer do not wait in TMEM for the whole layer: they flow through a ring
+// of TWO 48-column unit slots (two K-steps: [a1 16 | a2 16 | a3 16]; the tail uses 16 columns of a
+// slot).  Units are numbered globally (all passes of all evaluations): unit i = pass i / UT, position
+// i % UT, slot i & 1.  Barriers are per POSITION (every phase of a barrier is consumed by the same
+// waiter, in order, so the parity never aliases): the producing group of unit i first waits for
+// unit_done of unit i - 2 (the previous user of its slot), stores, and arrives on unit_ready (one
+// arrival per warp); the MMA warp issues the unit's K-steps as soon as it lands and commits
+// unit_done.  So the MMAs of layer l + 1 start after the FIRST unit of the epilogue of layer l and
+// run under the rest of it, accumulating into the other D buffer.
+constexpr unsigned kTcStaggerNs = 200;   // start delay per column group after d_ready
+constexpr int kTcMaxUnits = 8;     // NP <= 208: at most 7 units of two K-steps + the tail
+__device__ __forceinline__ uint32_t tc_unit_slot_col(const TcGeom& g, unsigned gi) {
+  return (uint32_t)g.col_ring + 48u * (gi & 1u);
+}
+__device__ __forceinline__ void tc_unit_acquire(const TcGeom& g, const TcLane& tl, unsigned gi) {
+  if (gi >= 2u) {
+    const unsigned UT = (unsigned)(g.units + g.tail);
+    const unsigned prev = gi - 2u;
+    mbar_wait(&tl.unit_done[prev % UT], (prev / UT) & 1u);
+    tc::fence_after_sync();
+  }
+}
+__device__ __forceinline__ void tc_unit_publish(const TcGeom& g, const TcLane& tl, unsigned gi) {
   tc::wait_st();
   tc::fence_before_sync();
   __syncwarp();
-  if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
+  if ((tl.lane & 31) == 0) mbar_arrive(&tl.unit_ready[gi % (unsigned)(g.units + g.tail)]);
 }
+// unit u of a pass belongs to column group u % G; the tail is unit number g.units
+template <int G>
+__device__ __forceinline__ int tc_units_total(const TcGeom& g) { return g.units + g.tail; }
 
-// One epilogue work unit of NK = 1 or 2 k-steps (16 NK features starting at feature c0): the
-// pre-activations arrive in v (raw fp32 bits: D columns, or layer-0 sums), get bias + LeakyReLU,
-// and either become the next A operand (three bf16 terms, written with one 16 NK-column store for
-// [a1 | a2] and one 8 NK-column store for a3) or are reduced against w_last.
+// One epilogue work unit of NK = 1 or 2 k-steps (features 32 u ..): the pre-activations arrive in v
+// (raw fp32 bits: D columns, or layer-0 sums), get bias + LeakyReLU, and either become a unit of the
+// next A operand (three bf16 terms: one 16 NK-column store for [a1 | a2], one 8 NK-column store for
+// a3, into ring slot `gi`) or are reduced against w_last.
 template <int NK>
-__device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl, int u, const float* bias,
-                                               uint32_t (&v)[16 * NK], bool last, const float* wl,
-                                               float (&s)[4]) {
+__device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl, int u, unsigned gi,
+                                               const float* bias, uint32_t (&v)[16 * NK], bool last,
+                                               const float* wl, float (&s)[4]) {
   const int c0 = 32 * u;
   const tc::f32x2_t slope2 = tc::p2(tl.slope, tl.slope);
   tc::f32x2_t h[8 * NK];
@@ -238,25 +257,16 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
     uint32_t w12[16 * NK], w3[8 * NK];
 #pragma unroll
     for (int q = 0; q < 8 * NK; ++q) tc::split3t(h[q], w12[q], w12[8 * NK + q], w3[q]);
-    const uint32_t dst = tl.taddr + g.col_a + 48 * u;
-#ifdef IKR_TC_TRACE
-    const long long ts0 = clock64();
-#endif
+    tc_unit_acquire(g, tl, gi);
+    const uint32_t dst = tl.taddr + tc_unit_slot_col(g, gi);
     if (NK == 2) {
       tc::st32(dst, reinterpret_cast<uint32_t(&)[32]>(w12));
-#ifdef IKR_TC_TRACE
-      const long long ts1 = clock64();
-#endif
       tc::st16(dst + 32, reinterpret_cast<uint32_t(&)[16]>(w3));
-#ifdef IKR_TC_TRACE
-      const long long ts2 = clock64();
-      if (tl.trace_eval == 300 && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && u == 0 && bias == tl.sp + 4 * g.NP)
-        printf("[trace-st] warp %d: st32 issue %lld, st16 issue %lld cycles\n", (int)(threadIdx.x >> 5), ts1 - ts0, ts2 - ts1);
-#endif
     } else {
       tc::st16(dst, reinterpret_cast<uint32_t(&)[16]>(w12));
       tc::st8(dst + 16, reinterpret_cast<uint32_t(&)[8]>(w3));
     }
+    tc_unit_publish(g, tl, gi);
   } else {
 #pragma unroll
     for (int q = 0; q < 4 * NK; ++q) {
@@ -272,8 +282,9 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
   }
 }
 // the 8 tail features (columns 16 KSf ..): blocks [a1t | a2t | a1t | a3t] in one 16-column store
-__device__ __forceinline__ void tc_tail_finish(const TcGeom& g, const TcLane& tl, const float* bias,
-                                               uint32_t (&v)[8], bool last, const float* wl, float (&s)[4]) {
+__device__ __forceinline__ void tc_tail_finish(const TcGeom& g, const TcLane& tl, unsigned gi,
+                                               const float* bias, uint32_t (&v)[8], bool last,
+                                               const float* wl, float (&s)[4]) {
   const int c0 = 16 * g.KSf;
   const tc::f32x2_t slope2 = tc::p2(tl.slope, tl.slope);
   tc::f32x2_t h[4];
@@ -292,7 +303,9 @@ __device__ __forceinline__ void tc_tail_finish(const TcGeom& g, const TcLane& tl
       tc::split3t(h[q], t[q], t[4 + q], t[12 + q]);
       t[8 + q] = t[q];
     }
-    tc::st16(tl.taddr + g.col_t1, t);
+    tc_unit_acquire(g, tl, gi);
+    tc::st16(tl.taddr + tc_unit_slot_col(g, gi), t);
+    tc_unit_publish(g, tl, gi);
   } else {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -325,103 +338,95 @@ __device__ __forceinline__ void tc_layer0_sums(const TcLane& tl, int NP, int c0,
   }
 }
 
-// One MLP evaluation of the 128-trajectory tile, executed by EVERY lane thread (all G groups, masked
-// lanes included: the a_ready barrier counts 128 G arrivals).  The caller has published (nv, a) in
-// tl.xin and passed the lanes barrier; the partial output sums land in tl.part (caller syncs).
-// Group c works on the contiguous unit range [c upg, (c + 1) upg); the last group adds the tail.
 struct TcNoHook {
   __device__ __forceinline__ void operator()() const {}
 };
-// `hook` runs right after this thread's layer-0 part is published, i.e. while the MMAs of layer 1
-// execute: the owners use it to compute time-only RHS terms of the next stage ahead.
+// wait for the D of the next layer pass; returns its TMEM column (the two D buffers alternate)
+__device__ __forceinline__ uint32_t tc_wait_d(const TcGeom& g, TcLane& tl) {
+#ifdef IKR_TC_BACKOFF
+  mbar_wait_backoff(tl.bar_d, tl.phase_d, IKR_TC_BACKOFF);
+#else
+  mbar_wait(tl.bar_d, tl.phase_d);
+#endif
+  tl.phase_d ^= 1u;
+  tc::fence_after_sync();
+  const uint32_t col = (tl.n_pass & 1u) ? (uint32_t)g.NP : 0u;
+  tl.n_pass += 1u;
+  // Stagger the column groups: the MMAs of the next layer start with unit 0 (group 0), and a pass of
+  // MMAs (~7.6 k cycles) is several times longer than a whole epilogue, so the later groups give the
+  // first ones the issue slots (unit 0 lands in ~0.4 k instead of ~1.1 k cycles after d_ready).
+  if (tl.group > 0) __nanosleep(kTcStaggerNs * (unsigned)tl.group);
+  return col;
+}
+
+// One MLP evaluation of the 128-trajectory tile, executed by EVERY lane thread (all G groups, masked
+// lanes included).  The caller has published (nv, a) in tl.xin and passed the lanes barrier; the
+// partial output sums land in tl.part (caller syncs).  Group c produces the units u = c (mod G) of
+// every pass.  `hook` runs after this thread's layer-0 units are published, i.e. while the MMAs of
+// layer 1 execute: the owners use it to compute time-only RHS terms of the next stage ahead.
 template <int G, typename Hook = TcNoHook>
 __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook hook = Hook()) {
   const int NP = g.NP;
   const float2 in = *reinterpret_cast<const float2*>(tl.xin + 2 * tl.lane);
   const float nv = in.x, a = in.y;
-  const int upg = (g.units + G - 1) / G;
-  const int u_begin = tl.group * upg;
-  const int u_end = min(g.units, u_begin + upg);
-  const bool tail_mine = g.tail && tl.group == G - 1;
+  const int UT = g.units + g.tail;
   float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   const float* wl = tl.sp + (size_t)(3 + g.L) * NP;
   long long c0 = clock64();
   // ---- layer 0 ------------------------------------------------------------------------------
   {
     const float* b0 = tl.sp + 2 * NP;
-    for (int u = u_begin; u < u_end; ++u) {
-      if (2 * u + 1 < g.KSf) {
-        uint32_t v[32];
-        tc_layer0_sums<32>(tl, NP, 32 * u, nv, a, v);
-        tc_unit_finish<2>(g, tl, u, b0, v, false, wl, s);
+    if (tl.group > 0) __nanosleep(kTcStaggerNs * (unsigned)tl.group);
+    for (int u = tl.group; u < UT; u += G) {
+      const unsigned gi = tl.unit_idx + (unsigned)u;
+      if (u < g.units) {
+        if (2 * u + 1 < g.KSf) {
+          uint32_t v[32];
+          tc_layer0_sums<32>(tl, NP, 32 * u, nv, a, v);
+          tc_unit_finish<2>(g, tl, u, gi, b0, v, false, wl, s);
+        } else {
+          uint32_t v[16];
+          tc_layer0_sums<16>(tl, NP, 32 * u, nv, a, v);
+          tc_unit_finish<1>(g, tl, u, gi, b0, v, false, wl, s);
+        }
       } else {
-        uint32_t v[16];
-        tc_layer0_sums<16>(tl, NP, 32 * u, nv, a, v);
-        tc_unit_finish<1>(g, tl, u, b0, v, false, wl, s);
+        uint32_t v[8];
+        tc_layer0_sums<8>(tl, NP, 16 * g.KSf, nv, a, v);
+        tc_tail_finish(g, tl, gi, b0, v, false, wl, s);
       }
     }
-    if (tail_mine) {
-      uint32_t v[8];
-      tc_layer0_sums<8>(tl, NP, 16 * g.KSf, nv, a, v);
-      tc_tail_finish(g, tl, b0, v, false, wl, s);
-    }
-    tc_publish_a(tl);
+    tl.unit_idx += (unsigned)UT;
   }
   { const long long c1 = clock64(); tl.c_l0 += c1 - c0; c0 = c1; }
   hook();
-  // ---- hidden layers: read D, bias + LeakyReLU, write the next A (or reduce the output) -----------
+  // ---- hidden layers: read D, bias + LeakyReLU, produce the next A units (or reduce the output) ---
   for (int layer = 0; layer < g.L; ++layer) {
     const float* bias = tl.sp + (size_t)(3 + layer) * NP;
     const bool last = layer + 1 == g.L;
-#ifdef IKR_TC_BACKOFF
-    mbar_wait_backoff(tl.bar_d, tl.phase_d, IKR_TC_BACKOFF);
-#else
-    mbar_wait(tl.bar_d, tl.phase_d);
-#endif
-    tl.phase_d ^= 1u;
-    tc::fence_after_sync();
+    const uint32_t dcol = tc_wait_d(g, tl);
     { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
-#ifdef IKR_TC_TRACE
-    long long tr[8]; int ti = 0;
-    const bool tracing = layer == 1 && tl.trace_eval == 300 && blockIdx.x == 0;   // warp-uniform
-    if (tracing) tr[ti++] = clock64();
-#endif
-    for (int u = u_begin; u < u_end; ++u) {
-      if (2 * u + 1 < g.KSf) {
-        uint32_t v[32];
-        tc::ld32(tl.taddr + 32 * u, v);
-        tc::wait_ld();
-#ifdef IKR_TC_TRACE
-        if (tracing && ti < 7) tr[ti++] = clock64();
-#endif
-        tc_unit_finish<2>(g, tl, u, bias, v, last, wl, s);
-#ifdef IKR_TC_TRACE
-        if (tracing && ti < 7) tr[ti++] = clock64();
-#endif
+    for (int u = tl.group; u < UT; u += G) {
+      const unsigned gi = tl.unit_idx + (unsigned)u;
+      if (u < g.units) {
+        if (2 * u + 1 < g.KSf) {
+          uint32_t v[32];
+          tc::ld32(tl.taddr + dcol + 32 * u, v);
+          tc::wait_ld();
+          tc_unit_finish<2>(g, tl, u, gi, bias, v, last, wl, s);
+        } else {
+          uint32_t v[16];
+          tc::ld16(tl.taddr + dcol + 32 * u, v);
+          tc::wait_ld();
+          tc_unit_finish<1>(g, tl, u, gi, bias, v, last, wl, s);
+        }
       } else {
-        uint32_t v[16];
-        tc::ld16(tl.taddr + 32 * u, v);
+        uint32_t v[8];
+        tc::ld8(tl.taddr + dcol + 16 * g.KSf, v);
         tc::wait_ld();
-        tc_unit_finish<1>(g, tl, u, bias, v, last, wl, s);
+        tc_tail_finish(g, tl, gi, bias, v, last, wl, s);
       }
     }
-    if (tail_mine) {
-      uint32_t v[8];
-      tc::ld8(tl.taddr + 16 * g.KSf, v);
-      tc::wait_ld();
-      tc_tail_finish(g, tl, bias, v, last, wl, s);
-    }
-#ifdef IKR_TC_TRACE
-    if (tracing) { tr[ti++] = clock64(); tc::wait_st(); tr[ti++] = clock64(); }
-#endif
-    if (!last) tc_publish_a(tl);
-#ifdef IKR_TC_TRACE
-    if (tracing && (threadIdx.x & 31) == 0) {
-      const long long te = clock64();
-      printf("[trace] warp %d (group %d): d_ready->ld0 %lld, unit0 %lld, ld1 %lld, unit1 %lld, tail.. %lld, wait_st %lld, publish %lld | abs start %lld end %lld\n",
-             (int)(threadIdx.x >> 5), tl.group, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], te - tr[6], tr[0], te);
-    }
-#endif
+    if (!last) tl.unit_idx += (unsigned)UT;
     { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
   }
 #ifdef IKR_TC_TRACE
@@ -444,71 +449,123 @@ __device__ __forceinline__ float tc_owner_eval(const TcGeom& g, TcLane& tl, floa
   return out + tl.sp[(size_t)(4 + g.L) * g.NP];
 }
 
-// ---- engine warps (shared by the forward and the adjoint kernel) ---------------------------------------
+// ---- engine warps (shared by the forward, adjoint and regression kernels) ------------------------------
 struct TcEngineCtx {
   uint64_t* bar_full;
   uint64_t* bar_empty;
-  uint64_t* bar_a;        // every lane thread arrives once its part of the A operand is in TMEM
-  uint64_t* bar_d;        // tcgen05.commit: the layer's D is complete
+  uint64_t* unit_ready;   // [kTcMaxUnits]
+  uint64_t* unit_done;    // [kTcMaxUnits]
+  uint64_t* bar_d;
   volatile int* stop_flag;
   unsigned char* ring;
 };
+__device__ __forceinline__ TcEngineCtx tc_engine_ctx(uint64_t* bars, volatile int* stop_flag, unsigned char* ring) {
+  TcEngineCtx e;
+  e.bar_full = bars;
+  e.bar_empty = bars + kTcMaxStages;
+  e.unit_ready = bars + 2 * kTcMaxStages;
+  e.unit_done = e.unit_ready + kTcMaxUnits;
+  e.bar_d = e.unit_done + kTcMaxUnits;
+  e.stop_flag = stop_flag;
+  e.ring = ring;
+  return e;
+}
+// thread 0, before the first CTA barrier
+__device__ __forceinline__ void tc_engine_init(const TcEngineCtx& e, int stages) {
+  for (int s = 0; s < stages; ++s) {
+    mbar_init(&e.bar_full[s], 1);
+    mbar_init(&e.bar_empty[s], 1);
+  }
+  for (int s = 0; s < kTcMaxUnits; ++s) {
+    mbar_init(&e.unit_ready[s], 4);     // the four warps of the producing column group
+    mbar_init(&e.unit_done[s], 1);
+  }
+  mbar_init(e.bar_d, 1);
+  mbar_fence_init();
+  *e.stop_flag = 0;
+}
+__device__ __forceinline__ void tc_lane_attach(TcLane& tl, const TcEngineCtx& e) {
+  tl.unit_ready = e.unit_ready;
+  tl.unit_done = e.unit_done;
+  tl.bar_d = e.bar_d;
+  tl.phase_d = 0;
+  tl.n_pass = 0;
+  tl.unit_idx = 0;
+}
+// after the stop flag is set: the four warps of group 0 (the producers of unit 0) complete one more
+// phase of unit_ready[0], on which the MMA warp is waiting between passes (it sees the flag and leaves)
+__device__ __forceinline__ void tc_release_engines(const TcLane& tl) {
+  __syncwarp();
+  if (tl.group == 0 && (tl.lane & 31) == 0) mbar_arrive(&tl.unit_ready[0]);
+}
 
 // MMA issuer.  The whole warp runs the loop (warp-uniform control flow and operands => the descriptors
 // live in uniform registers and each MMA is one UTCHMMA); one elected lane issues the MMAs and commits.
-// Every a_ready phase triggers the MMAs of ONE layer: KST ring stages, six MMAs per regular K-step.
+// A layer pass = the units 0 .. UT-1 in order; every unit is issued as soon as its slot is filled.
 __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& c, uint32_t tbase, bool timing) {
   const unsigned stages = (unsigned)g.stages;
   const uint32_t idesc = tc::idesc_bf16_f32(kTcM, g.NP);
   const uint64_t desc0 = tc::smem_desc(smem_u32(c.ring), 128, 256);
   const uint32_t blk16 = (uint32_t)g.block_bytes >> 4, stage16 = (uint32_t)g.stage_bytes >> 4;
-  const uint32_t a_base = tbase + g.col_a;
-  unsigned s = 0, round = 0, consumed = 0, phase_a = 0;
+  const int UT = g.units + g.tail;
+  unsigned s = 0, round = 0, consumed = 0, gi = 0, pass = 0;
   long long e_wait = 0, e_issue = 0, ec = clock64();
-  while (true) {
-    mbar_wait(c.bar_a, phase_a);
-    phase_a ^= 1u;
-    if (*c.stop_flag) break;
-    tc::fence_after_sync();
-    { const long long c1 = clock64(); e_wait += c1 - ec; ec = c1; }
-#pragma unroll 1
-    for (int j = 0; j < g.KST; ++j) {
-      mbar_wait(&c.bar_full[s], round);
+  bool stop = false;
+  while (!stop) {
+    const uint32_t dcol = tbase + ((pass & 1u) ? (uint32_t)g.NP : 0u);
+    bool first = true;
+    for (int u = 0; u < UT; ++u, ++gi) {
+      const unsigned slot = gi & 1u;
+      { const long long c1 = clock64(); e_issue += c1 - ec; ec = c1; }
+      mbar_wait(&c.unit_ready[u], pass & 1u);
+      if (*c.stop_flag) { stop = true; break; }
       tc::fence_after_sync();
-      if (tc::elect_one()) {
-        const uint64_t b1 = desc0 + (uint64_t)(s * stage16);
-        const uint64_t b2 = b1 + blk16, b3 = b2 + blk16;
-        if (j < g.KSf) {
-          const bool full = (j | 1) < g.KSf;
-          const uint32_t a1 = a_base + 48 * (j >> 1) + (full ? 8 * (j & 1) : 0);
-          const uint32_t dt = full ? 16u : 8u;
-          tc::mma_ts(tbase, a1, b1, idesc, j > 0 ? 1u : 0u);
-          tc::mma_ts(tbase, a1 + dt, b1, idesc, 1u);
-          tc::mma_ts(tbase, a1 + 2 * dt, b1, idesc, 1u);
-          tc::mma_ts(tbase, a1, b2, idesc, 1u);
-          tc::mma_ts(tbase, a1 + dt, b2, idesc, 1u);
-          tc::mma_ts(tbase, a1, b3, idesc, 1u);
-        } else {
-          tc::mma_ts(tbase, tbase + g.col_t1, b1, idesc, j > 0 ? 1u : 0u);
-          tc::mma_ts(tbase, tbase + g.col_t1, b2, idesc, 1u);
-          tc::mma_ts(tbase, tbase + g.col_t2, b3, idesc, 1u);
+      { const long long c1 = clock64(); e_wait += c1 - ec; ec = c1; }
+      const uint32_t a_slot = tbase + (uint32_t)g.col_ring + 48u * slot;
+      const bool is_tail = u >= g.units;
+      const int nk = is_tail ? 1 : ((2 * u + 1 < g.KSf) ? 2 : 1);
+#pragma unroll 1
+      for (int jj = 0; jj < nk; ++jj) {
+        mbar_wait(&c.bar_full[s], round);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint64_t b1 = desc0 + (uint64_t)(s * stage16);
+          const uint64_t b2 = b1 + blk16, b3 = b2 + blk16;
+          if (!is_tail) {
+            const uint32_t dt = nk == 2 ? 16u : 8u;
+            const uint32_t a1 = a_slot + 8u * (uint32_t)jj;
+            tc::mma_ts(dcol, a1, b1, idesc, first ? 0u : 1u);
+            tc::mma_ts(dcol, a1 + dt, b1, idesc, 1u);
+            tc::mma_ts(dcol, a1 + 2 * dt, b1, idesc, 1u);
+            tc::mma_ts(dcol, a1, b2, idesc, 1u);
+            tc::mma_ts(dcol, a1 + dt, b2, idesc, 1u);
+            tc::mma_ts(dcol, a1, b3, idesc, 1u);
+          } else {
+            tc::mma_ts(dcol, a_slot, b1, idesc, first ? 0u : 1u);
+            tc::mma_ts(dcol, a_slot, b2, idesc, 1u);
+            tc::mma_ts(dcol, a_slot + 8u, b3, idesc, 1u);
+          }
+          tc::commit(smem_u32(&c.bar_empty[s]));   // weight slot free once these MMAs have read it
         }
-        tc::commit(smem_u32(&c.bar_empty[s]));   // slot free once these MMAs have read it
+        __syncwarp();
+        first = false;
+        ++consumed;
+        if (++s == stages) { s = 0; round ^= 1u; }
       }
+      if (tc::elect_one()) tc::commit(smem_u32(&c.unit_done[u]));      // its A slot may be refilled
       __syncwarp();
-      ++consumed;
-      if (++s == stages) { s = 0; round ^= 1u; }
     }
+    if (stop) break;
     if (tc::elect_one()) tc::commit(smem_u32(c.bar_d));
     __syncwarp();
-    { const long long c1 = clock64(); e_issue += c1 - ec; ec = c1; }
+    ++pass;
   }
   // stop: every MMA has completed (its D was consumed).  The producer can only be blocked on the
   // slot of the next k-step to consume: complete that phase by hand (it re-checks the flag).
   if (tc::elect_one()) {
     mbar_arrive(&c.bar_empty[s]);
     if (timing)
-      printf("[tc timing] mma warp: wait_a %lld issue %lld cycles, %u k-steps\n", e_wait, e_issue, consumed);
+      printf("[tc timing] mma warp: wait_units %lld issue %lld cycles, %u k-steps\n", e_wait, e_issue, consumed);
   }
   __syncwarp();
 }
@@ -542,10 +599,6 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
   constexpr int kMmaWarp = 4 * G, kLoadWarp = 4 * G + 1;
   const TcSmemLayout<S> lay(g, g.stages, G);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + lay.off_bar);
-  uint64_t* bar_full = bars;
-  uint64_t* bar_empty = bars + kTcMaxStages;
-  uint64_t* bar_a = bars + 2 * kTcMaxStages;
-  uint64_t* bar_d = bar_a + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + lay.off_misc);
   volatile int* stop_flag = reinterpret_cast<volatile int*>(smem_raw + lay.off_misc + 4);
   long long* tile_slot = reinterpret_cast<long long*>(smem_raw + lay.off_misc + 8);
@@ -554,21 +607,11 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
   Lane<S>* lanes = reinterpret_cast<Lane<S>*>(smem_raw + lay.off_lanes);
   double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);
   float* sp = reinterpret_cast<float*>(smem_raw + lay.off_sp);
-  unsigned char* ring = smem_raw + lay.off_ring;
-  TcEngineCtx eng;
-  eng.bar_full = bar_full; eng.bar_empty = bar_empty; eng.bar_a = bar_a; eng.bar_d = bar_d;
-  eng.stop_flag = stop_flag; eng.ring = ring;
+  const TcEngineCtx eng = tc_engine_ctx(bars, stop_flag, smem_raw + lay.off_ring);
 
   // ---- one-time setup ------------------------------------------------------------------------------
   if (tid == 0) {
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1);
-    }
-    mbar_init(bar_a, kLaneThreads / 32);
-    mbar_init(bar_d, 1);
-    mbar_fence_init();
-    *stop_flag = 0;
+    tc_engine_init(eng, g.stages);
     *cmd_exit = 0;
   }
   if (warp == kMmaWarp) tc::tmem_alloc(smem_u32(tmem_slot), tc::kTmemCols);
@@ -602,9 +645,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
     tl.group = warp >> 2;
     tl.lane = tid & 127;
     tl.taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    tl.bar_a = smem_u32(bar_a);
-    tl.bar_d = bar_d;
-    tl.phase_d = 0;
+    tc_lane_attach(tl, eng);
     tl.sp = sp;
     tl.xin = reinterpret_cast<float*>(smem_raw + lay.off_xin);
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
@@ -772,9 +813,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
       owners_sync();
       if (G > 1) lanes_sync<G>();
     }
-    // one more a_ready phase wakes the MMA thread, which sees the stop flag
-    __syncwarp();
-    if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
+    tc_release_engines(tl);     // wakes the MMA warp, which sees the stop flag
   }
 
   tc::fence_before_sync();
@@ -808,20 +847,10 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
   double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);
   LaneAux<S>* aux = reinterpret_cast<LaneAux<S>*>(smem_raw + lay.off_aux);
   float* sp = reinterpret_cast<float*>(smem_raw + lay.off_sp);
-  TcEngineCtx eng;
-  eng.bar_full = bars; eng.bar_empty = bars + kTcMaxStages;
-  eng.bar_a = bars + 2 * kTcMaxStages; eng.bar_d = eng.bar_a + 1;
-  eng.stop_flag = stop_flag; eng.ring = smem_raw + lay.off_ring;
+  const TcEngineCtx eng = tc_engine_ctx(bars, stop_flag, smem_raw + lay.off_ring);
 
   if (tid == 0) {
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&eng.bar_full[s], 1);
-      mbar_init(&eng.bar_empty[s], 1);
-    }
-    mbar_init(eng.bar_a, kLaneThreads / 32);
-    mbar_init(eng.bar_d, 1);
-    mbar_fence_init();
-    *stop_flag = 0;
+    tc_engine_init(eng, g.stages);
     *cmd_exit = 0;
   }
   if (warp == kMmaWarp) tc::tmem_alloc(smem_u32(tmem_slot), tc::kTmemCols);
@@ -864,9 +893,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
     tl.group = warp >> 2;
     tl.lane = tid & 127;
     tl.taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    tl.bar_a = smem_u32(eng.bar_a);
-    tl.bar_d = eng.bar_d;
-    tl.phase_d = 0;
+    tc_lane_attach(tl, eng);
     tl.sp = sp;
     tl.xin = reinterpret_cast<float*>(smem_raw + lay.off_xin);
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
@@ -1030,8 +1057,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
       owners_sync();
       if (G > 1) lanes_sync<G>();
     }
-    __syncwarp();
-    if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
+    tc_release_engines(tl);
   }
 
   tc::fence_before_sync();

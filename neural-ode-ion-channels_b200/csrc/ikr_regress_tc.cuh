@@ -48,20 +48,10 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_regress_tc_kernel(const 
   volatile long long* stash_slot = reinterpret_cast<volatile long long*>(smem_raw + lay.off_misc + 16);
   volatile int* cmd_exit = reinterpret_cast<volatile int*>(smem_raw + lay.off_misc + 24);
   float* sp = reinterpret_cast<float*>(smem_raw + lay.off_sp);
-  TcEngineCtx eng;
-  eng.bar_full = bars; eng.bar_empty = bars + kTcMaxStages;
-  eng.bar_a = bars + 2 * kTcMaxStages; eng.bar_d = eng.bar_a + 1;
-  eng.stop_flag = stop_flag; eng.ring = smem_raw + lay.off_ring;
+  const TcEngineCtx eng = tc_engine_ctx(bars, stop_flag, smem_raw + lay.off_ring);
 
   if (tid == 0) {
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&eng.bar_full[s], 1);
-      mbar_init(&eng.bar_empty[s], 1);
-    }
-    mbar_init(eng.bar_a, kLaneThreads / 32);
-    mbar_init(eng.bar_d, 1);
-    mbar_fence_init();
-    *stop_flag = 0;
+    tc_engine_init(eng, g.stages);
     *cmd_exit = 0;
   }
   if (warp == kMmaWarp) tc::tmem_alloc(smem_u32(tmem_slot), tc::kTmemCols);
@@ -93,9 +83,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_regress_tc_kernel(const 
     tl.group = warp >> 2;
     tl.lane = tid & 127;
     tl.taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    tl.bar_a = smem_u32(eng.bar_a);
-    tl.bar_d = eng.bar_d;
-    tl.phase_d = 0;
+    tc_lane_attach(tl, eng);
     tl.sp = sp;
     tl.xin = reinterpret_cast<float*>(smem_raw + lay.off_xin);
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
@@ -156,8 +144,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_regress_tc_kernel(const 
       owners_sync();
       if (G > 1) lanes_sync<G>();
     }
-    __syncwarp();
-    if ((tl.lane & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tl.bar_a) : "memory");
+    tc_release_engines(tl);
   }
 
   tc::fence_before_sync();
