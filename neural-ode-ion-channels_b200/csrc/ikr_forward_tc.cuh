@@ -12,19 +12,22 @@
 //                lane threads: tcgen05.ld the D row, + bias, LeakyReLU      -> A operand (TMEM)
 //   output       lane threads: dot(h, w_last) while reading the last D row, owner adds b_last
 // G threads share one TMEM lane (column groups, warps w and w + 4 c see the same lane quarter):
-// they split the k-steps of every epilogue; the owner broadcasts (nv, a) and collects the G partial
-// output sums through shared memory.
+// group c produces the 32-feature UNITS u = c (mod G) of every layer; the owner broadcasts (nv, a)
+// and collects the G partial output sums through shared memory.
 //
 // FP32 accuracy on BF16 tensor cores: every fp32 value x is split into three bf16 terms
-// x = x1 + x2 + x3 (exact to 2^-24 |x|), and each layer issues the six products whose weight is
-// >= 2^-16: a1 b1, a2 b1, a3 b1, a1 b2, a2 b2, a1 b3 (dropped terms <= 2^-24 relative), all
-// accumulated in fp32 in TMEM.  Measured on B200 (tests/tc_probe.cu): one 128 x 208 x 16 MMA
-// = 104 cycles, i.e. 75 MMAs = 7.8 k cycles per layer against ~200 k cycles of FFMA2 work.
+// x = x1 + x2 + x3 (exact), and each layer issues the six products whose weight is >= 2^-16:
+// a1 b1, a2 b1, a3 b1, a1 b2, a2 b2, a1 b3 (dropped terms <= 2^-24 relative), all accumulated in
+// fp32 in TMEM.  Measured on B200 (tests/tc_probe.cu): one 128 x 208 x 16 MMA = 104 cycles, i.e.
+// 75 MMAs = 7.8 k cycles per layer against ~200 k cycles of FFMA2 work.
 //
-// TMEM budget (512 columns): D uses NP = roundup(n, 16) columns; each bf16 term of A uses n / 2
-// columns.  For n = 200 (every shipped model): 208 + 3 x 96 (k < 192) + 16 (tail) = 512.  The last
-// n % 16 <= 8 input features form a TAIL step: two A blocks [a1t | a2t], [a1t | a3t] against B
-// blocks [b1t | b1t], [b2t | b2t], [b3t | b1t] give the same six products in 3 MMAs.
+// TMEM budget (512 columns), n = 200: TWO accumulators D (2 x 208 columns: the MMAs of layer l + 1
+// write the one the epilogue of layer l is not reading) + a ring of TWO A-operand unit slots (2 x 48
+// columns: [a1 16 | a2 16 | a3 16] = two K = 16 steps) = 512.  The activations never sit in TMEM as
+// a whole: the epilogue of layer l hands them to the MMA warp unit by unit, and the MMAs of layer
+// l + 1 start after the first unit.  The last n % 16 <= 8 input features form a TAIL unit: two A
+// blocks [a1t | a2t], [a1t | a3t] against B blocks [b1t | b1t], [b2t | b2t], [b3t | b1t] give the
+// same six products in 3 MMAs.
 #ifndef IKR_FORWARD_TC_CUH_
 #define IKR_FORWARD_TC_CUH_
 
