@@ -377,9 +377,9 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
   // ---- backward: D = dz_l W_l  ->  dz_{l-1} = D * leaky'(H_{l-1}) ---------------------------------------
   for (int l = g.L; l >= 1; --l) {
     { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
-    const uint32_t dcol = tc_wait_d(g, tl);
-    { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
     const bool first = l == 1;
+    const uint32_t dcol = tc_wait_d(g, tl, !first);
+    { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
     for (int u = tl.group; u < UT; u += G) {
       const unsigned gi = tl.unit_idx + (unsigned)u;
       const int w = (u - tl.group) / G;

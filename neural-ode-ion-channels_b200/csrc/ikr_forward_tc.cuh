@@ -345,7 +345,7 @@ struct TcNoHook {
   __device__ __forceinline__ void operator()() const {}
 };
 // wait for the D of the next layer pass; returns its TMEM column (the two D buffers alternate)
-__device__ __forceinline__ uint32_t tc_wait_d(const TcGeom& g, TcLane& tl) {
+__device__ __forceinline__ uint32_t tc_wait_d(const TcGeom& g, TcLane& tl, bool stagger = true) {
 #ifdef IKR_TC_BACKOFF
   mbar_wait_backoff(tl.bar_d, tl.phase_d, IKR_TC_BACKOFF);
 #else
@@ -358,7 +358,7 @@ __device__ __forceinline__ uint32_t tc_wait_d(const TcGeom& g, TcLane& tl) {
   // Stagger the column groups: the MMAs of the next layer start with unit 0 (group 0), and a pass of
   // MMAs (~7.6 k cycles) is several times longer than a whole epilogue, so the later groups give the
   // first ones the issue slots (unit 0 lands in ~0.4 k instead of ~1.1 k cycles after d_ready).
-  if (tl.group > 0) __nanosleep(kTcStaggerNs * (unsigned)tl.group);
+  if (stagger && tl.group > 0) __nanosleep(kTcStaggerNs * (unsigned)tl.group);
   return col;
 }
 
@@ -406,7 +406,7 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
   for (int layer = 0; layer < g.L; ++layer) {
     const float* bias = tl.sp + (size_t)(3 + layer) * NP;
     const bool last = layer + 1 == g.L;
-    const uint32_t dcol = tc_wait_d(g, tl);
+    const uint32_t dcol = tc_wait_d(g, tl, !last);   // the output layer produces no units: no stagger
     { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
     for (int u = tl.group; u < UT; u += G) {
       const unsigned gi = tl.unit_idx + (unsigned)u;
@@ -512,7 +512,7 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
   const uint32_t blk16 = (uint32_t)g.block_bytes >> 4, stage16 = (uint32_t)g.stage_bytes >> 4;
   const int UT = g.units + g.tail;
   unsigned s = 0, round = 0, consumed = 0, gi = 0, pass = 0;
-  long long e_wait = 0, e_issue = 0, ec = clock64();
+  long long e_wait = 0, e_wait0 = 0, e_issue = 0, ec = clock64();
   bool stop = false;
   while (!stop) {
     const uint32_t dcol = tbase + ((pass & 1u) ? (uint32_t)g.NP : 0u);
@@ -523,7 +523,7 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
       mbar_wait(&c.unit_ready[u], pass & 1u);
       if (*c.stop_flag) { stop = true; break; }
       tc::fence_after_sync();
-      { const long long c1 = clock64(); e_wait += c1 - ec; ec = c1; }
+      { const long long c1 = clock64(); e_wait += c1 - ec; if (u == 0) e_wait0 += c1 - ec; ec = c1; }
       const uint32_t a_slot = tbase + (uint32_t)g.col_ring + 48u * slot;
       const bool is_tail = u >= g.units;
       const int nk = is_tail ? 1 : ((2 * u + 1 < g.KSf) ? 2 : 1);
@@ -568,7 +568,8 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
   if (tc::elect_one()) {
     mbar_arrive(&c.bar_empty[s]);
     if (timing)
-      printf("[tc timing] mma warp: wait_units %lld issue %lld cycles, %u k-steps\n", e_wait, e_issue, consumed);
+      printf("[tc timing] mma warp: wait_units %lld (first unit of a pass: %lld) issue %lld cycles, %u k-steps, %u passes\n",
+             e_wait, e_wait0, e_issue, consumed, pass);
   }
   __syncwarp();
 }
