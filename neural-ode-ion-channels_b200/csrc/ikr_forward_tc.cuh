@@ -220,8 +220,10 @@ __device__ __forceinline__ uint32_t tc_unit_slot_col(const TcGeom& g, unsigned g
   return (uint32_t)g.col_ring + 48u * (gi & 1u);
 }
 __device__ __forceinline__ void tc_unit_acquire(const TcGeom& g, const TcLane& tl, unsigned gi) {
-  if (gi >= 2u) {
-    const unsigned UT = (unsigned)(g.units + g.tail);
+  const unsigned UT = (unsigned)(g.units + g.tail);
+  // UT == 1: unit gi - 2 belongs to a pass whose D this thread has already consumed (all done), and a
+  // parity wait two phases behind the barrier would alias
+  if (gi >= 2u && UT >= 2u) {
     const unsigned prev = gi - 2u;
     mbar_wait(&tl.unit_done[prev % UT], (prev / UT) & 1u);
     tc::fence_after_sync();

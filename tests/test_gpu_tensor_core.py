@@ -85,7 +85,8 @@ def test_tc_logged_loss_and_narrow_architectures():
     t_tab, v_tab = protocols.ap2hz()
     t = torch.linspace(0., 60., 61)
     y0 = torch.tensor([[0.01, 0.97]] * 3, dtype=torch.float32).cuda()
-    for n, L in ((100, 5), (72, 2), (64, 1), (48, 3), (90, 2), (200, 1)):
+    # 32 / 16: a single unit per layer pass
+    for n, L in ((100, 5), (72, 2), (64, 1), (48, 3), (90, 2), (200, 1), (32, 2), (16, 1), (24, 3)):
         torch.manual_seed(n)
         f = ikr.ODEFuncNNf(arch=(L, n))
         f.set_fixed_form_voltage_protocol(t_tab, v_tab)
