@@ -493,6 +493,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
     tl.slope = (float)p.mlp.slope;
     tl.c_l0 = tl.c_wait = tl.c_epi = 0;
+    tl.c_sync_a = tl.c_sync_b = tl.c_last = 0;
     const long long c_begin = clock64();
     TcAdjLane al;
     al.samp = tc_stash_sample(tl.lane, sg.NGb);

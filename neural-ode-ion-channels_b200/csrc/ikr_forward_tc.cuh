@@ -197,6 +197,7 @@ struct TcLane {
   float* part;           // [G][128] partial output sums
   float slope;
   long long c_l0, c_wait, c_epi;   // phase clocks (timing runs)
+  long long c_sync_a, c_sync_b, c_last;   // owner: barrier A / barrier B waits, output-layer epilogue
 #ifdef IKR_TC_TRACE
   int trace_eval;
 #endif
@@ -432,7 +433,7 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
       }
     }
     if (!last) tl.unit_idx += (unsigned)UT;
-    { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
+    { const long long c1 = clock64(); tl.c_epi += c1 - c0; if (last) tl.c_last += c1 - c0; c0 = c1; }
   }
 #ifdef IKR_TC_TRACE
   ++tl.trace_eval;
@@ -445,9 +446,13 @@ template <int G, typename Hook = TcNoHook>
 __device__ __forceinline__ float tc_owner_eval(const TcGeom& g, TcLane& tl, float nv, float a,
                                                Hook hook = Hook()) {
   *reinterpret_cast<float2*>(tl.xin + 2 * tl.lane) = make_float2(nv, a);
+  long long t0 = clock64();
   if (G > 1) lanes_sync<G>();        // inputs visible to the helper groups (cmd word = run)
+  { const long long t1 = clock64(); tl.c_sync_a += t1 - t0; }
   tc_mlp_eval<G, Hook>(g, tl, hook);
+  t0 = clock64();
   if (G > 1) lanes_sync<G>();        // partial sums visible
+  { const long long t1 = clock64(); tl.c_sync_b += t1 - t0; }
   float out = tl.part[tl.lane];
 #pragma unroll
   for (int c = 1; c < G; ++c) out += tl.part[c * kTcM + tl.lane];
@@ -514,7 +519,7 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
   const uint32_t blk16 = (uint32_t)g.block_bytes >> 4, stage16 = (uint32_t)g.stage_bytes >> 4;
   const int UT = g.units + g.tail;
   unsigned s = 0, round = 0, consumed = 0, gi = 0, pass = 0;
-  long long e_wait = 0, e_wait0 = 0, e_issue = 0, ec = clock64();
+  long long e_wait = 0, e_wait0 = 0, e_wait00 = 0, e_issue = 0, ec = clock64();
   bool stop = false;
   while (!stop) {
     const uint32_t dcol = tbase + ((pass & 1u) ? (uint32_t)g.NP : 0u);
@@ -525,7 +530,7 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
       mbar_wait(&c.unit_ready[u], pass & 1u);
       if (*c.stop_flag) { stop = true; break; }
       tc::fence_after_sync();
-      { const long long c1 = clock64(); e_wait += c1 - ec; if (u == 0) e_wait0 += c1 - ec; ec = c1; }
+      { const long long c1 = clock64(); e_wait += c1 - ec; if (u == 0) { e_wait0 += c1 - ec; if (pass % (unsigned)g.L == 0) e_wait00 += c1 - ec; } ec = c1; }
       const uint32_t a_slot = tbase + (uint32_t)g.col_ring + 48u * slot;
       const bool is_tail = u >= g.units;
       const int nk = is_tail ? 1 : ((2 * u + 1 < g.KSf) ? 2 : 1);
@@ -570,8 +575,9 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
   if (tc::elect_one()) {
     mbar_arrive(&c.bar_empty[s]);
     if (timing)
-      printf("[tc timing] mma warp: wait_units %lld (first unit of a pass: %lld) issue %lld cycles, %u k-steps, %u passes\n",
-             e_wait, e_wait0, e_issue, consumed, pass);
+      printf("[tc timing] mma warp: wait_units %lld (first unit of a pass: %lld, of which first pass of an "
+             "evaluation [forward kernels]: %lld) issue %lld cycles, %u k-steps, %u passes\n",
+             e_wait, e_wait0, e_wait00, e_issue, consumed, pass);
   }
   __syncwarp();
 }
@@ -657,6 +663,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
     tl.slope = (float)p.mlp.slope;
     tl.c_l0 = tl.c_wait = tl.c_epi = 0;
+    tl.c_sync_a = tl.c_sync_b = tl.c_last = 0;
 #ifdef IKR_TC_TRACE
     tl.trace_eval = 0;
 #endif
@@ -811,8 +818,10 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
       }
       if (tp.timing && blockIdx.x == 0 && tid == 0) {
         const long long tot = clock64() - c_begin;
-        printf("[tc timing] owner 0: total %lld cycles: layer0 %lld, wait_d %lld, epilogue %lld, solver+other %lld\n",
-               tot, tl.c_l0, tl.c_wait, tl.c_epi, tot - tl.c_l0 - tl.c_wait - tl.c_epi);
+        printf("[tc timing] owner 0: total %lld cycles: layer0 %lld, wait_d %lld, epilogue %lld (output layer %lld), "
+               "barrier A %lld, barrier B %lld, solver %lld\n",
+               tot, tl.c_l0, tl.c_wait, tl.c_epi, tl.c_last, tl.c_sync_a, tl.c_sync_b,
+               tot - tl.c_l0 - tl.c_wait - tl.c_epi - tl.c_sync_a - tl.c_sync_b);
       }
       // release the helper groups and the engine warps
       if (tid == 0) { *cmd_exit = 1; *stop_flag = 1; }
@@ -905,6 +914,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
     tl.slope = (float)p.mlp.slope;
     tl.c_l0 = tl.c_wait = tl.c_epi = 0;
+    tl.c_sync_a = tl.c_sync_b = tl.c_last = 0;
 #ifdef IKR_TC_TRACE
     tl.trace_eval = 0;
 #endif

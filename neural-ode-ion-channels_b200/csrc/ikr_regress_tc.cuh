@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_regress_tc_kernel(const 
     tl.part = reinterpret_cast<float*>(smem_raw + lay.off_part);
     tl.slope = (float)tp.mlp.slope;
     tl.c_l0 = tl.c_wait = tl.c_epi = 0;
+    tl.c_sync_a = tl.c_sync_b = tl.c_last = 0;
 #ifdef IKR_TC_TRACE
     tl.trace_eval = 0;
 #endif
