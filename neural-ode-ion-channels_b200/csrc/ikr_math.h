@@ -468,13 +468,14 @@ IKR_HD void rhs_finish(const Lane<S>& L, const SolverCfg& c, double net_out, dou
 // Same expressions as hh_drdt / hh_rate_pair (in-table branch) => bit-identical results; anything
 // else (time mismatch, out-of-table fallback) takes the uncached path.
 struct TimeCache {
-  double t, v, k1, k2, k3, k4;
+  double t, v, nv, k1, k2, k3, k4;
   int valid, in_table;
 };
 IKR_HD void time_cache_fill(TimeCache& tcx, const SolverCfg& c, double t_eval) {
   tcx.t = t_eval;
   tcx.in_table = table_voltage(c.tab, t_eval, &tcx.v) ? 1 : 0;
   if (tcx.in_table) {
+    tcx.nv = mlp_input_nv(tcx.v, true, c.vrange, c.mlp_is_f64 != 0);
     tcx.k3 = c.hp.p[4] * exp(c.hp.p[5] * tcx.v);
     tcx.k4 = c.hp.p[6] * exp(-c.hp.p[7] * tcx.v);
     if (c.nn_d) {
@@ -499,7 +500,7 @@ IKR_HD void rhs_prepare_cached(Lane<S>& L, const SolverCfg& c, double t_eval, SS
   } else {
     L.hh_a = 0.0;
   }
-  *nv = mlp_input_nv(tcx.v, true, c.vrange, c.mlp_is_f64 != 0);
+  *nv = tcx.nv;
   *a_in = (double)a;
 }
 
@@ -853,7 +854,7 @@ IKR_HD void bdp_stage_inputs_cached(BLane<S>& B, const SolverCfg& c, int s, doub
   S Ya = dp_stage_state<S>(s, B.ya, B.ka, B.dt);
   B.jr = (S)(-(tcx.k3 + tcx.k4));
   B.ja = c.nn_d ? (S)(-(tcx.k1 + tcx.k2)) : (S)0;
-  *nv = mlp_input_nv(tcx.v, true, c.vrange, c.mlp_is_f64 != 0);
+  *nv = tcx.nv;
   *a_in = (double)Ya;
   *up = adj_mlp_upstream((double)B.lka[s + 1], c);
 }
