@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libikr_b200.so')
+# IKR_B200_LIB: another build of the same library (A/B runs of kernel variants on one GPU box)
+LIB_PATH = os.environ.get('IKR_B200_LIB') or os.path.join(_HERE, 'csrc', 'libikr_b200.so')
 
 F32, F64 = 0, 1
 DOPRI5, RK4 = 0, 1

@@ -26,22 +26,28 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: a variant build next to the shipped library (A/B runs select it with
+    IKR_B200_LIB); the default call builds libikr_b200.so."""
+    if out is None and not force and not needs_build():
         return OUT
+    out = out or OUT
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(HERE, s) for s in SOURCES] + ['-o', OUT]
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + [os.path.join(HERE, s) for s in SOURCES] + ['-o', out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
-    with open(os.path.join(HERE, 'build.log'), 'w') as fh:
+    with open(os.path.join(HERE, 'build.log') if out == OUT else out + '.build.log', 'w') as fh:
         fh.write(' '.join(cmd) + '\n' + log)
     if verbose or res.returncode != 0:
         sys.stderr.write(log)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed building libikr_b200.so (see csrc/build.log)')
-    return OUT
+    return out
 
 
 if __name__ == '__main__':
-    build(force=True, verbose=True)
-    print(OUT)
+    # python build.py [variant.so -DNAME=VALUE ...]
+    if len(sys.argv) > 1:
+        print(build(force=True, out=os.path.abspath(sys.argv[1]), defines=sys.argv[2:]))
+    else:
+        print(build(force=True, verbose=True))

@@ -215,7 +215,10 @@ __device__ __forceinline__ float tc_leaky(float x, float slope) { return x > 0.0
 // arrival per warp); the MMA warp issues the unit's K-steps as soon as it lands and commits
 // unit_done.  So the MMAs of layer l + 1 start after the FIRST unit of the epilogue of layer l and
 // run under the rest of it, accumulating into the other D buffer.
-constexpr unsigned kTcStaggerNs = 200;   // start delay per column group after d_ready
+#ifndef IKR_TC_STAGGER_NS
+#define IKR_TC_STAGGER_NS 200
+#endif
+constexpr unsigned kTcStaggerNs = IKR_TC_STAGGER_NS;   // start delay per column group after d_ready
 constexpr int kTcMaxUnits = 8;     // NP <= 208: at most 7 units of two K-steps + the tail
 __device__ __forceinline__ uint32_t tc_unit_slot_col(const TcGeom& g, unsigned gi) {
   return (uint32_t)g.col_ring + 48u * (gi & 1u);
