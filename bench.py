@@ -69,9 +69,11 @@ def forward_roofline(achieved_tflops, fma_peak_tflops, tensor_cores):
     return {
         'bound': 'tensor', 'achieved': achieved_tflops, 'peak': mp['bf16_sustained'], 'unit': 'TFLOP/s',
         'frac': achieved_tflops / mp['bf16_sustained'],
-        # dram__bytes_read + write of one ikr_forward_tc_kernel launch (ncu --set full,
-        # profiles/r1_forward_tc_summary.md): weight image + tables; the kernel writes nothing to DRAM
-        'traffic': 1.64e6, 'flop_per_eval': FLOP_PER_EVAL,
+        # dram__bytes_read + write of one ikr_forward_tc_pool_kernel launch of this bench step (ncu
+        # --set full, profiles/r1_fwd_tc_pool_ncu_raw.csv: 53.4 MB read + 86.8 MB written in 1.16 s:
+        # data traces, per-trajectory results, L2 write-backs); the tile kernel on 18,944
+        # trajectories moves 1.68 MB (weight image + tables) and writes nothing
+        'traffic': 1.403e8, 'flop_per_eval': FLOP_PER_EVAL,
         'peak_source': 'dense bf16 tensor peak, sustained figure of %s (kernel timed inside a long '
                        'step)' % mp['source'],
         'executed_bf16_tflops': executed, 'frac_executed': executed / mp['bf16_sustained'],
