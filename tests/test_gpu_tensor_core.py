@@ -143,6 +143,38 @@ def test_tc_backward_matches_ffma_backward(study, B):
     assert abs(a[2] - b[2]) <= 1e-4 * abs(b[2])
 
 
+@pytest.mark.parametrize('arch', [(2, 72), (3, 100), (1, 200), (7, 200), (1, 64)])
+def test_tc_backward_other_architectures(arch):
+    """Widths / depths other than s00 through the tensor-core training step (n % 16 in 1..8: the
+    constant-1 bias column rides in the tail group; (1, 64) has no tail and must take the FFMA2
+    backward on its own): gradient blocks agree with the FFMA2 step at the same 1e-2 of the block
+    maximum as above."""
+    L, n = arch
+    torch.manual_seed(100 * L + n)
+    func = ikr.ODEFuncNNf(arch=(L, n)).cuda()
+    t_tab, v_tab = protocols.ap2hz()
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 60., 31)
+    rng = np.random.RandomState(L + n)
+    B = 40
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1),
+                      dtype=torch.float32).cuda()
+    data = torch.from_numpy((rng.randn(len(t), B) * 0.1).astype(np.float32))
+    out = {}
+    with torch.enable_grad():
+        for tcore in (True, False):
+            total, per, grads, res = ikr.loss_and_grad(
+                func, y0, t, data, want_y0=True, options={'tensor_cores': tcore, 'first_step': 0.05})
+            out[tcore] = (_flat(grads), res.grad_y0.cpu().double().numpy(), float(total))
+    a, b = out[True], out[False]
+    assert np.isfinite(a[0]).all() and np.abs(a[0]).max() > 0
+    for name, lo, hi in _segments(n, L):
+        ref = np.abs(b[0][lo:hi]).max()
+        assert np.abs(a[0][lo:hi] - b[0][lo:hi]).max() <= 1e-2 * ref, (arch, name, ref)
+    assert np.abs(a[1] - b[1]).max() <= 1e-2 * np.abs(b[1]).max()
+    assert abs(a[2] - b[2]) <= 1e-4 * abs(b[2])
+
+
 def test_tc_backward_round_and_shard_invariance():
     """One reversed step per round (small workspace) versus the default round size, and the sum of
     two batch shards versus the whole batch: same gradient up to fp32 summation order."""
