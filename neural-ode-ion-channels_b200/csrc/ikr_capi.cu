@@ -217,13 +217,9 @@ struct TcPlan {
   size_t smem, img_bytes;
 };
 
-// Column groups: 3 by default; the tile-scheduled forward kernel runs 3-5 % faster with 2 (fewer
-// warps share the schedulers while the first unit of a layer pass is produced), every other kernel
-// is indifferent or 1 % better with 3 (same-box A/B runs, profiles/r1_forward_tc_summary.md).
 constexpr int kTcDefaultGroups = 3;
-constexpr int kTcForwardTileGroups = 2;
 
-TcPlan make_tc_plan(const ikr_desc* d, int default_groups = kTcDefaultGroups) {
+TcPlan make_tc_plan(const ikr_desc* d) {
   TcPlan t;
   t.ok = false;
   t.smem = 0; t.img_bytes = 0;
@@ -231,7 +227,7 @@ TcPlan make_tc_plan(const ikr_desc* d, int default_groups = kTcDefaultGroups) {
   if (d->mlp_dtype != IKR_F32 || (d->reserved & 2) || d->tile_m > 0) return t;
   if (!(d->negative_slope >= 0.0 && d->negative_slope <= 1.0)) return t;   // epilogues use max(z, slope z)
   if (!tc_geometry_ok(t.g)) return t;
-  t.groups = default_groups;
+  t.groups = kTcDefaultGroups;
   if (const char* e = getenv("IKR_TC_GROUPS")) {   // tuning / A-B runs
     const int v = atoi(e);
     if (v >= 1 && v <= 3) t.groups = v;
@@ -811,14 +807,13 @@ int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B) {
 int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[8]) {
   if (!valid_desc(d) || n_jobs < 1 || !B || !out) return IKR_ERR_ARG;
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
-  if (make_tc_plan(d).ok) {
+  const TcPlan tcp = make_tc_plan(d);
+  if (tcp.ok) {
     const int sms = device_sms();
     long long tiles = 0, b_total = 0;
     for (int j = 0; j < n_jobs; ++j) b_total += B[j];
     const int tl = tc_tile_lanes(b_total, sms);
-    const bool pool = use_pool_tc(d, b_total, sms);
-    const TcPlan tcp = make_tc_plan(d, pool ? kTcDefaultGroups : kTcForwardTileGroups);
-    if (pool) tiles = (b_total + tl - 1) / tl;
+    if (use_pool_tc(d, b_total, sms)) tiles = (b_total + tl - 1) / tl;
     else for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + tl - 1) / tl;
     out[0] = tl; out[1] = tc_threads(tcp.groups); out[2] = tiles < sms ? tiles : sms; out[3] = (int64_t)tcp.smem;
     out[4] = tiles; out[5] = 16; out[6] = tcp.g.KST; out[7] = sms;
@@ -858,10 +853,7 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
     if (io->T > 2147483647LL || io->G > 2147483647LL) return IKR_ERR_ARG;
     if (io->weights != jobs[0].weights) return IKR_ERR_ARG;
   }
-  long long b_all = 0;
-  for (int j = 0; j < n_jobs; ++j) b_all += jobs[j].B;
-  const TcPlan tcp = make_tc_plan(
-      d, use_pool_tc(d, b_all, device_sms()) ? kTcDefaultGroups : kTcForwardTileGroups);
+  const TcPlan tcp = make_tc_plan(d);
   const size_t need = fwd_fixed_workspace(n_jobs) + (tcp.ok ? tcp.img_bytes : 0);
   if (!workspace || workspace_bytes < need) return IKR_ERR_WORKSPACE;
 

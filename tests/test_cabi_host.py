@@ -97,9 +97,6 @@ def test_packed_layout_and_param_count(lib):
     geo = _cabi.launch_geometry(d, [13107] * 4 + [13108])
     assert lib.ikr_uses_tensor_cores(ctypes.byref(d)) == 1 and geo['tensor_cores']
     assert (geo['tile_m'], geo['threads']) == (128, 448)
-    # up to 1.5 waves of tiles the tile-scheduled kernel runs, with 2 x 128 lane threads
-    small = _cabi.launch_geometry(d, 4096)
-    assert (small['tile_m'], small['threads'], small['n_tiles']) == (128, 320, 32)
     # opting out (reserved bit 1) gives the FFMA2 kernel its 16-warp, 160-trajectory tile
     d.reserved = 2
     geo = _cabi.launch_geometry(d, [13107] * 4 + [13108])
