@@ -71,7 +71,7 @@ typedef struct ikr_desc {
   int32_t reserved;       /* bit 0: dopri5 on the lane-pool kernel (slots refill from a queue);
                              bit 1: keep an fp32 MLP on the FFMA2 kernel (no tensor cores);
                              bit 2: never use lane-pool scheduling (default: automatic on the
-                             tensor-core path for launches of more than ~1.5 waves of tiles)        */
+                             tensor-core path for launches with more tiles than SMs)                */
 } ikr_desc;
 
 /* One JOB = one protocol table + one batch of trajectories, i.e. the shape of one reference

@@ -254,13 +254,13 @@ TcPlan make_tc_plan(const ikr_desc* d) {
 int tc_tile_lanes(long long /*b_total*/, int /*sms*/) { return kTcM; }
 
 // Lane-pool scheduling of the tensor-core forward kernel.  desc.reserved bit 0 forces it, bit 2 forbids
-// it; otherwise it is used when the launch holds more than ~1.5 waves of 128-trajectory tiles
-// (measured on B200: +7 % at 65,536 x pr4, +2.4 % on the five-protocol bench mix, -3 % when every
-// SM gets exactly one tile).
+// it; otherwise it is used when the launch holds more 128-trajectory tiles than SMs (measured on
+// B200: +7 % at 65,536 x pr4, +2.4 % on the five-protocol bench mix, +5.7 / +4.2 / +2.9 % at 1.125 /
+// 1.25 / 1.5 waves of pr4, -3 % when every SM gets exactly one tile).
 bool use_pool_tc(const ikr_desc* d, long long b_total, int sms) {
   if (d->method != IKR_DOPRI5 || (d->reserved & 4)) return false;
   if (d->reserved & 1) return true;
-  return 2 * b_total > 3LL * kTcM * sms;
+  return b_total > (long long)kTcM * sms;   // more than one tile per SM
 }
 
 size_t fwd_fixed_workspace(int n_jobs) {

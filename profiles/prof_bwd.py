@@ -33,7 +33,8 @@ cap = int(os.environ.get('CKPT_CAP', '0')) or None
 for _ in range(2):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
-    opts = {'check_status': False, 'tensor_cores': not os.environ.get('NO_TC')}
+    opts = {'check_status': False, 'tensor_cores': not os.environ.get('NO_TC'),
+            'lane_pool': {'1': True, '0': False}.get(os.environ.get('POOL', ''), None)}
     if cap:
         opts['ckpt_cap'] = cap
     res = ikr.integrate(f, y0, t, data=data, want_y=True, want_ckpt=True, options=opts)
