@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IKR_ABI_VERSION 1
+#define IKR_ABI_VERSION 2
 
 /* dtype codes */
 #define IKR_F32 0
@@ -68,10 +68,16 @@ typedef struct ikr_desc {
   double safety, ifactor, dfactor; /* 0.9, 10, 0.2                                               */
   int64_t max_num_steps;  /* per output interval, torchdiffeq semantics                          */
   int32_t tile_m;         /* 0: library picks the trajectories-per-CTA tile                      */
-  int32_t reserved;       /* bit 0: dopri5 on the lane-pool kernel (slots refill from a queue);
+  int32_t reserved;       /* option bits (0 = library defaults; every knob lives HERE, the library
+                             reads no environment variable and keeps no state between calls):
+                             bit 0: dopri5 on the lane-pool kernel (slots refill from a queue);
                              bit 1: keep an fp32 MLP on the FFMA2 kernel (no tensor cores);
                              bit 2: never use lane-pool scheduling (default: automatic on the
-                             tensor-core path for launches with more tiles than SMs)                */
+                             tensor-core path for launches with more tiles than SMs);
+                             bit 3: debug, CTA 0 prints its phase clocks (device printf);
+                             bits 4-5: epilogue column groups of the tensor-core kernels, 1..3
+                             (0 = default 3; fixes the output-layer summation order, i.e. results);
+                             bit 6: never use the two-tile ping-pong kernel; bit 7: force it      */
 } ikr_desc;
 
 /* One JOB = one protocol table + one batch of trajectories, i.e. the shape of one reference
@@ -140,8 +146,13 @@ int ikr_packed_layout(const ikr_desc* d, int64_t out[8]);
 
 /* trajectories per CTA the library will use for jobs of the given batch sizes */
 int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B);
-/* out[8] = tile_m, threads/CTA, grid, dynamic smem bytes, n_tiles, kc, chunks/layer, SM count */
-int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[8]);
+/* What ikr_forward will launch for jobs of the given batch sizes (the library's own decision, so
+ * that callers report it instead of guessing):
+ * out[16] = tile_m, threads/CTA, grid, dynamic smem bytes, n_tiles, kc, chunks/layer (k-steps/layer
+ * on the tensor-core path), SM count, scheduling (0: tile queue, longest job first; 1: lane pool,
+ * slots refill from one trajectory queue; 2: two-tile ping-pong lane pool), kernel launches of
+ * one ikr_forward call, tensor-core path (0/1), epilogue column groups, rest reserved (0).          */
+int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[16]);
 
 /* 1 when ikr_forward will run this configuration on the tcgen05 tensor-core kernel (fp32 MLP with
  * n_nodes <= 200: hidden layers as bf16x3 split MMAs, fp32-faithful), 0 for the FFMA2 / DFMA kernel.

@@ -118,7 +118,7 @@ def lib():
     L.ikr_interp_protocol.argtypes = [ctypes.POINTER(IkrIO), c_vp, c_i64, c_vp, c_vp]
     L.ikr_fma_peak.restype = c_i32
     L.ikr_fma_peak.argtypes = [c_i32, c_i64, ctypes.POINTER(c_f64), c_vp]
-    if L.ikr_abi_version() != 1:
+    if L.ikr_abi_version() != 2:
         raise RuntimeError('libikr_b200.so ABI version mismatch')
     _lib = L
     return L
@@ -144,10 +144,12 @@ def packed_layout(desc):
 
 
 def launch_geometry(desc, B):
-    out = (c_i64 * 8)()
+    out = (c_i64 * 16)()
     Bs = [int(B)] if not isinstance(B, (list, tuple)) else [int(b) for b in B]
     arr = (c_i64 * len(Bs))(*Bs)
     check(lib().ikr_launch_geometry(ctypes.byref(desc), len(Bs), arr, out), 'ikr_launch_geometry')
     return {'tile_m': out[0], 'threads': out[1], 'grid': out[2], 'smem': out[3],
             'n_tiles': out[4], 'kc': out[5], 'cpl': out[6], 'sms': out[7],
-            'tensor_cores': bool(lib().ikr_uses_tensor_cores(ctypes.byref(desc)) == 1)}
+            'scheduling': ('tile queue (longest job first)', 'lane pool (slots refill from one '
+                           'trajectory queue)', 'two-tile ping-pong lane pool')[out[8]],
+            'launches': out[9], 'tensor_cores': bool(out[10]), 'column_groups': out[11]}

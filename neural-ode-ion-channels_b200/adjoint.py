@@ -44,7 +44,8 @@ def _run_backward(func, res, *, grad_y=None, fused_loss=0, want_y0=True, want_g=
             bio.grad_y = gy.data_ptr()
             keep.append(gy)
         bio.fused_loss = fused_loss
-        bio.max_accepted_steps = int(res.stats[:, 0].max().item())
+        known = getattr(res, 'max_accepted', None)
+        bio.max_accepted_steps = int(res.stats[:, 0].max().item()) if known is None else known
         bio.grad_weights = grad_flat.data_ptr()
         bio.grad_y0 = grad_y0.data_ptr() if want_y0 else None
         bio.grad_g = grad_g.data_ptr() if want_g else None
@@ -58,29 +59,79 @@ def _run_backward(func, res, *, grad_y=None, fused_loss=0, want_y0=True, want_g=
     return grad_flat, grad_y0, grad_g
 
 
+def _ckpt_cap_default(B, T, state_dtype, dev):
+    """First guess of the per-trajectory step-checkpoint capacity: 4,096 accepted steps unless that
+    would take more than a quarter of the free device memory (80 B / step / trajectory in fp32)."""
+    per_step = B * (16 * (4 if state_dtype == torch.float32 else 8) + 16)
+    free, _ = torch.cuda.mem_get_info(dev)
+    cap = int(min(4096, max(256, (free // 4) // max(per_step, 1))))
+    return cap
+
+
+def _forward_with_ckpt(func, y0, t, kwargs, **extra):
+    """Forward with step checkpoints; a run that overflows the checkpoint capacity (status 4) is
+    repeated with the capacity doubled (the caller did not have to guess it)."""
+    kw = dict(kwargs)
+    opts = dict(kw.pop('options', None) or {})
+    method = kw.get('method') or 'dopri5'
+    user_cap = int(opts.get('ckpt_cap', 0) or 0)
+    user_check = opts.get('check_status', True)
+    dev = _resolve_device(y0, kw.get('device'))
+    cap = user_cap or (0 if method == 'rk4' else
+                       _ckpt_cap_default(y0.shape[0], len(t), y0.dtype, dev))
+    while True:
+        res = integrate(func, y0, t, want_ckpt=True,
+                        options=dict(opts, ckpt_cap=cap, check_status=False), **kw, **extra)
+        # ONE host read per training forward: checkpoint overflow flag + the longest step count
+        # (the backward pass sizes its round loop with it)
+        summary = torch.stack([(res.stats[:, 3] == 4).any().long(),
+                               res.stats[:, 0].max().long()]).tolist()
+        res.max_accepted = int(summary[1])
+        if not summary[0] or user_cap or method == 'rk4':
+            break
+        del res
+        cap *= 2
+    if user_check:
+        from .solver import _raise_on_status
+        _raise_on_status(res.stats)
+    return res
+
+
+class _Saved:
+    """What the backward pass needs of a forward result -- everything except the output tensor
+    (keeping ``res.y`` on the autograd context would tie output -> grad_fn -> ctx -> output)."""
+
+    def __init__(self, res):
+        self.stats, self.ckpt, self.geometry = res.stats, res.ckpt, res.geometry
+        self.max_accepted = getattr(res, 'max_accepted', None)
+        self._desc, self._io, self._keep = res._desc, res._io, res._keep
+
+
 class _OdeintFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, func, y0, t, kwargs, *params):
-        res = integrate(func, y0, t, want_ckpt=True, **kwargs)
-        ctx.res = res
+        res = _forward_with_ckpt(func, y0, t, kwargs)
+        ctx.saved = _Saved(res)
         ctx.func = func
         ctx.y0_requires_grad = y0.requires_grad
         return res.y
 
     @staticmethod
     def backward(ctx, grad_y):
-        res = ctx.res
+        saved = ctx.saved
+        if saved is None:
+            raise RuntimeError('odeint: backward through the same integration a second time; the '
+                               'step checkpoints were freed after the first pass')
         spec = describe(ctx.func)
-        flat, grad_y0, _ = _run_backward(ctx.func, res, grad_y=grad_y, fused_loss=0,
+        flat, grad_y0, _ = _run_backward(ctx.func, saved, grad_y=grad_y, fused_loss=0,
                                          want_y0=ctx.y0_requires_grad)
+        ctx.saved = None          # frees the step checkpoints (cap * B * 80 bytes in fp32)
         plist = [q for m in spec.linears for q in (m.weight, m.bias)]
         grads = [g.to(device=q.device, dtype=q.dtype) for g, q in zip(unpack_grads(spec, flat), plist)]
         return (None, grad_y0 if ctx.y0_requires_grad else None, None, None) + tuple(grads)
 
 
 def odeint_with_grad(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None):
-    if (method or 'dopri5') != 'dopri5':
-        raise NotImplementedError('odeint: gradients are implemented for method="dopri5"')
     dev = _resolve_device(y0, None)
     kwargs = dict(rtol=rtol, atol=atol, method=method, options=options, device=dev)
     spec = describe(func)
@@ -89,7 +140,7 @@ def odeint_with_grad(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=
 
 
 def loss_and_grad(func, y0, t, data, *, g=None, E=-86.0, loss='sse', rtol=1e-7, atol=1e-9,
-                  options=None, want_y0=False, want_g=False, accumulate=False, device=None,
+                  method=None, options=None, want_y0=False, want_g=False, accumulate=False, device=None,
                   workspace_bytes=None):
     """Fused training step of the hot path: integrate B trajectories with dopri5, form
     ``I = g a r (V - E)``, reduce ``loss`` ('sse': sum (I - data)^2, the
@@ -102,8 +153,9 @@ def loss_and_grad(func, y0, t, data, *, g=None, E=-86.0, loss='sse', rtol=1e-7, 
     gradients are also added into ``p.grad`` of the module's parameters."""
     if loss not in _LOSSES:
         raise ValueError("loss must be 'sse' or 'sae'")
-    res = integrate(func, y0, t, rtol=rtol, atol=atol, method='dopri5', options=options, g=g, E=E,
-                    data=data, want_y=True, want_current=False, want_ckpt=True, device=device)
+    res = _forward_with_ckpt(func, y0, t, dict(rtol=rtol, atol=atol, method=method, options=options,
+                                               device=device),
+                             g=g, E=E, data=data, want_y=True, want_current=False)
     per_traj = res.sse if loss == 'sse' else res.sae
     flat, grad_y0, grad_g = _run_backward(func, res, fused_loss=_LOSSES[loss], want_y0=want_y0,
                                           want_g=want_g, workspace_bytes=workspace_bytes)

@@ -15,6 +15,9 @@ NVCC_FLAGS = [
     '-fmad=false',          # solver arithmetic must not be contracted (torchdiffeq semantics);
                             # the MLP inner loops use explicit fma intrinsics
     '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v', '--expt-relaxed-constexpr',
+    # link the CUDA runtime dynamically: the process already holds libcudart.so.12 (torch's), and the
+    # shipped binary then carries none of the runtime's unused entry-point names
+    '-cudart', 'shared', '-Xlinker', '-rpath,/usr/local/cuda/lib64',
 ]
 
 

@@ -4,7 +4,6 @@
 
 #include <algorithm>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -228,8 +227,10 @@ TcPlan make_tc_plan(const ikr_desc* d) {
   if (!(d->negative_slope >= 0.0 && d->negative_slope <= 1.0)) return t;   // epilogues use max(z, slope z)
   if (!tc_geometry_ok(t.g)) return t;
   t.groups = kTcDefaultGroups;
-  if (const char* e = getenv("IKR_TC_GROUPS")) {   // tuning / A-B runs
-    const int v = atoi(e);
+  {
+    // desc.reserved bits 4-5: column-group override for tuning / A-B runs (0 = library default).
+    // NOTE: the group count fixes the summation order of the output layer, i.e. results.
+    const int v = (d->reserved >> 4) & 3;
     if (v >= 1 && v <= 3) t.groups = v;
   }
   // every column group must produce at least one unit per layer pass (it then consumes every phase
@@ -575,7 +576,7 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
   tp.img = ws + pl.off_img;
   tp.stash = ws + off_stash;
   tp.mask_words = pl.mask_words;
-  tp.timing = getenv("IKR_TC_TIMING") != nullptr;
+  tp.timing = (d->reserved & 8) ? 1 : 0;
 
   TcWgradParams wp;
   wp.g = pl.g; wp.sg = pl.sg;
@@ -804,24 +805,35 @@ int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B) {
   return make_geometry(d, n_jobs, (const long long*)B, use_pool(d)).M;
 }
 
-int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[8]) {
+int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[16]) {
   if (!valid_desc(d) || n_jobs < 1 || !B || !out) return IKR_ERR_ARG;
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
+  for (int i = 0; i < 16; ++i) out[i] = 0;
   const TcPlan tcp = make_tc_plan(d);
   if (tcp.ok) {
     const int sms = device_sms();
     long long tiles = 0, b_total = 0;
     for (int j = 0; j < n_jobs; ++j) b_total += B[j];
     const int tl = tc_tile_lanes(b_total, sms);
-    if (use_pool_tc(d, b_total, sms)) tiles = (b_total + tl - 1) / tl;
+    const bool pool = use_pool_tc(d, b_total, sms);
+    if (pool) tiles = (b_total + tl - 1) / tl;
     else for (int j = 0; j < n_jobs; ++j) tiles += (B[j] + tl - 1) / tl;
     out[0] = tl; out[1] = tc_threads(tcp.groups); out[2] = tiles < sms ? tiles : sms; out[3] = (int64_t)tcp.smem;
     out[4] = tiles; out[5] = 16; out[6] = tcp.g.KST; out[7] = sms;
+    out[8] = pool ? 1 : 0;
+    out[9] = 2;            // ikr_tc_pack_kernel + the forward kernel
+    out[10] = 1;
+    out[11] = tcp.groups;
     return 0;
   }
-  Geometry g = make_geometry(d, n_jobs, (const long long*)B, use_pool(d));
+  const bool pool = use_pool(d);
+  Geometry g = make_geometry(d, n_jobs, (const long long*)B, pool);
   out[0] = g.M; out[1] = g.threads; out[2] = g.grid; out[3] = (int64_t)g.smem;
   out[4] = g.n_tiles; out[5] = g.kc; out[6] = g.cpl; out[7] = g.sms;
+  out[8] = pool ? 1 : 0;
+  out[9] = 1;
+  out[10] = 0;
+  out[11] = 0;
   return 0;
 }
 
@@ -933,7 +945,7 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
     tp.g = tcp.g;
     unsigned char* img = ws + fwd_fixed_workspace(n_jobs);
     tp.img = img;
-    tp.timing = getenv("IKR_TC_TIMING") != nullptr;
+    tp.timing = (d->reserved & 8) ? 1 : 0;
     TcPackParams pk;
     pk.wn = reinterpret_cast<const float*>(jobs[0].weights) + p.mlp.off_wn;
     pk.wt = reinterpret_cast<const float*>(jobs[0].weights) + p.mlp.off_wt;

@@ -3,7 +3,13 @@
     from neural_ode_ion_channels_b200 import odeint          # was: from torchdiffeq import odeint
     func = ODEFunc(); func.load_state_dict(torch.load('d1/model-state-dict.pt')); func.eval()
     func.set_fixed_form_voltage_protocol(t_np, v_np)         # train-s1.py:218-222
-    y = odeint(func, y0, t, method='dopri5')                 # (len(t), *y0.shape)
+    with torch.no_grad():                                    # as every reference call site does
+        y = odeint(func, y0, t, method='dopri5')             # (len(t), *y0.shape)
+
+Like ``torchdiffeq.odeint`` the call is differentiable when an MLP parameter requires grad and
+grad mode is on: the forward then records step checkpoints (80 B per accepted step and
+trajectory in fp32; the capacity is sized from free memory and grown on demand) for the discrete
+adjoint in ``adjoint.py``.  Prediction loops should run under ``torch.no_grad()``.
 
 Signature and semantics follow ``torchdiffeq.odeint`` 0.2.x as the reference uses it
 (``train-s1.py:322,327``, ``table-1.py:404,413``, ``train-d0.py:436``): ``rtol=1e-7, atol=1e-9``,
@@ -18,6 +24,7 @@ There is no CPU path: tensors are moved to the current CUDA device and the C-ABI
 ``csrc/libikr_b200.so`` does the work; if it is missing this module raises.
 """
 import ctypes
+import hashlib
 import warnings
 from dataclasses import dataclass
 from typing import Optional
@@ -31,7 +38,8 @@ from .protocols import compact_table
 
 _ADAPTIVE_OPTS = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps'}
 _FIXED_OPTS = {'step_size', 'perturb'}
-_EXT_OPTS = {'tile_m', 'check_status', 'compact_table', 'ckpt_cap', 'lane_pool', 'tensor_cores'}
+_EXT_OPTS = {'tile_m', 'check_status', 'compact_table', 'ckpt_cap', 'lane_pool', 'tensor_cores',
+             'tc_groups', 'tc_timing', 'ping_pong'}
 
 
 # =============================================================================================
@@ -152,19 +160,30 @@ def _make_desc(spec: ModelSpec, state_dtype, method, rtol, atol, opts, time_f32=
     d.tile_m = int(opts.get('tile_m', 0))
     # bit 0: force the lane-pool kernel; bit 2: forbid it (lane_pool=None: library decides);
     # bit 1: keep the fp32 MLP on the FFMA2 kernel (no tcgen05 path)
+    # bit 3: phase-clock printf of CTA 0; bits 4-5: epilogue column groups (tuning; changes the
+    # output-layer summation order); bit 6 / 7: forbid / force the two-tile ping-pong kernel
     lp = opts.get('lane_pool', None)
+    pp = opts.get('ping_pong', None)
+    groups = int(opts.get('tc_groups', 0) or 0)
+    if groups not in (0, 1, 2, 3):
+        raise ValueError('odeint: tc_groups must be 1, 2 or 3')
     d.reserved = ((1 if lp else 0) | (4 if lp is False else 0) |
-                  (0 if opts.get('tensor_cores', True) else 2))
+                  (0 if opts.get('tensor_cores', True) else 2) |
+                  (8 if opts.get('tc_timing', False) else 0) | (groups << 4) |
+                  (64 if pp is False else 0) | (128 if pp else 0))
     return d
 
 
-def pack_weights(spec: ModelSpec, desc, device):
+def pack_weights(spec: ModelSpec, desc, device, out=None):
     """Pack the state-dict tensors into the kernel layout documented in ``include/ikr.h``
-    (``[w0[:,0] | w0[:,1] | b0] | L x W^T[k][npad] | L x b[npad] | w_last | b_last | L x W``)."""
+    (``[w0[:,0] | w0[:,1] | b0] | L x W^T[k][npad] | L x b[npad] | w_last | b_last | L x W``).
+    ``out``: a buffer of a previous call with the same layout (its padding is already zero)."""
     lay = _cabi.packed_layout(desc)
     npad, n, L = lay['npad'], spec.n_nodes, spec.n_layers
     dt = spec.mlp_dtype
-    buf = torch.zeros(lay['total'], dtype=dt, device=device)
+    # a launch that is still reading the previous contents is ordered before these copies by the
+    # stream; callers on several streams must not share one func object
+    buf = out if out is not None else torch.zeros(lay['total'], dtype=dt, device=device)
     lin = spec.linears
     w0 = lin[0].weight.detach().to(device=device, dtype=dt)
     o = lay['off_w0']
@@ -215,8 +234,12 @@ class _DeviceTable:
 
 
 def _table_key(t, v, use_compaction):
-    return (t.ctypes.data, v.ctypes.data, len(t), float(t[0]), float(t[-1]), float(v.sum()),
-            bool(use_compaction))
+    """Content key of a protocol table (never the host addresses: temporaries of the reference's
+    protocol loops are freed and reallocated at the same place with other contents)."""
+    h = hashlib.blake2b(digest_size=16)
+    h.update(t.tobytes())
+    h.update(v.tobytes())
+    return (len(t), h.digest(), bool(use_compaction))
 
 
 class _DeviceModel:
@@ -245,12 +268,19 @@ class _DeviceModel:
             self.tables[key] = tab
         return tab
 
-    def weights_for(self, desc):
-        key = tuple((p.data_ptr(), p._version) for m in self.spec.linears
-                    for p in (m.weight, m.bias))
-        if self.weights is None or key != self.weights_key:
-            self.weights = pack_weights(self.spec, desc, self.device)
-            self.weights_key = key
+    def weights_for(self, desc, private=False):
+        """Packed parameter buffer for this call (``private``: a buffer of its own, for results
+        whose backward pass reads the weights again later).  Re-packed on EVERY call (a handful of small
+        device copies): writes through ``p.data`` or ``optimizer.step()`` leave neither the data
+        pointer nor a reliable version counter behind, and integrating with stale weights would be
+        silent.  The buffer itself is reused when the layout is unchanged."""
+        if private:
+            return pack_weights(self.spec, desc, self.device)
+        lay = _cabi.packed_layout(desc)
+        key = (lay['total'], self.spec.mlp_dtype)
+        if self.weights is None or self.weights_key != key:
+            self.weights, self.weights_key = None, key
+        self.weights = pack_weights(self.spec, desc, self.device, out=self.weights)
         return self.weights
 
 
@@ -460,7 +490,7 @@ def integrate_many(func, jobs, *, rtol=1e-7, atol=1e-9, method=None, options=Non
             raise TypeError('odeint: float32 state with a float64 MLP is not supported')
         desc = _make_desc(spec, state_dtype, method, rtol, atol, opts,
                           time_f32=(t_dtype == torch.float32))
-        weights = dm.weights_for(desc)
+        weights = dm.weights_for(desc, private=any(j.get('want_ckpt') for j in prepared))
         lib = _cabi.lib()
         stream = torch.cuda.current_stream(dev)
         sptr = ctypes.c_void_p(stream.cuda_stream)

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
     for sym in declared:
         assert hasattr(lib, sym), 'libikr_b200.so does not export %s' % sym
     assert set(_cabi.EXPORTS) <= declared
-    assert lib.ikr_abi_version() == 1
+    assert lib.ikr_abi_version() == 2
     assert lib.ikr_error_string(-1) == b'invalid argument'
 
 

@@ -161,3 +161,22 @@ def test_adjoint_fp32_as_shipped_host_logic():
                                          replay=[tuple(r) for r in steps])
     assert np.abs(got_g - want_g).max() <= 2e-4 * np.abs(want_g).max()
     assert np.abs(got_y0 - want_y0).max() <= 2e-4 * np.abs(want_y0).max()
+
+
+def test_table_cache_key_is_content_not_address():
+    """a freed protocol array reallocated at the same address with the same length, span
+    and sum (a time-shifted pulse) must not hit the stale device table."""
+    from neural_ode_ion_channels_b200 import solver
+    t = np.linspace(0.0, 100.0, 1001)
+    v1 = np.full_like(t, -80.0)
+    v1[100:200] = 20.0
+    v2 = np.full_like(t, -80.0)
+    v2[300:400] = 20.0                       # same length, span and sum
+    assert v1.sum() == v2.sum()
+    k1, k2 = solver._table_key(t, v1, True), solver._table_key(t, v2, True)
+    assert k1 != k2
+    buf = v1.copy()
+    ka = solver._table_key(t, buf, True)
+    buf[:] = v2                              # in-place edit: same address, new content
+    assert solver._table_key(t, buf, True) == k2 != ka
+    assert solver._table_key(t, v1, True) != solver._table_key(t, v1, False)
