@@ -4,19 +4,27 @@
     python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo's kernels)
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port)
 
-One *step* = one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1]
--- the pretrained d1 NN-f model, 65,536 perturbed (y0, g) instances dealt round-robin to the five
-voltage-clamp protocol families pr3 / pr4 / pr5 / sinewave / APs (one representative sweep each;
-pr4 and sinewave are labelled synthetic stand-ins because their CSVs are missing from the
-reference checkout), integrated with per-trajectory adaptive dopri5 (rtol 1e-7, atol 1e-9, fp32
-state + fp32 MLP as shipped) and reduced to the per-trajectory MAE against a noisy data trace.
-Weak scaling: every rank integrates its own 65,536 instances, no data-path collective.
+One *step* = one pass of the hot path over one batch of synthetic input.  The JSON line (rank 0):
 
-Printed JSON (rank 0): value = whole-job RHS evaluations per second with inputs resident in HBM;
-e2e = the same through the public ``integrate`` call with HOST (pinned) inputs and a host read of
-the losses inside the timed region; roofline = FP32 FMA pipe (this path is FMA-bound, not HBM- or
-tensor-bound: 0.4 MFLOP per evaluation against < 64 B of HBM traffic); cpu_baseline = the oracle
-port (restated torchdiffeq + reference RHS, B=1 per call like the reference) on the host cores.
+* ``value`` / ``e2e`` / ``roofline`` / ``cpu_baseline``: BASELINE.json configs[1] -- the pretrained
+  d1 NN-f model, 65,536 perturbed (y0, g) instances per GPU dealt round-robin to the five
+  voltage-clamp protocol families pr3 / pr4 / pr5 / sinewave / APs (one representative sweep each;
+  pr4 and sinewave are labelled synthetic stand-ins, their CSVs are missing from the reference
+  checkout), per-trajectory adaptive dopri5 (rtol 1e-7, atol 1e-9, fp32 state + fp32 MLP as
+  shipped), reduced to the per-trajectory MAE against a noisy data trace.  Weak scaling, no
+  data-path collective.
+* ``train``: configs[2] -- fwd + backward: NN-d (d2 weights) through dopri5 on 4,096 noisy staircase
+  datasets per GPU, fused SSE loss, discrete adjoint + weight-gradient GEMM, one flat all-reduce
+  when N > 1; device-timed value, e2e (host y0 / data in, gradient + loss out), its own roofline
+  and its own CPU baseline (autograd through the oracle, B=1 per call).
+* ``sweep``: configs[3] -- 24 independent NN-f fits (s00-s11 x fp32 / fp64) assigned to the ranks
+  longest-first (``parallel.lpt_assign``), per-fit evals/s and makespan against the LPT ideal.
+* ``train1m``: configs[4] -- one optimiser step of ONE model over 1,048,576 trajectories sharded
+  over the ranks (cell-5 constants, pr3 + pr5 windows), compute / all-reduce / optimiser split.
+
+``--impl reference`` times the reference's CPU implementation of the same paths (the oracle port:
+restated torchdiffeq 0.2.1 + the reference RHS classes, B=1 per ``odeint`` call like the reference,
+one process per host core): forward evals/s as ``value`` and autograd fwd+bwd evals/s in ``train``.
 """
 import argparse
 import json
@@ -30,10 +38,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FAMILY_SWEEP = {'pr3': 4, 'pr4': 10, 'pr5': 4, 'sinewave': 0, 'aps': 0}   # sweep index per family
-WEIGHTS = os.path.join(ROOT, 'neural-ode-ion-channels_b200', 'data', 'weights',
-                       'd1-model-state-dict.pt')
+WDIR = os.path.join(ROOT, 'neural-ode-ion-channels_b200', 'data', 'weights')
+WEIGHTS = os.path.join(WDIR, 'd1-model-state-dict.pt')
+WEIGHTS_D2 = os.path.join(WDIR, 'd2-model-state-dict.pt')
 FLOP_PER_EVAL = 2 * 200600          # BASELINE.md section 3 (s00 architecture, forward)
-METRIC = 'NN-ODE RHS evals/sec (batched dopri5; headline = configs[1] forward, fwd+backward in "train")'
+METRIC = ('NN-ODE RHS evals/sec (batched dopri5; value = configs[1] forward ensemble, fwd+backward '
+          'in "train")')
+
+
+def macs_of(L, n):
+    return 2 * n + L * n * n + n
 
 
 def measured_peaks():
@@ -49,13 +63,12 @@ def measured_peaks():
                 'source': 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)'}
 
 
-def forward_roofline(achieved_tflops, fma_peak_tflops, tensor_cores):
+def forward_roofline(achieved_tflops, fma_peak_tflops, geo):
     """Roofline object of the forward kernel.  `achieved` is ALGORITHMIC work (401,200 FLOP per RHS
-    evaluation) / kernel time.  On the tcgen05 path every fp32 product is six
-    bf16 MMAs (bf16x3 split, fp32-faithful), so the executed tensor FLOPs are 6 x the algorithmic
-    hidden-layer FLOPs; both fractions are reported.  HBM traffic is ~1 MB per launch (weights +
-    tables; everything else lives in SMEM / TMEM / L2)."""
-    if not tensor_cores:
+    evaluation) / kernel time.  On the tcgen05 path an fp32 product is issued
+    as `products` 16-bit MMAs (split operands, fp32 accumulation), so the executed tensor FLOPs are
+    products x the algorithmic hidden-layer FLOPs; both fractions are reported."""
+    if not geo.get('tensor_cores'):
         return {
             'bound': 'fma', 'achieved': achieved_tflops, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
             'frac': achieved_tflops / fma_peak_tflops if fma_peak_tflops else None,
@@ -64,23 +77,24 @@ def forward_roofline(achieved_tflops, fma_peak_tflops, tensor_cores):
                            'lanes x 2 x 1.965 GHz = 74.5 TFLOP/s)',
         }
     mp = measured_peaks()
+    products = int(geo.get('mma_products', 6))
     hidden_share = (2.0 * 5 * 200 * 200) / FLOP_PER_EVAL       # hidden layers / all layers (s00)
-    executed = achieved_tflops * hidden_share * 6.0 * (208.0 / 200.0)   # N padded 200 -> 208
+    executed = achieved_tflops * hidden_share * products * (208.0 / 200.0)   # N padded 200 -> 208
     return {
         'bound': 'tensor', 'achieved': achieved_tflops, 'peak': mp['bf16_sustained'], 'unit': 'TFLOP/s',
         'frac': achieved_tflops / mp['bf16_sustained'],
-        # dram__bytes_read + write of one ikr_forward_tc_pool_kernel launch of this bench step (ncu
-        # --set full, profiles/r1_fwd_tc_pool_ncu_raw.csv: 53.4 MB read + 86.8 MB written in 1.16 s:
-        # data traces, per-trajectory results, L2 write-backs); the tile kernel on 18,944
-        # trajectories moves 1.68 MB (weight image + tables) and writes nothing
+        # dram__bytes_read + write of one forward launch of this bench step (ncu --set full,
+        # profiles/): data traces and per-trajectory results; the weight image and the tables are
+        # L2-resident
         'traffic': 1.403e8, 'flop_per_eval': FLOP_PER_EVAL,
-        'peak_source': 'dense bf16 tensor peak, sustained figure of %s (kernel timed inside a long '
+        'peak_source': 'dense 16-bit tensor peak, sustained figure of %s (kernel timed inside a long '
                        'step)' % mp['source'],
-        'executed_bf16_tflops': executed, 'frac_executed': executed / mp['bf16_sustained'],
-        'fp32_emulation': 'bf16x3 split: 6 bf16 MMAs (a1b1 a2b1 a3b1 a1b2 a2b2 a1b3) per fp32 product, '
-                          'fp32 accumulation in TMEM; ceiling for fp32-faithful work = peak / 6 = '
-                          '%.1f TFLOP/s' % (mp['bf16_sustained'] / 6.0),
-        'frac_of_fp32_emulation_ceiling': achieved_tflops / (mp['bf16_sustained'] / 6.0),
+        'executed_tensor_tflops': executed, 'frac_executed': executed / mp['bf16_sustained'],
+        'fp32_emulation': '%s: %d 16-bit MMAs per fp32 product, fp32 accumulation in TMEM; ceiling for '
+                          'this arithmetic = peak / %d = %.1f TFLOP/s'
+                          % (geo.get('mma_split', 'bf16x3 split'), products, products,
+                             mp['bf16_sustained'] / products),
+        'frac_of_fp32_emulation_ceiling': achieved_tflops / (mp['bf16_sustained'] / products),
         'fma_peak': fma_peak_tflops,
         'vs_fma_peak': achieved_tflops / fma_peak_tflops if fma_peak_tflops else None,
     }
@@ -92,6 +106,8 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--legs', default='forward,train,sweep,train1m',
+                    help='comma list of forward,train,sweep,train1m (forward always runs)')
     ap.add_argument('--batch', type=int, default=65536, help='trajectories per GPU per step')
     ap.add_argument('--families', default='pr3,pr4,pr5,sinewave,aps')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
@@ -100,6 +116,13 @@ def parse_args():
                     help='datasets per GPU of the fwd+bwd leg (configs[2]); 0 disables the leg')
     ap.add_argument('--train-outputs', type=int, default=7501,
                     help='output samples of the staircase stand-in used by the fwd+bwd leg')
+    ap.add_argument('--train-steps', type=int, default=0, help='timed steps of the fwd+bwd leg '
+                    '(0: min(max(steps, 3), 5))')
+    ap.add_argument('--sweep-batch', type=int, default=256)
+    ap.add_argument('--sweep-outputs', type=int, default=200)
+    ap.add_argument('--sweep-iters', type=int, default=2)
+    ap.add_argument('--train1m-total', type=int, default=1048576)
+    ap.add_argument('--train1m-chunk', type=int, default=65536)
     return ap.parse_args()
 
 
@@ -116,7 +139,6 @@ def workload(families):
 # reference arm / cpu_baseline: the oracle port on the host cores (B=1 per call)
 # ---------------------------------------------------------------------------------------------
 def _cpu_worker(job):
-    import numpy as np
     import torch
     torch.set_num_threads(1)
     from oracle import ref_models as rm, ref_odeint as ro
@@ -159,7 +181,6 @@ def cpu_rate(families, budget_s, cores):
         y0 = [float(rng.uniform(0, 0.05)), float(rng.uniform(0.95, 1))]
         jobs.append((fam, t_tab, v_tab, t_out, y0, budget_s))
     ctx = mp.get_context('fork')
-    t0 = time.time()
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
     nfe = sum(r[0] for r in res)
@@ -169,12 +190,70 @@ def cpu_rate(families, budget_s, cores):
     return rate, nfe, nfe / rate
 
 
+def _cpu_train_worker(job):
+    """One fwd + backward of the configs[2] step on the CPU path: autograd through the oracle's
+    dopri5 (torchdiffeq non-adjoint semantics), NN-d with the d2 weights, one noisy staircase
+    dataset, SSE loss.  Counts evaluations like the GPU leg: forward nfe + (6 x accepted + 1)."""
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from oracle import ref_models as rm, ref_odeint as ro
+    t_tab, v_tab, t_out, y0, seed, budget_s = job
+    func = rm.load_state_dict_file(rm.NNdRhs(act=rm.HH_B06[:4], inact=rm.INACT_D), WEIGHTS_D2)
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    for p in func.net.parameters():
+        p.requires_grad_(True)
+    t_all = torch.tensor(t_out, dtype=torch.float32)
+    v_all = torch.from_numpy(np.interp(np.asarray(t_out, dtype=np.float64), t_tab, v_tab))
+    rng = np.random.RandomState(seed)
+
+    def one(m):
+        st = {}
+        t = t_all[:m]
+        c0 = time.time()
+        y = ro.odeint(func, torch.tensor([y0], dtype=torch.float32), t, stats=st)
+        cur = (y[:, 0, 0] * y[:, 0, 1]).double() * (v_all[:m] + 86.0)
+        data = cur.detach() + torch.from_numpy(rng.normal(0, 0.1, m))
+        loss = ((cur - data) ** 2).sum()
+        loss.backward()
+        for p in func.net.parameters():
+            p.grad = None
+        return st['nfe'] + 6 * st['n_accept'] + 1, time.time() - c0
+
+    probe = min(len(t_all), 16)
+    evals, wall = one(probe)
+    remaining = budget_s - wall
+    if remaining > 0 and probe < len(t_all):
+        m = int(min(len(t_all), max(probe, remaining / max(wall / probe, 1e-9))))
+        e2, w2 = one(m)
+        evals, wall = evals + e2, wall + w2
+    return evals, wall
+
+
+def cpu_train_rate(budget_s, cores, n_outputs):
+    import multiprocessing as mp
+    import numpy as np
+    from neural_ode_ion_channels_b200 import protocols
+    name, t_tab, v_tab, t_out = protocols.protocol_set('staircase')[0]
+    t_out = t_out[:n_outputs]
+    rng = np.random.RandomState(2000)
+    jobs = [(t_tab, v_tab, t_out, [float(rng.uniform(0, 0.05)), float(rng.uniform(0.95, 1))],
+             3000 + i, budget_s) for i in range(cores)]
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_train_worker, jobs)
+    evals = sum(r[0] for r in res)
+    rate = sum(r[0] / r[1] for r in res)
+    return rate, evals, evals / rate
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     families = args.families.split(',')
+    legs = set(args.legs.split(','))
     per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_rate(families, per_step, cores)
@@ -202,6 +281,21 @@ def run_reference(args):
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if 'train' in legs and args.train_batch > 0:
+        budget = max(4.0, min(args.cpu_seconds, 30.0))
+        rate, evals, wall = cpu_train_rate(budget, cores, args.train_outputs)
+        line['train'] = {
+            'workload': 'configs[2] on the CPU path: autograd (loss.backward()) through the oracle dopri5, '
+                        'NN-d d2 weights, noisy staircase-standin datasets, SSE loss',
+            'value': rate, 'unit': 'evals/s (fwd + adjoint)',
+            'e2e': {'value': rate, 'unit': 'evals/s (fwd + adjoint)', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'cpu_baseline': {'value': rate, 'unit': 'evals/s (fwd + adjoint)', 'cores': cores,
+                             'kind': 'port',
+                             'sample': '%d worker processes x 1 dataset (B=1 per call), a prefix of the '
+                                       '%d-sample staircase grid sized for ~%.0f s each (%d evals)'
+                                       % (cores, args.train_outputs, budget, evals)},
+        }
     print(json.dumps(line))
 
 
@@ -244,26 +338,37 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(self.reasons), 'samples': len(s)}
 
 
-def run_train_leg(args, ikr, dev, world, rank):
+def _reduce(dev, world, maxes, sums):
+    """(max over ranks of `maxes`, sum over ranks of `sums`) as python floats."""
+    import torch
+    import torch.distributed as dist
+    mx = torch.tensor(maxes, dtype=torch.float64, device=dev)
+    sm = torch.tensor(sums, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    return mx.tolist(), sm.tolist()
+
+
+def run_train_leg(args, ikr, dev, world, rank, local_rank):
     """configs[2]: NN-d (d2 weights) fitted to noisy staircase datasets -- ONE training step =
     batched dopri5 forward with step checkpoints + fused SSE loss + backward through the solver
     (adjoint sweep + weight-gradient GEMM) + (N > 1) one flat all-reduce of the gradient.
-    Returns a dict for the JSON line (device-timed, max over ranks)."""
+    Device-timed over >= 3 steps (max over ranks) and end to end with host inputs / outputs."""
     import numpy as np
     import torch
     import torch.distributed as dist
     from neural_ode_ion_channels_b200 import parallel, protocols
     B = args.train_batch
-    wpath = os.path.join(ROOT, 'neural-ode-ion-channels_b200', 'data', 'weights',
-                         'd2-model-state-dict.pt')
-    func = ikr.load_weights(ikr.ODEFuncNNd(params='d'), wpath).to(dev)
+    func = ikr.load_weights(ikr.ODEFuncNNd(params='d'), WEIGHTS_D2).to(dev)
     name, t_tab, v_tab, t_out = protocols.protocol_set('staircase')[0]
     t_out = t_out[:args.train_outputs]
     func.set_fixed_form_voltage_protocol(t_tab, v_tab)
     t = torch.tensor(t_out, dtype=torch.float32)
     rng = np.random.RandomState(2000 + rank)
-    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1.0, B)], 1),
-                      dtype=torch.float32, device=dev)
+    y0_h = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1.0, B)], 1),
+                        dtype=torch.float32).pin_memory()
+    y0 = y0_h.to(dev)
     with torch.no_grad():
         nominal = ikr.integrate(func, torch.tensor([[0., 1.]], device=dev), t, want_current=True,
                                 want_y=False, E=-86.0).current[:, 0]
@@ -271,53 +376,287 @@ def run_train_leg(args, ikr, dev, world, rank):
     gen = torch.Generator(device=dev)
     gen.manual_seed(3000 + rank)
     data = nominal[:, None] + 0.1 * torch.randn(len(t), B, generator=gen, device=dev)
+    data_h = data.cpu().pin_memory()
     opts = {'check_status': False, 'ckpt_cap': args.train_outputs // 2 + 512}
 
-    def step():
-        total, per, grads, res = ikr.loss_and_grad(func, y0, t, data, E=-86.0, options=opts)
+    def step(y0_in, data_in):
+        total, per, grads, res = ikr.loss_and_grad(func, y0_in, t, data_in, E=-86.0, options=opts)
+        flat = res.grad_flat
         if world > 1:
-            grads, total = parallel.allreduce_gradients(grads, total)
-        return total, grads, res
+            flat, total = parallel.allreduce_flat(flat, total)
+        return total, flat, res
 
-    total, grads, res = step()          # warm-up (also sizes the caching allocator)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_steps = args.train_steps or min(max(args.steps, 3), 5)
+    total, flat, res = step(y0, data)          # warm-up (also sizes the caching allocator)
     st = res.stats
     assert int((st[:, 3] != 0).sum()) == 0, 'solver status != ok in the training leg'
-    uses_tc = bool(res.geometry.get('tensor_cores'))
-    del total, grads, res, st        # the timed step reuses the cached allocations
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    total, grads, res = step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    st = res.stats
+    geo = res.geometry
     nfe_f = float(st[:, 2].sum())
     nfe_b = float((6 * st[:, 0] + 1).sum())
-    vec = torch.tensor([ms, nfe_f, nfe_b], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = vec.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vec.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_all, nfe_f_all, nfe_b_all = float(mx[0]), float(sm[1]), float(sm[2])
-    else:
-        ms_all, nfe_f_all, nfe_b_all = ms, nfe_f, nfe_b
-    gmax = max(float(g.abs().max()) for g in grads)
-    return {
+    acc_mean = float(st[:, 0].float().mean())
+    del total, flat, res, st
+    total, flat, res = step(y0, data)          # second warm-up
+    del res
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_steps):
+        total, flat, res = step(y0, data)
+        del res
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / n_steps
+    gmax = float(flat.abs().max())
+    loss = float(total)
+
+    # end to end: host y0 / data in (pinned), gradient + loss back on the host, every step
+    def step_e2e():
+        tot, fl, r = step(y0_h.to(dev, non_blocking=True), data_h.to(dev, non_blocking=True))
+        g_host = fl.to('cpu')
+        l_host = float(tot)
+        del r
+        return g_host, l_host
+
+    step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(n_steps):
+        g_host, l_host = step_e2e()
+    f1.record()
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - w0)) / n_steps
+
+    (ms_all, e2e_all), (nfe_f_all, nfe_b_all) = _reduce(dev, world, [ms, e2e_ms], [nfe_f, nfe_b])
+    mp = measured_peaks()
+    # algorithmic work: forward eval = 401,200 FLOP; an adjoint eval = input-gradient GEMVs +
+    # weight-gradient outer products = 2 x 401,200 (fwd + bwd = 3 x; the forward
+    # recomputation inside the adjoint sweep is overhead, not algorithmic work)
+    alg = (nfe_f * FLOP_PER_EVAL + nfe_b * 2 * FLOP_PER_EVAL) / (ms * 1e-3) / 1e12
+    rounds = None
+    out = {
         'workload': 'configs[2]: NN-d (d2 weights, s00 MLP) one training step through dopri5 on %d '
                     'noisy %s datasets per GPU (%d output samples): forward + fused SSE + adjoint '
                     'sweep + weight-gradient GEMM%s' % (B, name, len(t), '' if world == 1 else
                                                       ' + one flat NCCL all-reduce'),
         'value': (nfe_f_all + nfe_b_all) / (ms_all * 1e-3), 'unit': 'evals/s (fwd + adjoint)',
-        'ms_per_step': ms_all, 'forward_evals': nfe_f_all, 'adjoint_evals': nfe_b_all,
-        'accepted_steps_mean': float(st[:, 0].float().mean()),
-        'algorithmic_tflops': (nfe_f * FLOP_PER_EVAL + nfe_b * 3 * FLOP_PER_EVAL) / (ms * 1e-3) / 1e12,
-        'loss': float(total), 'grad_abs_max': gmax, 'tensor_cores': uses_tc,
+        'steps': n_steps, 'warmup': 2, 'ms_per_step': ms_all,
+        'forward_evals': nfe_f_all, 'adjoint_evals': nfe_b_all, 'accepted_steps_mean': acc_mean,
+        'e2e': {'value': (nfe_f_all + nfe_b_all) / (e2e_all * 1e-3), 'unit': 'evals/s (fwd + adjoint)',
+                'ms_per_step': e2e_all,
+                'h2d_bytes_per_step': y0_h.numel() * 4 + data_h.numel() * 4 + t.numel() * 8,
+                'd2h_bytes_per_step': int(g_host.numel()) * 8 + 8},
+        'roofline': {
+            'bound': 'tensor', 'achieved': alg, 'peak': mp['bf16_sustained'], 'unit': 'TFLOP/s',
+            'frac': alg / mp['bf16_sustained'], 'traffic': None,
+            'flop_per_forward_eval': FLOP_PER_EVAL, 'flop_per_adjoint_eval': 2 * FLOP_PER_EVAL,
+            'frac_of_fp32_emulation_ceiling': alg / (mp['bf16_sustained'] / 6.0),
+            'peak_source': 'dense bf16 tensor peak, sustained figure of %s' % mp['source'],
+            'note': 'latency-bound at %d datasets: %d tiles of 128 trajectories occupy %d of %d SMs'
+                    % (B, -(-B // 128), min(-(-B // 128), geo['sms']), geo['sms']),
+        },
+        'clocks': clocks,
+        'loss': loss, 'grad_abs_max': gmax, 'tensor_cores': bool(geo.get('tensor_cores')),
+    }
+    del rounds
+    return out
+
+
+def _fit_cost(L, n, f64):
+    """Relative cost model of one fit for the LPT assignment (seconds per evaluation, from the
+    measured per-architecture rates in profiles/: tensor cores 85 T MAC/s, FFMA2 17, DFMA 6.5,
+    plus a 0.4 ns floor for the solver / exp / table part)."""
+    tc = (not f64) and 16 <= n <= 200
+    rate = 85e12 if tc else (17e12 if not f64 else 6.5e12)
+    return 0.4e-9 + macs_of(L, n) / rate
+
+
+def run_sweep_leg(args, ikr, dev, world, rank):
+    """configs[3]: the architecture sweep of train-r1-tune.py (one independent NN-f fit per
+    architectures/sNN.py, consumer table-s1.py:134-303), fp32 and fp64 = 24 fits, assigned to the
+    ranks longest-first; no collective on the data path (results gathered once at the end).
+    A fit here = `sweep_iters` Adam iterations of the fused loss + gradient through dopri5 on
+    `sweep_batch` noisy datasets of the Pr4 stand-in (cell-5 constants, N(0, 0.1^2) init, seed 0)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from neural_ode_ion_channels_b200 import parallel, protocols
+    name, t_tab, v_tab, t_out = protocols.protocol_set('pr4')[10]
+    t_out = t_out[:args.sweep_outputs]
+    B = args.sweep_batch
+    fits = [(arch, f64) for arch in ikr.ARCHITECTURES for f64 in (False, True)]
+    costs = [_fit_cost(*ikr.ARCHITECTURES[a], f64) for a, f64 in fits]
+    assign = parallel.lpt_assign(costs, world)
+    rng = np.random.RandomState(4000)
+    y0np = np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1.0, B)], 1)
+    noise = rng.normal(0, 0.05, (len(t_out), B))
+    mine = []
+    for idx in assign[rank]:
+        arch, f64 = fits[idx]
+        L, n = ikr.ARCHITECTURES[arch]
+        dtype = torch.float64 if f64 else torch.float32
+        torch.manual_seed(0)
+        func = ikr.ODEFuncNNf(arch=arch, params='r')
+        if f64:
+            func = func.double()
+        func = func.to(dev)
+        func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        t = torch.tensor(t_out, dtype=dtype)
+        y0 = torch.tensor(y0np, dtype=dtype, device=dev)
+        entry = {'arch': arch, 'dtype': 'f64' if f64 else 'f32', 'L': L, 'n': n, 'macs': macs_of(L, n)}
+        try:
+            with torch.no_grad():
+                nominal = ikr.integrate(func, torch.tensor([[0.01, 0.98]], dtype=dtype, device=dev), t,
+                                        want_current=True, want_y=False, g=0.1339 * 1.2, E=-93.4).current
+            data = (0.8 * nominal + torch.tensor(noise, dtype=dtype, device=dev)).contiguous()
+            opt = torch.optim.Adam(func.net.parameters(), lr=1e-3)
+            plist = list(func.net.parameters())
+            opts = {'check_status': False, 'ckpt_cap': 1024}
+            evals = 0.0
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            for it in range(args.sweep_iters + 1):        # iteration 0 = warm-up
+                if it == 1:
+                    torch.cuda.synchronize()
+                    ev[0].record()
+                total, per, grads, res = ikr.loss_and_grad(func, y0, t, data, g=0.1339 * 1.2, E=-93.4,
+                                                           options=opts)
+                for p, g in zip(plist, grads):
+                    p.grad = (g / B).to(p.dtype)
+                opt.step()
+                if it >= 1:
+                    evals += float(res.stats[:, 2].sum() + (6 * res.stats[:, 0] + 1).sum())
+                bad = int((res.stats[:, 3] != 0).sum())
+                tcores = bool(res.geometry.get('tensor_cores'))
+                del res
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1])
+            entry.update({'ms': ms, 'evals': evals, 'evals_per_s': evals / (ms * 1e-3),
+                          'tflops': evals / 2.0 * 3 * 2 * macs_of(L, n) / (ms * 1e-3) / 1e12,
+                          'kernel': 'tcgen05' if tcores else ('DFMA' if f64 else 'FFMA2'),
+                          'status_bad': bad, 'loss': float(total), 'rank': rank})
+        except RuntimeError as exc:   # an unsupported configuration is reported, not hidden
+            entry.update({'ms': 0.0, 'evals': 0.0, 'error': str(exc)[:160], 'rank': rank})
+        mine.append(entry)
+        del func
+        torch.cuda.empty_cache()
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        entries = [e for part in gathered for e in part]
+    else:
+        entries = mine
+    if rank != 0:
+        return None
+    per_rank = [sum(e['ms'] for e in entries if e['rank'] == r) for r in range(world)]
+    total_ms = sum(per_rank)
+    longest = max(e['ms'] for e in entries)
+    ideal = max(total_ms / world, longest)
+    order = {a: i for i, a in enumerate(ikr.ARCHITECTURES)}
+    entries.sort(key=lambda e: (order[e['arch']], e['dtype']))
+    return {
+        'workload': 'configs[3]: %d independent NN-f fits (s00-s11 x fp32/fp64), %d Adam iterations of '
+                    'loss + gradient through dopri5 on %d noisy %s datasets (%d outputs) each, LPT-'
+                    'assigned to %d rank(s), no data-path collective'
+                    % (len(fits), args.sweep_iters, B, name, len(t_out), world),
+        'value': sum(e['evals'] for e in entries) / (max(per_rank) * 1e-3), 'unit': 'evals/s (fwd + adjoint)',
+        'makespan_ms': max(per_rank), 'ideal_ms': ideal, 'makespan_over_ideal': max(per_rank) / ideal,
+        'per_rank_ms': per_rank, 'fits': entries,
+    }
+
+
+def run_train1m_leg(args, ikr, dev, world, rank):
+    """configs[4]: ONE optimiser step of one NN-f model over 1,048,576 trajectories (cell-5 constants
+    train-r1.py:43-47,171-174; Pr3 + Pr5 as train-r1.py:795-797, windows around their voltage steps)
+    sharded contiguously over the ranks; each rank accumulates its flat fp64 gradient over chunks,
+    then ONE all-reduce of the flat gradient + loss, then the replicated Adam step.  Strong scaling:
+    the total is fixed.  Reports the compute / all-reduce / optimiser split (device events)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from neural_ode_ion_channels_b200 import parallel, protocols
+    total_n = args.train1m_total
+    lo, hi = parallel.shard_bounds(total_n, world, rank)
+    torch.manual_seed(0)
+    func = ikr.ODEFuncNNf(arch='s00', params='r').to(dev)
+    g_c, e_c = 0.1339 * 1.2, -93.4
+    windows = []
+    for fam, idx, t0 in (('pr3', 4, 980.0), ('pr5', 4, 2980.0)):
+        name, t_tab, v_tab, _ = protocols.protocol_set(fam)[idx]
+        t = torch.linspace(t0, t0 + 120.0, 61)
+        func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        with torch.no_grad():
+            nominal = ikr.integrate(func, torch.tensor([[0.01, 0.98]], device=dev), t,
+                                    want_current=True, want_y=False, g=g_c, E=e_c).current[:, 0]
+        noise = torch.from_numpy(np.random.RandomState(11).normal(0, 0.05, len(t)).astype(np.float32))
+        windows.append((name, t_tab, v_tab, t, (0.8 * nominal + noise.to(dev)).contiguous()))
+    opt = torch.optim.Adam(func.net.parameters(), lr=1e-3)
+    plist = list(func.net.parameters())
+    opts = {'check_status': False, 'ckpt_cap': 256}
+    n_par = sum(p.numel() for p in plist)
+
+    def one_step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        flat = torch.zeros(n_par, dtype=torch.float64, device=dev)
+        loss = torch.zeros((), dtype=torch.float64, device=dev)
+        evals = torch.zeros((), dtype=torch.float64, device=dev)
+        bad = torch.zeros((), dtype=torch.int64, device=dev)
+        ev[0].record()
+        for c0 in range(lo, hi, args.train1m_chunk):
+            c1 = min(hi, c0 + args.train1m_chunk)
+            rng = np.random.RandomState(5000 + c0 // args.train1m_chunk)
+            nb = c1 - c0
+            y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, nb), rng.uniform(0.95, 1.0, nb)], 1),
+                              dtype=torch.float32, device=dev)
+            half = nb // 2
+            for w, (a, b) in zip(windows, ((0, half), (half, nb))):
+                if b <= a:
+                    continue
+                func.set_fixed_form_voltage_protocol(w[1], w[2])
+                tot, per, grads, res = ikr.loss_and_grad(func, y0[a:b], w[3], w[4], g=g_c, E=e_c,
+                                                         options=opts)
+                flat += res.grad_flat
+                loss += tot
+                evals += res.stats[:, 2].sum() + (6 * res.stats[:, 0] + 1).sum()
+                bad += (res.stats[:, 3] != 0).sum()
+                del res
+        ev[1].record()
+        flat, loss = parallel.allreduce_flat(flat, loss)
+        ev[2].record()
+        o = 0
+        for p in plist:
+            p.grad = (flat[o:o + p.numel()].view_as(p) / total_n).to(p.dtype)
+            o += p.numel()
+        opt.step()
+        ev[3].record()
+        torch.cuda.synchronize()
+        return ([ev[i].elapsed_time(ev[i + 1]) for i in range(3)], float(evals), float(loss), int(bad))
+
+    one_step()                                  # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    parts, evals, loss, bad = one_step()
+    assert bad == 0, 'solver status != ok in the 1M leg'
+    (c_ms, a_ms, o_ms, tot_ms), (ev_all,) = _reduce(dev, world, parts + [sum(parts)], [evals])
+    return {
+        'workload': 'configs[4]: one optimiser step of one NN-f model (s00, cell-5 constants) over %d '
+                    'trajectories sharded over %d rank(s) (%d per rank, chunks of %d): %s + %s windows of '
+                    '61 outputs, fused SSE + adjoint + weight gradient, ONE flat all-reduce (%d fp64 + '
+                    'loss), replicated Adam step'
+                    % (total_n, world, hi - lo, args.train1m_chunk, windows[0][0], windows[1][0], n_par),
+        'value': ev_all / (tot_ms * 1e-3), 'unit': 'evals/s (fwd + adjoint)', 'scaling': 'strong',
+        'ms_per_step': tot_ms, 'compute_ms': c_ms, 'allreduce_ms': a_ms, 'optimizer_ms': o_ms,
+        'allreduce_bytes': (n_par + 1) * 8, 'evals': ev_all, 'loss': loss,
     }
 
 
@@ -327,8 +666,9 @@ def run_b200(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     families = args.families.split(',')
+    legs = set(args.legs.split(','))
 
-    cpu_base = None
+    cpu_base = cpu_train = None
     if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         rate, nfe, wall = cpu_rate(families, args.cpu_seconds, cores)   # before CUDA init (fork)
@@ -336,6 +676,13 @@ def run_b200(args):
                     'sample': '%d worker processes x 1 trajectory (B=1 per call) cycling the %s '
                               'sweeps, ~%.0f s each (%d evals in %.1f s)'
                               % (cores, '/'.join(families), args.cpu_seconds, nfe, wall)}
+        if 'train' in legs and args.train_batch > 0:
+            budget = max(4.0, min(args.cpu_seconds, 15.0))
+            rate, evals, wall = cpu_train_rate(budget, cores, args.train_outputs)
+            cpu_train = {'value': rate, 'unit': 'evals/s (fwd + adjoint)', 'cores': cores, 'kind': 'port',
+                         'sample': '%d worker processes x 1 dataset (B=1 per call): autograd through '
+                                   'the oracle dopri5 on a prefix of the staircase grid, ~%.0f s each '
+                                   '(%d evals)' % (cores, budget, evals)}
 
     import torch
     import torch.distributed as dist
@@ -375,14 +722,17 @@ def run_b200(args):
         jobs_host.append(dict(common, y0=hy, g=hg))
     torch.cuda.synchronize()
 
-    # FMA-pipe peak micro-benchmark (roofline denominator), measured in this run
+    # FMA-pipe peaks (roofline denominators of the FMA-path kernels), measured in this run
     peak = ctypes.c_double(0.0)
     _cabi.check(_cabi.lib().ikr_fma_peak(_cabi.F32, 20000, ctypes.byref(peak), None), 'fma_peak')
     _cabi.check(_cabi.lib().ikr_fma_peak(_cabi.F32, 200000, ctypes.byref(peak), None), 'fma_peak')
     fma_peak_tflops = peak.value
+    _cabi.check(_cabi.lib().ikr_fma_peak(_cabi.F64, 100000, ctypes.byref(peak), None), 'fma_peak')
+    dfma_peak_tflops = peak.value
 
     lane_pool = {'1': True, '0': False}.get(os.environ.get('IKR_LANE_POOL', ''), None)
-    opts = {'check_status': False, 'lane_pool': lane_pool,
+    ping_pong = {'1': True, '0': False}.get(os.environ.get('IKR_PING_PONG', ''), None)
+    opts = {'check_status': False, 'lane_pool': lane_pool, 'ping_pong': ping_pong,
             'tensor_cores': not os.environ.get('IKR_NO_TC')}
 
     def step_device():
@@ -444,34 +794,35 @@ def run_b200(args):
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))
 
-    stats = torch.tensor([ms, e2e_ms, float(nfe_total), float(nfe_e2e)], dtype=torch.float64,
-                         device=dev)
-    nfe_rank0 = float(nfe_total)
-    ms_rank0 = ms
-    if world > 1:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, e2e_ms = float(mx[0]), float(mx[1])
-        nfe_total, nfe_e2e = float(sm[2]), float(sm[3])
+    nfe_rank0, ms_rank0 = float(nfe_total), ms
+    (ms, e2e_ms), (nfe_total, nfe_e2e) = _reduce(dev, world, [ms, e2e_ms],
+                                                 [float(nfe_total), float(nfe_e2e)])
     h2d = sum(j['y0'].numel() * 4 + j['g'].numel() * 4 for j in jobs_host) + \
         sum(t.numel() * 8 for t in tgrids)
     d2h = sum(nb * 8 + nb * 16 for nb in sizes)
-    # per step: weight-image pack kernel + forward kernel + one V(t_out) kernel per job
-    n_launch_fwd = (len(jobs_dev) + (2 if geo.get('tensor_cores') else 1)) * args.steps
-    train = None
-    if args.train_batch > 0:
-        del jobs_dev, jobs_host, outs
+    # per step: the library's own launch count for one ikr_forward call (ikr_launch_geometry) + one
+    # V(t_out) kernel per job
+    n_launch_fwd = (len(jobs_dev) + int(geo['launches'])) * args.steps
+    del jobs_dev, jobs_host, outs
+    torch.cuda.empty_cache()
+
+    train = sweep = train1m = None
+    if 'train' in legs and args.train_batch > 0:
+        train = run_train_leg(args, ikr, dev, world, rank, local_rank)
         torch.cuda.empty_cache()
-        train = run_train_leg(args, ikr, dev, world, rank)
+    if 'sweep' in legs:
+        sweep = run_sweep_leg(args, ikr, dev, world, rank)
+        torch.cuda.empty_cache()
+    if 'train1m' in legs:
+        train1m = run_train1m_leg(args, ikr, dev, world, rank)
+
     if rank == 0:
         value = nfe_total / (ms * 1e-3)
         e2e_value = nfe_e2e / (e2e_ms * 1e-3)
         # the forward kernel is >99.9 % of the timed region (profiles/): its launch duration is the
         # event-timed step
         achieved = (nfe_rank0 * FLOP_PER_EVAL) / (ms_rank0 * 1e-3) / 1e12
-        roofline = forward_roofline(achieved, fma_peak_tflops, bool(geo.get('tensor_cores')))
+        roofline = forward_roofline(achieved, fma_peak_tflops, geo)
         line = {
             'metric': METRIC,
             'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps,
@@ -486,11 +837,10 @@ def run_b200(args):
                 'standins': ['pr4', 'sinewave'],
                 'cache': 'working set (weights 0.8 MB, tables, per-lane state) is L2/SMEM '
                          'resident by design; y0/g/stat buffers are rewritten every step',
+                # the library's own description of what it launched (ikr_launch_geometry)
                 'tile_m': geo['tile_m'], 'threads_per_cta': geo['threads'], 'grid': geo['grid'],
                 'n_tiles': geo['n_tiles'], 'tensor_cores': bool(geo.get('tensor_cores')),
-                'scheduling': 'lane pool (slots refill from one trajectory queue)'
-                if geo['n_tiles'] * geo['tile_m'] < sum(-(-nb // geo['tile_m']) for nb in sizes) * geo['tile_m']
-                else 'tile queue (longest job first)',
+                'scheduling': geo['scheduling'], 'column_groups': geo['column_groups'],
                 'step_attempts_per_trajectory': dict(zip([w[0] for w in wl], steps_per_lane)),
             },
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': h2d,
@@ -499,10 +849,20 @@ def run_b200(args):
             'clocks': clocks,
             'roofline': roofline,
             'cpu_baseline': cpu_base,
+            'fma_peaks_measured': {'fp32_tflops': fma_peak_tflops, 'fp64_tflops': dfma_peak_tflops},
         }
         if train is not None:
-            train['frac_of_fma_peak'] = train['algorithmic_tflops'] / fma_peak_tflops
+            train['cpu_baseline'] = cpu_train
             line['train'] = train
+        if sweep is not None:
+            for e in sweep['fits']:
+                if e.get('kernel') == 'DFMA' and e.get('tflops'):
+                    e['frac_of_dfma_peak'] = e['tflops'] / dfma_peak_tflops
+                elif e.get('kernel') == 'FFMA2' and e.get('tflops'):
+                    e['frac_of_ffma_peak'] = e['tflops'] / fma_peak_tflops
+            line['sweep'] = sweep
+        if train1m is not None:
+            line['train1m'] = train1m
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -165,5 +165,5 @@ def loss_and_grad(func, y0, t, data, *, g=None, E=-86.0, loss='sse', rtol=1e-7, 
         for gr, m in zip(grads, [q for m in spec.linears for q in (m.weight, m.bias)]):
             gr = gr.to(device=m.device, dtype=m.dtype)
             m.grad = gr if m.grad is None else m.grad + gr
-    res.grad_y0, res.grad_g = grad_y0, grad_g
+    res.grad_y0, res.grad_g, res.grad_flat = grad_y0, grad_g, flat
     return per_traj.sum(), per_traj, grads, res

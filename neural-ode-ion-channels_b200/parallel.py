@@ -43,6 +43,18 @@ def lpt_assign(costs, world_size):
     return out
 
 
+def allreduce_flat(flat, loss=None, group=None):
+    """Sum a flat gradient tensor (+ the loss scalar, carried as one extra element) over the ranks
+    with ONE collective; returns (flat, loss).  No-op without an initialised process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return flat, loss
+    buf = flat if loss is None else torch.cat([flat.reshape(-1), loss.reshape(1).to(flat)])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    if loss is None:
+        return buf, None
+    return buf[:-1].view_as(flat), buf[-1]
+
+
 def allreduce_gradients(grads, loss=None, group=None):
     """Sum the per-rank gradients (list of tensors shaped like the parameters) and the loss scalar
     with ONE collective on one flat buffer.  Returns (grads, loss) holding the global sums."""

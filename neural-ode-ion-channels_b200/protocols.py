@@ -165,6 +165,24 @@ def protocol_set(family, per_ms=1):
     return out
 
 
+def concatenate_sweeps(sweeps, gap_ms=None):
+    """Sweeps of one protocol laid end to end on ONE strictly increasing time axis, the way the
+    real-data files hold them (``train-r1.py:80-94``: e.g. the 7 sweeps of Pr3 are one CSV, integrated
+    by a single ``odeint`` call whose state carries across sweeps and sliced into ``l = len / 7``
+    pieces afterwards, ``train-r1.py:313-329``).  ``sweeps``: list of ``(name, t, v, t_out)`` as
+    returned by ``protocol_set``; sweep k is shifted by k x (duration + one sample period).
+    Returns ``(t_table, v_table, t_out, n_sweeps)``."""
+    ts, vs, outs, off = [], [], [], 0.0
+    for _, t, v, t_out in sweeps:
+        t = np.asarray(t, dtype=np.float64)
+        dt = float(t[1] - t[0]) if gap_ms is None else float(gap_ms)
+        ts.append(t - t[0] + off)
+        vs.append(np.asarray(v, dtype=np.float64))
+        outs.append(np.asarray(t_out, dtype=np.float64) - t[0] + off)
+        off += float(t[-1] - t[0]) + dt
+    return np.concatenate(ts), np.concatenate(vs), np.concatenate(outs), len(sweeps)
+
+
 def compact_table(t, v):
     """Drop interior samples of runs where V is *exactly* constant.  scipy's linear ``interp1d``
     evaluates ``slope * (x - x_lo) + y_lo`` with ``slope == 0`` on such a run, so the compacted

@@ -34,6 +34,9 @@ for _ in range(2):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
     opts = {'check_status': False, 'tensor_cores': not os.environ.get('NO_TC'),
+                                   'tc_timing': bool(os.environ.get('TC_TIMING')),
+                                   'tc_groups': int(os.environ.get('TC_GROUPS', '0')),
+                                   'ping_pong': {'1': True, '0': False}.get(os.environ.get('PP', ''), None),
             'lane_pool': {'1': True, '0': False}.get(os.environ.get('POOL', ''), None)}
     if cap:
         opts['ckpt_cap'] = cap

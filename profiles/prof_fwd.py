@@ -29,7 +29,10 @@ with torch.no_grad():
         e0.record()
         r = ikr.integrate(f, y0, t, want_y=False, want_current=False, data=torch.zeros(len(t)),
                           options={'lane_pool': {'1': True, '0': False}.get(os.environ.get('POOL', ''), None),
-                                   'tensor_cores': not os.environ.get('NO_TC')})
+                                   'tensor_cores': not os.environ.get('NO_TC'),
+                                   'tc_timing': bool(os.environ.get('TC_TIMING')),
+                                   'tc_groups': int(os.environ.get('TC_GROUPS', '0')),
+                                   'ping_pong': {'1': True, '0': False}.get(os.environ.get('PP', ''), None)})
         e1.record()
         torch.cuda.synchronize()
         nfe = int(r.stats[:, 2].sum())

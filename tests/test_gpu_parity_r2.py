@@ -1,0 +1,378 @@
+"""Round-2 GPU parity tests (through the C ABI) that close the gaps of VERDICT r1:
+
+* the bench's stand-in protocols (sinewave, staircase, pr4) against the CPU oracle -- fp32 as shipped
+  on the tensor-core path (MAE <= 5e-5, rk4 window <= 5e-6 and no further from exact arithmetic than
+  the reference's fp32 path) and fp64 step-wise (<= 1e-10);
+* full-trace fp64 parity with the accepted steps replayed into the oracle (north star: traces within
+  10 x atol, loss equal to 1e-8 relative) on one sweep of each of pr3 / pr4 / pr5 / sinewave / APs;
+* the tensor-core backward against oracle autograd at B = 64 and against the FFMA backward on the
+  SAME step checkpoints (isolates the MMA arithmetic from adaptive-step noise);
+* reference-sized long inputs: seven sweeps on one time axis integrated as ONE trajectory
+  (train-r1.py:313-329) and a 480,032-sample uncompactable table (real Pr4 has 464,096);
+* the reference's 92 logged losses ({s1,s2,d1,d2}/log2) with ground truth AND model on the GPU.
+"""
+import copy
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import neural_ode_ion_channels_b200 as ikr
+from neural_ode_ion_channels_b200 import _cabi, protocols
+from neural_ode_ion_channels_b200.adjoint import _run_backward
+from oracle import ref_models as rm
+from oracle import ref_odeint as ro
+from tests import kat
+from tests.test_gpu_backward import _flat, _oracle_grads, _steps
+from tests.test_gpu_forward import _nn, _rel
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _family(fam):
+    idx = {'pr3': 4, 'pr4': 10, 'pr5': 4, 'sinewave': 0, 'aps': 0, 'staircase': 0}[fam]
+    name, t_tab, v_tab, t_out = protocols.protocol_set(fam)[idx]
+    return name, t_tab, v_tab, t_out
+
+
+def _set(funcs, t_tab, v_tab):
+    for f in funcs:
+        f.set_fixed_form_voltage_protocol(t_tab, v_tab)
+
+
+# ---------------------------------------------------------------------------------------------
+# (i) the stand-in protocols of the bench, tensor-core path, fp32 as shipped
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('fam', ['sinewave', 'staircase', 'pr4'])
+def test_standin_fp32_tensor_core_mae_matches_oracle(fam):
+    """Whole sweep, dopri5, fp32 state + fp32 MLP (the bench's configuration): the MAE against a
+    noisy data trace equals the oracle's to 5e-5 (the KAT tolerance: both controllers take their
+    own fp32 step sequences), the traces agree to 2e-4."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn('d1')
+    name, t_tab, v_tab, t_out = _family(fam)
+    _set((func, ofunc), t_tab, v_tab)
+    t = torch.tensor(t_out, dtype=torch.float32)
+    y0 = torch.tensor([[0.02, 0.97]])
+    with torch.no_grad():
+        want = ro.odeint(ofunc, y0, t)
+        res = ikr.integrate(func, y0.cuda(), t, want_current=True, E=-86.0,
+                            data=torch.zeros(len(t)))
+    assert res.geometry['tensor_cores'] and int(res.stats[0, 3]) == 0
+    got = res.y.cpu()
+    v = torch.from_numpy(np.interp(np.asarray(t_out), t_tab, v_tab))
+    i_want = (want[:, 0, 0] * want[:, 0, 1]).double() * (v + 86.0)
+    i_got = res.current[:, 0].cpu().double()
+    rng = np.random.RandomState(1)
+    data = i_want + torch.from_numpy(rng.normal(0, 0.1, len(t)))
+    mae_want = (i_want - data).abs().mean().item()
+    mae_got = (i_got - data).abs().mean().item()
+    assert abs(mae_got - mae_want) <= 5e-5, (fam, mae_got, mae_want)
+    assert (got - want).abs().max().item() <= 2e-4, fam
+
+
+@pytest.mark.parametrize('fam,t0', [('sinewave', 4000.0), ('staircase', 300.0), ('pr4', 650.0)])
+def test_standin_rk4_window_tensor_core_fp32(fam, t0):
+    """Fixed grid through the active part of each stand-in (sine segment / ramp / inactivation
+    step): no accept-reject decisions, so this is a clean check of the MLP arithmetic.  240 steps of an
+    fp32 state: (1) the tensor-core trace stays within 5e-6 abs of the oracle's fp32 torch MLP;
+    (2) measured against EXACT arithmetic (the oracle with fp64 state and fp64 MLP on the same grid)
+    the tensor-core path is at least as accurate as the reference's own fp32 path -- two fp32-level
+    evaluations of the same network differ from each other by as much as each differs from the
+    truth, which is what the 2-3e-6 of (1) is (measured: FFMA2 kernel 1e-7 from the fp32 oracle,
+    whose k-ascending FMA chain it happens to reproduce)."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn('d1')
+    _, ofunc64 = _nn('d1', double=True)
+    name, t_tab, v_tab, _ = _family(fam)
+    _set((func, ofunc, ofunc64), t_tab, v_tab)
+    t = torch.linspace(t0, t0 + 120.0, 241)
+    y0 = torch.tensor([[0.3, 0.6], [0.02, 0.97]])
+    with torch.no_grad():
+        res = ikr.integrate(func, y0.cuda(), t, method='rk4')
+        assert res.geometry['tensor_cores']
+        for b in range(2):
+            want = ro.odeint(ofunc, y0[b:b + 1], t, method='rk4')
+            truth = ro.odeint(ofunc64, y0[b:b + 1].double(), t.double(), method='rk4')
+            got = res.y[:, b:b + 1].cpu()
+            err_tc = (got - want).abs().max().item()
+            tc_truth = (got.double() - truth).abs().max().item()
+            ref_truth = (want.double() - truth).abs().max().item()
+            assert err_tc < 5e-6, (fam, b, err_tc)
+            assert tc_truth <= 1.5 * ref_truth + 5e-7, (fam, b, tc_truth, ref_truth)
+
+
+def _stepwise_worst(func, ofunc, t, y0, n_sample=40):
+    """Every sampled accepted step of the CUDA run restarted on the oracle from its checkpoint."""
+    with torch.no_grad():
+        res = ikr.integrate(func, y0.cuda(), t, want_ckpt=True, options={'ckpt_cap': 8192})
+    stats = res.stats.cpu().numpy()
+    ck_t, ck_y, y_gpu = res.ckpt[0].cpu(), res.ckpt[1].cpu(), res.y.cpu()
+    solver = ro.Dopri5(ofunc, y0[:1], 1e-7, 1e-9)
+    worst = 0.0
+    for b in range(y0.shape[0]):
+        n_acc = int(stats[b, 0])
+        assert stats[b, 3] == 0 and n_acc > 20
+        for j in range(0, n_acc - 1, max(1, n_acc // n_sample)):
+            ts, dt = ck_t[j, b, 0], ck_t[j, b, 1]
+            yy = ck_y[j, b, :2].reshape(1, 2)
+            ff = ck_y[j, b, [2, 9]].reshape(1, 2)
+            with torch.no_grad():
+                y1, f1, err, k = solver._rk_step(yy, ff, ts, dt, ts + dt)
+                coef = solver._mid_fit(yy, y1, k, dt)
+            want = torch.cat([y1.reshape(-1), f1.reshape(-1)]).numpy()
+            worst = max(worst, _rel(ck_y[j + 1, b, [0, 1, 2, 9]].numpy(), want, 1e-30))
+            for i in torch.nonzero((t > ts) & (t <= ts + dt)).reshape(-1).tolist():
+                with torch.no_grad():
+                    yi = ro._dense_eval(coef, ts, ts + dt, t[i]).reshape(-1).numpy()
+                worst = max(worst, _rel(y_gpu[i, b].numpy(), yi, 1e-30))
+    return worst
+
+
+@pytest.mark.parametrize('fam', ['sinewave', 'staircase', 'pr4'])
+def test_standin_fp64_stepwise_parity(fam):
+    torch.set_num_threads(1)
+    func, ofunc = _nn('d2', double=True)
+    name, t_tab, v_tab, t_out = _family(fam)
+    _set((func, ofunc), t_tab, v_tab)
+    t = torch.tensor(t_out, dtype=torch.float64)
+    y0 = torch.tensor([[0.02, 0.97]], dtype=torch.float64)
+    assert _stepwise_worst(func, ofunc, t, y0) <= 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# (ii) full-trace fp64 parity with replayed steps: traces <= 10 x atol, loss <= 1e-8 relative
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('fam', ['pr3', 'pr4', 'pr5', 'sinewave', 'aps'])
+def test_full_trace_fp64_replay_parity(fam):
+    """The oracle takes exactly the steps the CUDA run accepted (its `replay` test hook, see
+    oracle/ref_odeint.py): with the ill-conditioned controller out of the comparison, the whole
+    (a, r) trace must agree within 10 x atol = 1e-8 and the MAE loss to 1e-8 relative."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn('d1', double=True)
+    name, t_tab, v_tab, t_out = _family(fam)
+    _set((func, ofunc), t_tab, v_tab)
+    t = torch.tensor(t_out, dtype=torch.float64)
+    y0 = torch.tensor([[0.02, 0.97]], dtype=torch.float64)
+    rng = np.random.RandomState(2)
+    data = torch.from_numpy(rng.normal(0, 0.1, len(t)))
+    with torch.no_grad():
+        res = ikr.integrate(func, y0.cuda(), t, want_ckpt=True, data=data, E=-86.0,
+                            options={'ckpt_cap': 8192})
+        assert int(res.stats[0, 3]) == 0
+        want = ro.odeint(ofunc, y0, t, options={'replay': _steps(res)[0]})
+    got = res.y.cpu()
+    assert (got - want).abs().max().item() <= 1e-8, fam
+    v = torch.from_numpy(np.interp(np.asarray(t_out), t_tab, v_tab))
+    i_want = want[:, 0, 0] * want[:, 0, 1] * (v + 86.0)
+    mae_want = (i_want - data).abs().mean().item()
+    mae_got = float(res.sae[0]) / len(t)
+    assert abs(mae_got - mae_want) <= 1e-8 * abs(mae_want), (fam, mae_got, mae_want)
+    sse_want = ((i_want - data) ** 2).sum().item()
+    assert abs(float(res.sse[0]) - sse_want) <= 1e-8 * sse_want
+
+
+# ---------------------------------------------------------------------------------------------
+# (iii) tensor-core backward
+# ---------------------------------------------------------------------------------------------
+def _segments(n=200, L=5):
+    segs, o = [('w0', 0, 2 * n), ('b0', 2 * n, 3 * n)], 3 * n
+    for l in range(L):
+        segs += [('W%d' % (l + 1), o, o + n * n), ('b%d' % (l + 1), o + n * n, o + n * n + n)]
+        o += n * n + n
+    return segs + [('w_last', o, o + n), ('b_last', o + n, o + n + 1)]
+
+
+def _staircase_window(B, seed, t0=850.0, t1=950.0, n_out=26):
+    """B noisy datasets on the -80 -> +40 mV edge of the staircase stand-in (configs[2] inputs)."""
+    name, t_tab, v_tab, _ = _family('staircase')
+    t = torch.linspace(t0, t1, n_out)
+    rng = np.random.RandomState(seed)
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.9, 1.0, B)], 1),
+                      dtype=torch.float32)
+    data = torch.from_numpy((rng.randn(n_out, B) * 0.1).astype(np.float32))
+    return t_tab, v_tab, t, y0, data
+
+
+def test_tc_backward_vs_oracle_autograd_64_datasets():
+    """configs[2] shape on a window: NN-d (d2 weights), fp32 as shipped, 64 noisy datasets, fused SSE
+    loss; gradient of the tensor-core backward against PyTorch autograd through the oracle with the
+    accepted steps of every lane replayed.  Tolerance per parameter block: 1e-4 of the block's
+    largest entry (measured 2e-6 .. 1e-5: fp32 state, bf16x2 weight-gradient products of 2^-16
+    each), loss 1e-5 relative."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn('d2')
+    B = 64
+    t_tab, v_tab, t, y0, data = _staircase_window(B, 21)
+    _set((func, ofunc), t_tab, v_tab)
+    func.cuda()
+    total, per, grads, res = ikr.loss_and_grad(func, y0.cuda(), t, data, E=-86.0, want_y0=True,
+                                               options={'first_step': 0.05})
+    assert res.geometry['tensor_cores']
+    v = torch.from_numpy(np.interp(t.double().numpy(), t_tab, v_tab))
+
+    def loss_fn(b, yb):
+        cur = (yb[:, 0] * yb[:, 1]).double() * (v + 86.0)
+        return ((cur - data[:, b].double()) ** 2).sum()
+
+    want, want_y0, want_l = _oracle_grads(ofunc, y0, t, _steps(res), 0.05, loss_fn)
+    got = _flat(grads)
+    assert np.abs(per.cpu().numpy() - want_l).max() <= 1e-5 * np.abs(want_l).max()
+    worst = {}
+    for name, lo, hi in _segments():
+        ref = np.abs(want[lo:hi]).max()
+        worst[name] = np.abs(got[lo:hi] - want[lo:hi]).max() / ref
+        assert worst[name] <= 1e-4, (name, worst[name])
+    assert np.abs(res.grad_y0.cpu().numpy() - want_y0).max() <= 1e-4 * np.abs(want_y0).max()
+    print('tc backward vs oracle, worst relative error per block:', json.dumps(worst))
+
+
+@pytest.mark.parametrize('study,B', [('d2', 300), ('d1', 64)])
+def test_tc_backward_equals_ffma_backward_on_identical_checkpoints(study, B):
+    """ONE forward (tensor cores, step checkpoints), then both backward families over the same
+    checkpoints: adaptive-step noise is gone, what is left is the arithmetic of the adjoint MMAs
+    (bf16x3, fp32-faithful) and of the weight-gradient GEMM (bf16x2 products, 2^-16 each, summed in
+    fp32 / fp64).  Every parameter block, grad_y0 and grad_g within 1e-4 of the block maximum."""
+    func, _ = _nn(study)
+    t_tab, v_tab, t, y0, data = _staircase_window(B, 22, n_out=21)
+    _set((func,), t_tab, v_tab)
+    func.cuda()
+    res = ikr.integrate(func, y0.cuda(), t, data=data, E=-86.0, want_y=True, want_ckpt=True,
+                        options={'first_step': 0.05})
+    assert res.geometry['tensor_cores']
+    flat_tc, gy0_tc, gg_tc = _run_backward(func, res, fused_loss=1, want_y0=True, want_g=True)
+    ffma = copy.copy(res)
+    ffma._desc = copy.copy(res._desc)
+    ffma._desc.reserved |= 2                       # FFMA2 backward kernels (no tensor cores)
+    assert _cabi.lib().ikr_uses_tensor_cores(ctypes.byref(ffma._desc)) == 0
+    flat_fm, gy0_fm, gg_fm = _run_backward(func, ffma, fused_loss=1, want_y0=True, want_g=True)
+    a, b = flat_tc.cpu().numpy(), flat_fm.cpu().numpy()
+    assert np.isfinite(a).all() and np.abs(b).max() > 0
+    worst = {}
+    for name, lo, hi in _segments():
+        worst[name] = np.abs(a[lo:hi] - b[lo:hi]).max() / np.abs(b[lo:hi]).max()
+        assert worst[name] <= 1e-4, (name, worst[name])
+    assert (gy0_tc - gy0_fm).abs().max().item() <= 1e-4 * gy0_fm.abs().max().item()
+    assert (gg_tc - gg_fm).abs().max().item() <= 1e-4 * gg_fm.abs().max().item()
+    print('tc vs ffma backward on identical checkpoints:', json.dumps(worst))
+
+
+# ---------------------------------------------------------------------------------------------
+# (iv) reference-sized long inputs
+# ---------------------------------------------------------------------------------------------
+def test_seven_sweeps_as_one_trajectory_fp64_replay():
+    """train-r1.py:313-329: the 7 sweeps of Pr3 sit on one monotone time axis and are integrated by
+    ONE odeint call (state carried across sweeps), then sliced into l = len / 7 pieces.  56,007
+    outputs, fp64, steps replayed into the oracle: trace within 10 x atol; the carried state makes
+    sweep k differ from the same sweep integrated on its own."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn('d1', double=True)
+    sweeps = protocols.protocol_set('pr3')
+    t_tab, v_tab, t_out, n = protocols.concatenate_sweeps(sweeps)
+    assert n == 7 and len(t_out) == 56007 and len(t_tab) == 56007
+    _set((func, ofunc), t_tab, v_tab)
+    t = torch.tensor(t_out, dtype=torch.float64)
+    y0 = torch.tensor([[0.0, 1.0]], dtype=torch.float64)
+    with torch.no_grad():
+        res = ikr.integrate(func, y0.cuda(), t, want_ckpt=True, options={'ckpt_cap': 16384})
+        assert int(res.stats[0, 3]) == 0
+        want = ro.odeint(ofunc, y0, t, options={'replay': _steps(res)[0]})
+    got = res.y.cpu()
+    assert (got - want).abs().max().item() <= 1e-8
+    l = len(t_out) // 7
+    # sweep 4 on its own starts from y0, inside the concatenation from the end state of sweep 3
+    name, t4, v4, to4 = sweeps[4]
+    func.set_fixed_form_voltage_protocol(t4, v4)
+    with torch.no_grad():
+        alone = ikr.odeint(func, y0.cuda(), torch.tensor(to4, dtype=torch.float64)).cpu()
+    assert (alone[:50, 0] - got[4 * l:4 * l + 50, 0]).abs().max().item() > 1e-4
+
+
+def test_uncompactable_480k_sample_table():
+    """Real Pr4 is one 464,096-sample file.  32 sweeps of the Pr4 stand-in on one axis
+    = 480,032 samples at 0.1 ms with measurement-like jitter (nothing for `compact_table` to drop):
+    V(t) lookups bit-exact against numpy at 100,000 random times, and a window 45 s into the table
+    integrates like the oracle (rk4 fp64 <= 1e-10, dopri5 fp64 step-wise <= 1e-10)."""
+    torch.set_num_threads(1)
+    func, ofunc = _nn('d1', double=True)
+    t_tab, v_tab, _, n = protocols.concatenate_sweeps(protocols.protocol_set('pr4') * 2)
+    rng = np.random.RandomState(5)
+    v_tab = v_tab + rng.normal(0, 0.05, len(v_tab))
+    assert len(t_tab) == 480032 >= 464096
+    ct, cv = protocols.compact_table(t_tab, v_tab)
+    assert len(ct) == len(t_tab)
+    _set((func, ofunc), t_tab, v_tab)
+    # table lookups through the C ABI
+    from neural_ode_ion_channels_b200.solver import _DeviceTable
+    tab = _DeviceTable(t_tab, v_tab, torch.device('cuda'), True)
+    io = _cabi.IkrIO()
+    tab.fill(io)
+    q = np.sort(rng.uniform(t_tab[0], t_tab[-1], 100000))
+    q[:3] = (t_tab[0], t_tab[-1], t_tab[123457])
+    q_d = torch.from_numpy(q).cuda()
+    out = torch.empty(len(q), dtype=torch.float64, device='cuda')
+    _cabi.check(_cabi.lib().ikr_interp_protocol(ctypes.byref(io), q_d.data_ptr(), len(q),
+                                                out.data_ptr(), None), 'interp')
+    from scipy.interpolate import interp1d
+    want_v = interp1d(t_tab, v_tab)(q)
+    assert np.array_equal(out.cpu().numpy(), want_v)
+    # a window deep inside the table: sweep 30, around its +50 -> test step edge
+    t0 = 30 * 1500.1 + 650.0
+    t = torch.linspace(t0, t0 + 100.0, 201, dtype=torch.float64)
+    y0 = torch.tensor([[0.3, 0.2]], dtype=torch.float64)
+    with torch.no_grad():
+        want = ro.odeint(ofunc, y0, t, method='rk4').numpy()
+        got = ikr.odeint(func, y0.cuda(), t, method='rk4').cpu().numpy()
+    assert _rel(got, want) <= 1e-10
+    assert _stepwise_worst(func, ofunc, t, y0) <= 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# (v) the reference's 92 logged losses, ground truth and model both on the GPU
+# ---------------------------------------------------------------------------------------------
+def test_all_92_logged_losses_on_the_gpu():
+    """{s1,s2,d1,d2}/log2: 4 studies x 23 protocol rows (train-s1.py:311-329, 431-546).  Ground-truth
+    model (HH for s*, 6-state Markov for d*) and trained NN model are both integrated by this
+    library on the GPU (fp32 state as shipped, fp32 linspace grids), currents formed as the reference
+    does; every logged 6-dp loss reproduced to 5e-5.  Writes the worst delta to gpurun_out/."""
+    worst, rows_done, report = 0.0, 0, []
+    for study in kat.STUDIES:
+        func, _ = _nn(study)
+        for row in kat.KAT[study]:
+            if not row.get('inputs_present', True):
+                continue                      # APs / Sinewave / Staircase rows: CSVs missing
+            t_tab, v_tab, t_out = kat.row_protocol(row)
+            with torch.no_grad():
+                if study in ('s1', 's2'):
+                    p = ikr.PARAMETER_SETS['s']
+                    gt = ikr.integrate_hh([p['p%d' % i] for i in range(1, 9)],
+                                          torch.tensor([[0., 1.]]).cuda(), t_out, (t_tab, v_tab)).y.cpu()
+                    o_gt = gt[:, 0, 0] * gt[:, 0, 1]
+                else:
+                    gt = ikr.integrate_markov(ikr.MARKOV_B06, torch.tensor([[0., 1., 0., 0., 0., 0.]]).cuda(),
+                                              t_out, (t_tab, v_tab)).y.cpu()
+                    o_gt = gt[:, 0, -1]
+                func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+                y = ikr.odeint(func, torch.tensor([[0., 1.]]).cuda(), t_out).cpu()
+            v = func._v(t_out).reshape(-1)
+            i_gt = o_gt * (v + 86)
+            i_nn = y[:, 0, 0] * y[:, 0, 1] * (v + 86)
+            loss = torch.mean(torch.abs(i_nn - i_gt)).item()
+            delta = abs(loss - row['loss'])
+            report.append((study, row['section'], row['name'], row['loss'], loss, delta))
+            worst = max(worst, delta)
+            rows_done += 1
+    assert rows_done == 92
+    out_dir = os.path.join(ROOT, 'gpurun_out')
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, 'r2_kat92_gpu.json'), 'w') as fh:
+        json.dump({'rows': rows_done, 'worst_abs_delta': worst,
+                   'cases': [dict(zip(('study', 'section', 'name', 'logged', 'gpu', 'delta'), r))
+                             for r in report]}, fh, indent=1)
+    bad = [r for r in report if r[5] >= 5e-5]
+    assert not bad, bad[:5]
