@@ -521,7 +521,7 @@ def run_sweep_leg(args, ikr, dev, world, rank):
             opt = torch.optim.Adam(func.net.parameters(), lr=1e-3)
             plist = list(func.net.parameters())
             opts = {'check_status': False, 'ckpt_cap': 1024}
-            evals = 0.0
+            evals = evals_b = 0.0
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             for it in range(args.sweep_iters + 1):        # iteration 0 = warm-up
                 if it == 1:
@@ -533,7 +533,8 @@ def run_sweep_leg(args, ikr, dev, world, rank):
                     p.grad = (g / B).to(p.dtype)
                 opt.step()
                 if it >= 1:
-                    evals += float(res.stats[:, 2].sum() + (6 * res.stats[:, 0] + 1).sum())
+                    evals_b += float((6 * res.stats[:, 0] + 1).sum())
+                    evals += float(res.stats[:, 2].sum()) + float((6 * res.stats[:, 0] + 1).sum())
                 bad = int((res.stats[:, 3] != 0).sum())
                 tcores = bool(res.geometry.get('tensor_cores'))
                 del res
@@ -541,7 +542,8 @@ def run_sweep_leg(args, ikr, dev, world, rank):
             torch.cuda.synchronize()
             ms = ev[0].elapsed_time(ev[1])
             entry.update({'ms': ms, 'evals': evals, 'evals_per_s': evals / (ms * 1e-3),
-                          'tflops': evals / 2.0 * 3 * 2 * macs_of(L, n) / (ms * 1e-3) / 1e12,
+                          # forward eval = 2 MACs FLOP, adjoint eval = 2 x that
+                          'tflops': (evals + evals_b) * 2 * macs_of(L, n) / (ms * 1e-3) / 1e12,
                           'kernel': 'tcgen05' if tcores else ('DFMA' if f64 else 'FFMA2'),
                           'status_bad': bad, 'loss': float(total), 'rank': rank})
         except RuntimeError as exc:   # an unsupported configuration is reported, not hidden

@@ -77,7 +77,11 @@ typedef struct ikr_desc {
                              bit 3: debug, CTA 0 prints its phase clocks (device printf);
                              bits 4-5: epilogue column groups of the tensor-core kernels, 1..3
                              (0 = default 3; fixes the output-layer summation order, i.e. results);
-                             bit 6: never use the two-tile ping-pong kernel; bit 7: force it      */
+                             bit 6: never use the two-tile ping-pong kernel; bit 7: force it;
+                             bit 8: tensor-core forward with the bf16x3 operand split (six MMAs per
+                             fp32 product, any activation range) instead of the default fp16x2
+                             split (three MMAs; hidden activations must stay below 65504 / 16 in
+                             magnitude -- beyond that the lane reports IKR_NONFINITE)               */
 } ikr_desc;
 
 /* One JOB = one protocol table + one batch of trajectories, i.e. the shape of one reference
@@ -151,11 +155,12 @@ int32_t ikr_tile_m(const ikr_desc* d, int32_t n_jobs, const int64_t* B);
  * out[16] = tile_m, threads/CTA, grid, dynamic smem bytes, n_tiles, kc, chunks/layer (k-steps/layer
  * on the tensor-core path), SM count, scheduling (0: tile queue, longest job first; 1: lane pool,
  * slots refill from one trajectory queue; 2: two-tile ping-pong lane pool), kernel launches of
- * one ikr_forward call, tensor-core path (0/1), epilogue column groups, rest reserved (0).          */
+ * one ikr_forward call, tensor-core path (0/1), epilogue column groups, 16-bit MMAs issued per fp32
+ * product on the tensor-core path (3: fp16x2 split, 6: bf16x3 split), rest reserved (0).            */
 int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int64_t out[16]);
 
 /* 1 when ikr_forward will run this configuration on the tcgen05 tensor-core kernel (fp32 MLP with
- * n_nodes <= 200: hidden layers as bf16x3 split MMAs, fp32-faithful), 0 for the FFMA2 / DFMA kernel.
+ * n_nodes <= 200: hidden layers as split-operand MMAs with fp32 accumulation), 0 for the FFMA2 / DFMA kernel.
  * desc->reserved bit 1 opts out. */
 int32_t ikr_uses_tensor_cores(const ikr_desc* d);
 

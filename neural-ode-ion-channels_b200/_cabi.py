@@ -152,4 +152,6 @@ def launch_geometry(desc, B):
             'n_tiles': out[4], 'kc': out[5], 'cpl': out[6], 'sms': out[7],
             'scheduling': ('tile queue (longest job first)', 'lane pool (slots refill from one '
                            'trajectory queue)', 'two-tile ping-pong lane pool')[out[8]],
-            'launches': out[9], 'tensor_cores': bool(out[10]), 'column_groups': out[11]}
+            'launches': out[9], 'tensor_cores': bool(out[10]), 'column_groups': out[11],
+            'mma_products': out[12],
+            'mma_split': {3: 'fp16x2 split', 6: 'bf16x3 split'}.get(out[12], 'none')}

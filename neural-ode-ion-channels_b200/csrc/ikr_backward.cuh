@@ -62,6 +62,9 @@ struct BwdParams {
   int small_stride;
   void* grad_y0;
   void* grad_g;
+  int method;        // 0 dopri5, 1 rk4 (fixed grid, four stages per step)
+  int time_f32;      // rk4: grid arithmetic in fp32
+  int rk4_perturb;   // rk4 `perturb` option
 };
 
 template <typename S, typename W>
@@ -339,6 +342,7 @@ __global__ void __launch_bounds__(512, 1) ikr_adjoint_kernel(const BwdParams p) 
 
   const SolverCfg cfg = p.cfg;
   const bool owner = tid < M;
+  const bool rk4 = p.method == 1;
   const long long jB = p.B;
   const int T = p.T;
   const S* y0 = reinterpret_cast<const S*>(p.y0);
@@ -422,16 +426,26 @@ __global__ void __launch_bounds__(512, 1) ikr_adjoint_kernel(const BwdParams p) 
           ck[2 * i] = v.x; ck[2 * i + 1] = v.y;
         }
         blane_load_step<S>(L, tt.x, tt.y, ck);
-        bdp_seed_step<S>(L, p.t_out, grad);
+        if (rk4) brk4_seed_step<S>(L, p.t_out, p.time_f32 != 0, grad);
+        else bdp_seed_step<S>(L, p.t_out, grad);
       }
 #pragma unroll 1
-      for (int s = 5; s >= 0; --s) {
+      for (int s = (rk4 ? 3 : 5); s >= 0; --s) {
         double nv = 0, ain = 0, up = 0;
-        if (act) bdp_stage_inputs<S>(lanes[tid], cfg, s, &nv, &ain, &up);
+        if (act) {
+          if (rk4) brk4_stage_inputs<S>(lanes[tid], cfg, s, p.time_f32 != 0, p.rk4_perturb != 0, &nv, &ain, &up);
+          else bdp_stage_inputs<S>(lanes[tid], cfg, s, &nv, &ain, &up);
+        }
         const W da = evaluate(act, nv, ain, up);
-        if (act) bdp_reverse_stage<S>(lanes[tid], s, (S)da);
+        if (act) {
+          if (rk4) brk4_reverse_stage<S>(lanes[tid], s, p.time_f32 != 0, (S)da);
+          else bdp_reverse_stage<S>(lanes[tid], s, (S)da);
+        }
       }
-      if (act) bdp_finish_step<S>(lanes[tid]);
+      if (act) {
+        if (rk4) brk4_finish_step<S>(lanes[tid]);
+        else bdp_finish_step<S>(lanes[tid]);
+      }
     }
 
     // f(t[0], y0): once no lane of the tile is still reversing steps
@@ -440,7 +454,20 @@ __global__ void __launch_bounds__(512, 1) ikr_adjoint_kernel(const BwdParams p) 
       const int p1 = owner && lanes[tid].phase == 1 ? 1 : 0;
       const int any0 = __syncthreads_or(p0);
       const int any1 = __syncthreads_or(p1);
-      if (!any0 && any1) {
+      if (!any0 && any1 && rk4) {
+        // fixed grid: there is no separate f(t[0], y0) evaluation, only the first output sample
+        if (p1) {
+          S g0a, g0r;
+          grad(0, &g0a, &g0r);
+          brk4_finish<S>(lanes[tid], g0a, g0r);
+          if (p.grad_y0) {
+            V2 v;
+            v.x = lanes[tid].lya; v.y = lanes[tid].lyr;
+            reinterpret_cast<V2*>(p.grad_y0)[b] = v;
+          }
+          if (p.grad_g) reinterpret_cast<S*>(p.grad_g)[b] = lanes[tid].gsum;
+        }
+      } else if (!any0 && any1) {
         double nv = 0, ain = 0, up = 0;
         S y0a = (S)0;
         if (p1) {

@@ -513,6 +513,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
       }
     } else {
       const SolverCfg cfg = p.cfg;
+      const bool rk4 = p.method == 1;
       const long long jB = p.B;
       const int T = p.T;
       const S* y0 = reinterpret_cast<const S*>(p.y0);
@@ -579,19 +580,29 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
               ck[2 * i] = v.x; ck[2 * i + 1] = v.y;
             }
             blane_load_step<S>(L, tt.x, tt.y, ck);
-            bdp_seed_step<S>(L, p.t_out, grad);
+            if (rk4) brk4_seed_step<S>(L, p.t_out, p.time_f32 != 0, grad);
+            else bdp_seed_step<S>(L, p.t_out, grad);
           }
 #pragma unroll 1
-          for (int s = 5; s >= 0; --s) {
+          for (int s = (rk4 ? 3 : 5); s >= 0; --s) {
             double nv = 0, ain = 0, up = 0;
-            if (act) bdp_stage_inputs_cached<S>(L, cfg, s, &nv, &ain, &up, tcache);
+            if (act) {
+              if (rk4) brk4_stage_inputs<S>(L, cfg, s, p.time_f32 != 0, p.rk4_perturb != 0, &nv, &ain, &up);
+              else bdp_stage_inputs_cached<S>(L, cfg, s, &nv, &ain, &up, tcache);
+            }
             const float da = tc_adj_owner_eval<G>(g, sg, tl, al, tp.stash, stash_slot, p.counters, act, nv,
                                                   ain, up, [&]() {
-                                                    if (act && s > 0) bdp_prefetch_stage_time<S>(L, cfg, s - 1, tcache);
+                                                    if (act && s > 0 && !rk4) bdp_prefetch_stage_time<S>(L, cfg, s - 1, tcache);
                                                   });
-            if (act) bdp_reverse_stage<S>(L, s, (S)da);
+            if (act) {
+              if (rk4) brk4_reverse_stage<S>(L, s, p.time_f32 != 0, (S)da);
+              else bdp_reverse_stage<S>(L, s, (S)da);
+            }
           }
-          if (act) bdp_finish_step<S>(L);
+          if (act) {
+            if (rk4) brk4_finish_step<S>(L);
+            else bdp_finish_step<S>(L);
+          }
         }
 
         // f(t[0], y0): once no lane of the tile is still reversing steps
@@ -600,7 +611,20 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
           const int p1 = L.phase == 1 ? 1 : 0;
           const int any0 = owners_or(p0);
           const int any1 = owners_or(p1);
-          if (!any0 && any1) {
+          if (!any0 && any1 && rk4) {
+            // fixed grid: no separate f(t[0], y0) evaluation, only the first output sample
+            if (p1) {
+              S g0a, g0r;
+              grad(0, &g0a, &g0r);
+              brk4_finish<S>(L, g0a, g0r);
+              if (p.grad_y0) {
+                V2 v;
+                v.x = L.lya; v.y = L.lyr;
+                reinterpret_cast<V2*>(p.grad_y0)[b] = v;
+              }
+              if (p.grad_g) reinterpret_cast<S*>(p.grad_g)[b] = L.gsum;
+            }
+          } else if (!any0 && any1) {
             double nv = 0, ain = 0, up = 0;
             S y0a = (S)0;
             if (p1) {

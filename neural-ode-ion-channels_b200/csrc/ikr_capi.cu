@@ -218,11 +218,16 @@ struct TcPlan {
 
 constexpr int kTcDefaultGroups = 3;
 
-TcPlan make_tc_plan(const ikr_desc* d) {
+// Operand split of the tensor-core FORWARD kernels: fp16x2 (three MMAs per fp32 product) unless
+// desc.reserved bit 8 asks for bf16x3 (six; no range restriction on the activations).  The adjoint /
+// regression kernels always use bf16x3 (gradients span too many decades for fp16).
+int tc_forward_terms(const ikr_desc* d) { return (d->reserved & 256) ? 3 : 2; }
+
+TcPlan make_tc_plan(const ikr_desc* d, int terms = 3) {
   TcPlan t;
   t.ok = false;
   t.smem = 0; t.img_bytes = 0;
-  t.g = tc_geometry(d->n_nodes, d->n_layers);
+  t.g = tc_geometry(d->n_nodes, d->n_layers, terms);
   if (d->mlp_dtype != IKR_F32 || (d->reserved & 2) || d->tile_m > 0) return t;
   if (!(d->negative_slope >= 0.0 && d->negative_slope <= 1.0)) return t;   // epilogues use max(z, slope z)
   if (!tc_geometry_ok(t.g)) return t;
@@ -243,8 +248,9 @@ TcPlan make_tc_plan(const ikr_desc* d) {
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   t.g.stages = stages;
   t.smem = fixed + (size_t)stages * t.g.stage_bytes;
-  t.img_bytes = (size_t)d->n_layers * t.g.KST * t.g.stage_bytes;
-  t.ok = true;
+  // + 512 bytes behind the blocks: per-layer |W| maxima and accumulator scales of the fp16x2 image
+  t.img_bytes = (((size_t)d->n_layers * t.g.KST * t.g.stage_bytes + 255) & ~(size_t)255) + 512;
+  t.ok = d->n_layers <= 64;
   return t;
 }
 
@@ -268,9 +274,9 @@ size_t fwd_fixed_workspace(int n_jobs) {
   return (256 + (size_t)n_jobs * sizeof(FwdJob) + 255) & ~(size_t)255;
 }
 
-template <typename S, int G>
+template <typename S, int G, int TERMS>
 int launch_forward_tc_g(const TcFwdParams& tp, const TcPlan& t, int grid, cudaStream_t st, bool pool) {
-  auto kern = pool ? ikr_forward_tc_pool_kernel<S, G> : ikr_forward_tc_kernel<S, G>;
+  auto kern = pool ? ikr_forward_tc_pool_kernel<S, G, TERMS> : ikr_forward_tc_kernel<S, G, TERMS>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) !=
       cudaSuccess) {
     cudaGetLastError();
@@ -280,11 +286,17 @@ int launch_forward_tc_g(const TcFwdParams& tp, const TcPlan& t, int grid, cudaSt
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
 }
 
+template <typename S, int TERMS>
+int launch_forward_tc_t(const TcFwdParams& tp, const TcPlan& t, int grid, cudaStream_t st, bool pool) {
+  if (t.groups == 1) return launch_forward_tc_g<S, 1, TERMS>(tp, t, grid, st, pool);
+  if (t.groups == 2) return launch_forward_tc_g<S, 2, TERMS>(tp, t, grid, st, pool);
+  return launch_forward_tc_g<S, 3, TERMS>(tp, t, grid, st, pool);
+}
+
 template <typename S>
 int launch_forward_tc(const TcFwdParams& tp, const TcPlan& t, int grid, cudaStream_t st, bool pool) {
-  if (t.groups == 1) return launch_forward_tc_g<S, 1>(tp, t, grid, st, pool);
-  if (t.groups == 2) return launch_forward_tc_g<S, 2>(tp, t, grid, st, pool);
-  return launch_forward_tc_g<S, 3>(tp, t, grid, st, pool);
+  if (t.g.terms == 2) return launch_forward_tc_t<S, 2>(tp, t, grid, st, pool);
+  return launch_forward_tc_t<S, 3>(tp, t, grid, st, pool);
 }
 
 template <typename S, typename W, int TN>
@@ -457,7 +469,7 @@ TcBwdPlan make_tc_bwd_plan(const ikr_desc* d, long long B) {
   TcBwdPlan pl;
   pl.ok = false;
   const TcPlan fw = make_tc_plan(d);
-  if (!fw.ok || !tc_backward_ok(fw.g) || d->method != IKR_DOPRI5) return pl;
+  if (!fw.ok || !tc_backward_ok(fw.g)) return pl;
   pl.g = fw.g;
   pl.sg = tc_stash_geometry(pl.g);
   pl.groups = fw.groups;
@@ -550,6 +562,7 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
   pk.n_seq = 2 * d->n_layers;
   pk.g = pl.g;
   pk.img = reinterpret_cast<uint16_t*>(ws + pl.off_img);
+  pk.absmax = nullptr; pk.scales = nullptr;
   ikr_tc_pack_kernel<<<pl.sms, 256, 0, st>>>(pk);
   if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
 
@@ -571,6 +584,7 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
   p.counters = reinterpret_cast<unsigned long long*>(ws + pl.off_counters);
   p.small_grad = nullptr; p.small_stride = 0;
   p.grad_y0 = bio->grad_y0; p.grad_g = bio->grad_g;
+  p.method = d->method; p.time_f32 = d->time_f32; p.rk4_perturb = d->rk4_perturb;
   tp.g = pl.g;
   tp.sg = pl.sg;
   tp.img = ws + pl.off_img;
@@ -619,7 +633,6 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
 
 int bwd_dispatch(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, void* workspace,
                  size_t workspace_bytes, cudaStream_t st) {
-  if (d->method != IKR_DOPRI5) return IKR_ERR_UNSUPPORTED;
   if (io->B < 1 || io->T < 1 || !io->weights || !io->table_t || !io->table_v || !io->y0 ||
       !io->t_out || !io->stats_out || !io->ckpt_t || !io->ckpt_y || io->ckpt_cap < 1 ||
       !bio->grad_weights)
@@ -666,6 +679,7 @@ int bwd_dispatch(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, voi
   p.small_grad = reinterpret_cast<double*>(ws + pl.off_small);
   p.small_stride = pl.small_stride;
   p.grad_y0 = bio->grad_y0; p.grad_g = bio->grad_g;
+  p.method = d->method; p.time_f32 = d->time_f32; p.rk4_perturb = d->rk4_perturb;
 
   WgradParams wp;
   wp.L = d->n_layers; wp.n = d->n_nodes; wp.npad = g.npad; wp.M = g.M; wp.KC = pl.KC;
@@ -809,7 +823,7 @@ int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int
   if (!valid_desc(d) || n_jobs < 1 || !B || !out) return IKR_ERR_ARG;
   for (int j = 0; j < n_jobs; ++j) if (B[j] < 1) return IKR_ERR_ARG;
   for (int i = 0; i < 16; ++i) out[i] = 0;
-  const TcPlan tcp = make_tc_plan(d);
+  const TcPlan tcp = make_tc_plan(d, tc_forward_terms(d));
   if (tcp.ok) {
     const int sms = device_sms();
     long long tiles = 0, b_total = 0;
@@ -821,9 +835,10 @@ int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int
     out[0] = tl; out[1] = tc_threads(tcp.groups); out[2] = tiles < sms ? tiles : sms; out[3] = (int64_t)tcp.smem;
     out[4] = tiles; out[5] = 16; out[6] = tcp.g.KST; out[7] = sms;
     out[8] = pool ? 1 : 0;
-    out[9] = 2;            // ikr_tc_pack_kernel + the forward kernel
+    out[9] = tcp.g.terms == 2 ? 3 : 2;   // (ikr_tc_absmax_kernel +) ikr_tc_pack_kernel + the forward kernel
     out[10] = 1;
     out[11] = tcp.groups;
+    out[12] = tcp.g.terms == 2 ? 3 : 6;  // 16-bit MMAs per fp32 product
     return 0;
   }
   const bool pool = use_pool(d);
@@ -841,8 +856,8 @@ size_t ikr_workspace_bytes(const ikr_desc* d, int32_t n_jobs, int64_t B_total,
                            int32_t with_backward) {
   if (!valid_desc(d) || n_jobs < 1 || B_total < 1) return 0;
   size_t bytes = fwd_fixed_workspace(n_jobs);
-  const TcPlan tcp = make_tc_plan(d);
-  if (tcp.ok) bytes += (tcp.img_bytes + 255) & ~(size_t)255;   // bf16 weight image of the tcgen05 path
+  const TcPlan tcp = make_tc_plan(d, tc_forward_terms(d));
+  if (tcp.ok) bytes += (tcp.img_bytes + 255) & ~(size_t)255;   // weight image of the tcgen05 path
   if (with_backward) {
     const TcBwdPlan tpl = make_tc_bwd_plan(d, B_total);
     bytes += tpl.ok ? tc_bwd_workspace_bytes(tpl) : bwd_workspace_bytes(d, B_total);
@@ -865,7 +880,7 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
     if (io->T > 2147483647LL || io->G > 2147483647LL) return IKR_ERR_ARG;
     if (io->weights != jobs[0].weights) return IKR_ERR_ARG;
   }
-  const TcPlan tcp = make_tc_plan(d);
+  const TcPlan tcp = make_tc_plan(d, tc_forward_terms(d));
   const size_t need = fwd_fixed_workspace(n_jobs) + (tcp.ok ? tcp.img_bytes : 0);
   if (!workspace || workspace_bytes < need) return IKR_ERR_WORKSPACE;
 
@@ -953,6 +968,15 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
     pk.npad = p.mlp.npad;
     pk.g = tcp.g;
     pk.img = reinterpret_cast<uint16_t*>(img);
+    unsigned char* tail = img + tcp.img_bytes - 512;
+    pk.absmax = reinterpret_cast<unsigned*>(tail);
+    pk.scales = reinterpret_cast<float*>(tail + 256);
+    tp.scales = pk.scales;
+    if (tcp.g.terms == 2) {
+      if (cudaMemsetAsync(tail, 0, 256, st) != cudaSuccess) return IKR_ERR_DEVICE;
+      ikr_tc_absmax_kernel<<<g.sms, 256, 0, st>>>(pk);
+      if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
+    }
     ikr_tc_pack_kernel<<<g.sms, 256, 0, st>>>(pk);
     if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
     if (d->state_dtype == IKR_F32) return launch_forward_tc<float>(tp, tcp, g.grid, st, pool);
@@ -1039,6 +1063,7 @@ int ikr_regression_loss_grad(const ikr_desc* d, const void* weights, const void*
   pk.n_seq = 3 * d->n_layers;
   pk.g = pl.g;
   pk.img = reinterpret_cast<uint16_t*>(ws + r.off_img);
+  pk.absmax = nullptr; pk.scales = nullptr;
   ikr_tc_pack_kernel<<<pl.sms, 256, 0, st>>>(pk);
   if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
 

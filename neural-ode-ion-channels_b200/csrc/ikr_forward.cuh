@@ -255,7 +255,13 @@ __global__ void __launch_bounds__(512, 1) ikr_forward_kernel(const FwdParams p) 
           if (owner) rk4_store_stage<S>(lanes[tid], cfg, s, (double)out);
         }
         if (owner) {
-          rk4_finish_step<S>(lanes[tid], g0, g1, p.time_f32 != 0, job.t_out, T, emit);
+          Lane<S>& L = lanes[tid];
+          if (lane_active(L)) {
+            // step checkpoint for the backward sweep: (g0, g1), y0, k1..k4
+            L.t0 = g0; L.dt = g1;
+            if (!ckpt(L.n_acc, L)) L.status = LANE_CKPT_OVERFLOW;
+          }
+          rk4_finish_step<S>(L, g0, g1, p.time_f32 != 0, job.t_out, T, emit);
         }
       }
     }

@@ -52,18 +52,24 @@ struct TcGeom {
   int tail;          // 1: a final tail step covers the last n % 16 <= 8 features
   int KST;           // steps per layer = KSf + tail = ring stages consumed per layer
   int units;         // epilogue work units: pairs of k-steps (the last one may hold a single k-step)
-  int col_ring;      // TMEM column of the A-operand unit ring: two slots of 48 columns, a unit as
-                     // [a1 | a2 | a3] of 16 columns each (two k-steps) -- 8 each for a single k-step;
-                     // the tail as [a1t | a2t | a1t | a3t] in the first 16 columns of its slot.
+  int terms;         // split terms per fp32 operand: 3 = bf16x3 (six products per fp32 product:
+                     // a1b1 a2b1 a3b1 a1b2 a2b2 a1b3), 2 = fp16x2 (three: a1b1 a2b1 a1b2; operands
+                     // scaled by powers of two into the fp16 range, see tc::split2h)
+  int unit_cols;     // TMEM columns of one unit slot = 16 * terms
+  int ring_slots;    // unit slots of the A-operand ring (2, or 3 when the columns allow it)
+  int col_ring;      // TMEM column of the A-operand unit ring; a unit of two k-steps is laid out as
+                     // [a1 | a2 (| a3)] of 16 columns each -- 8 each for a single k-step; the tail as
+                     // [a1t | a2t | a1t | a3t] (bf16x3) or [a1t | a2t] (fp16x2) at the start of its slot.
                      // Columns [0, NP) and [NP, 2 NP) are the two D accumulators.
   int cols;          // TMEM columns used
-  int block_bytes;   // one B block: NP x 16 bf16 = NP * 32 bytes
-  int stage_bytes;   // one k-step: 3 blocks
+  int block_bytes;   // one B block: NP x 16 16-bit values = NP * 32 bytes
+  int stage_bytes;   // one k-step: `terms` blocks
   int stages;        // ring depth
-  int small_elems;   // zero-padded small-parameter block: (4 + L) NP + 8 floats
+  int small_elems;   // zero-padded small-parameter block: (4 + L) NP + 8 floats, then L per-layer
+                     // accumulator scales (1 for bf16x3), padded to 8
 };
 
-__host__ __device__ inline TcGeom tc_geometry(int n, int L) {
+__host__ __device__ inline TcGeom tc_geometry(int n, int L, int terms = 3) {
   TcGeom g;
   g.n = n; g.L = L;
   g.NP = (n + 15) / 16 * 16;
@@ -72,18 +78,26 @@ __host__ __device__ inline TcGeom tc_geometry(int n, int L) {
   g.tail = (rem > 0 && rem <= 8) ? 1 : 0;
   g.KST = g.KSf + g.tail;
   g.units = (g.KSf + 1) / 2;
+  g.terms = terms;
+  g.unit_cols = 16 * terms;
   g.col_ring = 2 * g.NP;
-  g.cols = g.col_ring + 96;
+  g.ring_slots = (terms == 2 && g.col_ring + 3 * g.unit_cols <= 512) ? 3 : 2;
+  g.cols = g.col_ring + g.ring_slots * g.unit_cols;
   g.block_bytes = g.NP * 32;
-  g.stage_bytes = 3 * g.block_bytes;
+  g.stage_bytes = terms * g.block_bytes;
   g.stages = 0;
-  g.small_elems = (4 + L) * g.NP + 8;
+  g.small_elems = (4 + L) * g.NP + 8 + (L + 7) / 8 * 8;
   return g;
 }
+// index of the accumulator scale of hidden layer l (0-based) in the small-parameter block
+__host__ __device__ inline int tc_scale_index(const TcGeom& g, int l) { return (4 + g.L) * g.NP + 8 + l; }
+// the A operand of the fp16x2 path carries 2^kTcActShift x the activation (exact), so that small
+// LeakyReLU outputs keep their second term in the normal fp16 range; |h| must stay below 65504 / 16
+constexpr int kTcActShift = 4;
 __host__ __device__ inline bool tc_geometry_ok(const TcGeom& g) {
   return g.n >= 16 && g.NP <= 256 && g.cols <= (int)tc::kTmemCols && g.KST >= 1;
 }
-// ---- weight image: [layer][k-step][block 0..2][NP x 16 bf16 in core-matrix order] -----------------
+// ---- weight image: [layer][k-step][block 0..terms-1][NP x 16 16-bit values in core-matrix order] -----
 struct TcPackParams {
   const float* wn;   // [L][n][npad] rows = output features (packed-parameter section off_wn)
   const float* wt;   // [L][n][npad] rows = input features  (section off_wt = W^T), backward images
@@ -92,6 +106,11 @@ struct TcPackParams {
                      // 3L (regression): forward images twice, then the transposed ones
   TcGeom g;
   uint16_t* img;
+  // fp16x2 images (g.terms == 2, forward only): per-layer |W| maximum as float bits (filled by
+  // ikr_tc_absmax_kernel, zeroed by the caller before) and the accumulator scales 2^-k_l the
+  // forward kernel multiplies D with (written by this kernel, [n_seq] floats)
+  unsigned* absmax;
+  float* scales;
 };
 
 __device__ __forceinline__ uint16_t bf16_term(float w, int term) {
@@ -103,36 +122,87 @@ __device__ __forceinline__ uint16_t bf16_term(float w, int term) {
   }
   return (uint16_t)h;
 }
+__device__ __forceinline__ uint16_t f16_term(float w, int term) {
+  uint32_t h = tc::pack_f16x2(w, 0.0f);
+  if (term == 0) return (uint16_t)(h & 0xFFFFu);
+  float lo, hi;
+  tc::u2(tc::unpack_f16x2(h), lo, hi);
+  return (uint16_t)(tc::pack_f16x2(w - lo, 0.0f) & 0xFFFFu);
+}
+// exponent k of the power-of-two weight scale of a layer: max |W| 2^k in [2^13, 2^14)
+__device__ __forceinline__ int tc_weight_shift(unsigned absmax_bits) {
+  const float m = __uint_as_float(absmax_bits);
+  if (!(m > 0.0f) || !isfinite(m)) return 0;
+  int e;
+  frexpf(m, &e);            // m = f 2^e, f in [0.5, 1)
+  int k = 14 - e;
+  return k < -100 ? -100 : (k > 100 ? 100 : k);
+}
+
+// per-layer maximum of |W| (positive floats order like their bit patterns)
+__global__ void ikr_tc_absmax_kernel(const TcPackParams p) {
+  const TcGeom& g = p.g;
+  const long long per = (long long)g.n * g.n;
+  const long long total = (long long)g.L * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(i / per);
+    const long long r = i - l * per;
+    const int o = (int)(r / g.n), k = (int)(r - (long long)o * g.n);
+    const float w = fabsf(p.wn[(long long)l * g.n * p.npad + (long long)o * p.npad + k]);
+    unsigned m = __float_as_uint(w);
+    const unsigned mask = __activemask();
+    const int l0 = __shfl_sync(mask, l, __ffs(mask) - 1);
+    if (__all_sync(mask, l == l0)) {
+      m = __reduce_max_sync(mask, m);
+      if ((int)(threadIdx.x & 31) == __ffs(mask) - 1) atomicMax(&p.absmax[l], m);
+    } else {
+      atomicMax(&p.absmax[l], m);          // a warp that straddles two layers
+    }
+  }
+}
 
 // B operand image of layer-MMA number `seq`: B[row][k] = src[row][k], src = W_l (forward: D = A W_l^T)
 // or W_l^T (backward: D = A W_l)
 __global__ void ikr_tc_pack_kernel(const TcPackParams p) {
   const TcGeom& g = p.g;
+  const int T = g.terms;
   const long long per_block = (long long)g.NP * 16;
-  const long long total = (long long)p.n_seq * g.KST * 3 * per_block;
+  const long long total = (long long)p.n_seq * g.KST * T * per_block;
+  if (T == 2 && blockIdx.x == 0 && (int)threadIdx.x < p.n_seq)
+    p.scales[threadIdx.x] = ldexpf(1.0f, -tc_weight_shift(p.absmax[threadIdx.x % g.L]));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int kk = (int)(i % 16);
     const int o = (int)((i / 16) % g.NP);
     const long long blk = i / per_block;
-    const int c = (int)(blk % 3);
-    const int step = (int)((blk / 3) % g.KST);
-    const int seq = (int)(blk / (3LL * g.KST));
+    const int c = (int)(blk % T);
+    const int step = (int)((blk / T) % g.KST);
+    const int seq = (int)(blk / ((long long)T * g.KST));
     const int n_fwd = p.n_seq == 3 * g.L ? 2 * g.L : g.L;
     const float* src = seq < n_fwd ? p.wn + (long long)(seq % g.L) * g.n * p.npad
                                    : p.wt + (long long)(p.n_seq - 1 - seq) * g.n * p.npad;
     int k, term;
+    bool zero = false;
     if (step < g.KSf) {
       k = 16 * step + kk;
       term = c;
-    } else {
+    } else if (T == 3) {
       k = 16 * g.KSf + (kk & 7);
       term = c == 0 ? 0 : (c == 1 ? 1 : (kk < 8 ? 2 : 0));
+    } else {
+      // fp16x2 tail, A block [a1t | a2t]: block 0 = [b1t | b1t], block 1 = [b2t | 0]
+      k = 16 * g.KSf + (kk & 7);
+      term = c;
+      zero = c == 1 && kk >= 8;
     }
     float w = 0.0f;
-    if (o < g.n && k < g.n) w = src[(long long)o * p.npad + k];
+    if (!zero && o < g.n && k < g.n) w = src[(long long)o * p.npad + k];
     const long long byte = (long long)(o >> 3) * 256 + (kk >> 3) * 128 + (o & 7) * 16 + (kk & 7) * 2;
-    p.img[(blk * g.block_bytes + byte) >> 1] = bf16_term(w, term);
+    uint16_t v;
+    if (T == 3) v = bf16_term(w, term);
+    else v = f16_term(ldexpf(w, tc_weight_shift(p.absmax[seq % g.L])), term);
+    p.img[(blk * g.block_bytes + byte) >> 1] = v;
   }
 }
 
@@ -161,7 +231,8 @@ struct TcFwdParams {
                          // would otherwise leave SMs idle); MG / NG / n_worker_warps unused
   TcGeom g;
   const void* img;       // weight image written by ikr_tc_pack_kernel
-  int timing;            // debug: block 0 prints its phase clocks (IKR_TC_TIMING=1)
+  const float* scales;   // fp16x2: per-layer accumulator scales 2^-k_l written by ikr_tc_pack_kernel
+  int timing;            // debug: block 0 prints its phase clocks (desc.reserved bit 3)
 };
 
 // named barriers: 1 = every lane thread (128 G), 2 = the 128 owner threads
@@ -221,14 +292,14 @@ __device__ __forceinline__ float tc_leaky(float x, float slope) { return x > 0.0
 constexpr unsigned kTcStaggerNs = IKR_TC_STAGGER_NS;   // start delay per column group after d_ready
 constexpr int kTcMaxUnits = 8;     // NP <= 208: at most 7 units of two K-steps + the tail
 __device__ __forceinline__ uint32_t tc_unit_slot_col(const TcGeom& g, unsigned gi) {
-  return (uint32_t)g.col_ring + 48u * (gi & 1u);
+  return (uint32_t)g.col_ring + (uint32_t)g.unit_cols * (gi % (unsigned)g.ring_slots);
 }
 __device__ __forceinline__ void tc_unit_acquire(const TcGeom& g, const TcLane& tl, unsigned gi) {
-  const unsigned UT = (unsigned)(g.units + g.tail);
-  // UT == 1: unit gi - 2 belongs to a pass whose D this thread has already consumed (all done), and a
+  const unsigned UT = (unsigned)(g.units + g.tail), R = (unsigned)g.ring_slots;
+  // UT < R: unit gi - R belongs to a pass whose D this thread has already consumed (all done), and a
   // parity wait two phases behind the barrier would alias
-  if (gi >= 2u && UT >= 2u) {
-    const unsigned prev = gi - 2u;
+  if (gi >= R && UT >= R) {
+    const unsigned prev = gi - R;
     mbar_wait(&tl.unit_done[prev % UT], (prev / UT) & 1u);
     tc::fence_after_sync();
   }
@@ -247,33 +318,45 @@ __device__ __forceinline__ int tc_units_total(const TcGeom& g) { return g.units 
 // (raw fp32 bits: D columns, or layer-0 sums), get bias + LeakyReLU, and either become a unit of the
 // next A operand (three bf16 terms: one 16 NK-column store for [a1 | a2], one 8 NK-column store for
 // a3, into ring slot `gi`) or are reduced against w_last.
-template <int NK>
+template <int NK, int TERMS = 3>
 __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl, int u, unsigned gi,
                                                const float* bias, uint32_t (&v)[16 * NK], bool last,
-                                               const float* wl, float (&s)[4]) {
+                                               const float* wl, float (&s)[4], float dscale = 1.0f) {
   const int c0 = 32 * u;
   const tc::f32x2_t slope2 = tc::p2(tl.slope, tl.slope);
+  const tc::f32x2_t ds2 = tc::p2(dscale, dscale);
   tc::f32x2_t h[8 * NK];
 #pragma unroll
   for (int q = 0; q < 4 * NK; ++q) {
     const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-    h[2 * q] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
-                                   tc::p2(bb.x, bb.y)), slope2);
-    h[2 * q + 1] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])),
-                                       tc::p2(bb.z, bb.w)), slope2);
+    const tc::f32x2_t d0 = tc::p2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]));
+    const tc::f32x2_t d1 = tc::p2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+    if (TERMS == 3) {
+      h[2 * q] = tc::leaky2(tc::add2(d0, tc::p2(bb.x, bb.y)), slope2);
+      h[2 * q + 1] = tc::leaky2(tc::add2(d1, tc::p2(bb.z, bb.w)), slope2);
+    } else {
+      // fp16x2: D carries 2^(k_l + 4) x the pre-activation sum, the bias is stored x 16:
+      // z' = D 2^-k_l + 16 b = 16 z exactly (powers of two), h' = LeakyReLU(z') = 16 h
+      h[2 * q] = tc::leaky2(tc::fma2(d0, ds2, tc::p2(bb.x, bb.y)), slope2);
+      h[2 * q + 1] = tc::leaky2(tc::fma2(d1, ds2, tc::p2(bb.z, bb.w)), slope2);
+    }
   }
   if (!last) {
+    // the split arithmetic comes BEFORE the slot wait: it runs while the MMAs still read the slot
     uint32_t w12[16 * NK], w3[8 * NK];
 #pragma unroll
-    for (int q = 0; q < 8 * NK; ++q) tc::split3t(h[q], w12[q], w12[8 * NK + q], w3[q]);
+    for (int q = 0; q < 8 * NK; ++q) {
+      if (TERMS == 3) tc::split3t(h[q], w12[q], w12[8 * NK + q], w3[q]);
+      else tc::split2h(h[q], w12[q], w12[8 * NK + q]);
+    }
     tc_unit_acquire(g, tl, gi);
     const uint32_t dst = tl.taddr + tc_unit_slot_col(g, gi);
     if (NK == 2) {
       tc::st32(dst, reinterpret_cast<uint32_t(&)[32]>(w12));
-      tc::st16(dst + 32, reinterpret_cast<uint32_t(&)[16]>(w3));
+      if (TERMS == 3) tc::st16(dst + 32, reinterpret_cast<uint32_t(&)[16]>(w3));
     } else {
       tc::st16(dst, reinterpret_cast<uint32_t(&)[16]>(w12));
-      tc::st8(dst + 16, reinterpret_cast<uint32_t(&)[8]>(w3));
+      if (TERMS == 3) tc::st8(dst + 16, reinterpret_cast<uint32_t(&)[8]>(w3));
     }
     tc_unit_publish(g, tl, gi);
   } else {
@@ -291,29 +374,42 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
   }
 }
 // the 8 tail features (columns 16 KSf ..): blocks [a1t | a2t | a1t | a3t] in one 16-column store
+// (bf16x3) or [a1t | a2t] in one 8-column store (fp16x2)
+template <int TERMS = 3>
 __device__ __forceinline__ void tc_tail_finish(const TcGeom& g, const TcLane& tl, unsigned gi,
                                                const float* bias, uint32_t (&v)[8], bool last,
-                                               const float* wl, float (&s)[4]) {
+                                               const float* wl, float (&s)[4], float dscale = 1.0f) {
   const int c0 = 16 * g.KSf;
   const tc::f32x2_t slope2 = tc::p2(tl.slope, tl.slope);
+  const tc::f32x2_t ds2 = tc::p2(dscale, dscale);
   tc::f32x2_t h[4];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-    h[2 * q] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
-                                   tc::p2(bb.x, bb.y)), slope2);
-    h[2 * q + 1] = tc::leaky2(tc::add2(tc::p2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])),
-                                       tc::p2(bb.z, bb.w)), slope2);
+    const tc::f32x2_t d0 = tc::p2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]));
+    const tc::f32x2_t d1 = tc::p2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+    if (TERMS == 3) {
+      h[2 * q] = tc::leaky2(tc::add2(d0, tc::p2(bb.x, bb.y)), slope2);
+      h[2 * q + 1] = tc::leaky2(tc::add2(d1, tc::p2(bb.z, bb.w)), slope2);
+    } else {
+      h[2 * q] = tc::leaky2(tc::fma2(d0, ds2, tc::p2(bb.x, bb.y)), slope2);
+      h[2 * q + 1] = tc::leaky2(tc::fma2(d1, ds2, tc::p2(bb.z, bb.w)), slope2);
+    }
   }
   if (!last) {
     uint32_t t[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      tc::split3t(h[q], t[q], t[4 + q], t[12 + q]);
-      t[8 + q] = t[q];
+      if (TERMS == 3) {
+        tc::split3t(h[q], t[q], t[4 + q], t[12 + q]);
+        t[8 + q] = t[q];
+      } else {
+        tc::split2h(h[q], t[q], t[4 + q]);
+      }
     }
     tc_unit_acquire(g, tl, gi);
-    tc::st16(tl.taddr + tc_unit_slot_col(g, gi), t);
+    if (TERMS == 3) tc::st16(tl.taddr + tc_unit_slot_col(g, gi), t);
+    else tc::st8(tl.taddr + tc_unit_slot_col(g, gi), reinterpret_cast<uint32_t(&)[8]>(t));
     tc_unit_publish(g, tl, gi);
   } else {
 #pragma unroll
@@ -373,7 +469,7 @@ __device__ __forceinline__ uint32_t tc_wait_d(const TcGeom& g, TcLane& tl, bool 
 // partial output sums land in tl.part (caller syncs).  Group c produces the units u = c (mod G) of
 // every pass.  `hook` runs after this thread's layer-0 units are published, i.e. while the MMAs of
 // layer 1 execute: the owners use it to compute time-only RHS terms of the next stage ahead.
-template <int G, typename Hook = TcNoHook>
+template <int G, int TERMS = 3, typename Hook = TcNoHook>
 __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook hook = Hook()) {
   const int NP = g.NP;
   const float2 in = *reinterpret_cast<const float2*>(tl.xin + 2 * tl.lane);
@@ -392,16 +488,16 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
         if (2 * u + 1 < g.KSf) {
           uint32_t v[32];
           tc_layer0_sums<32>(tl, NP, 32 * u, nv, a, v);
-          tc_unit_finish<2>(g, tl, u, gi, b0, v, false, wl, s);
+          tc_unit_finish<2, TERMS>(g, tl, u, gi, b0, v, false, wl, s);
         } else {
           uint32_t v[16];
           tc_layer0_sums<16>(tl, NP, 32 * u, nv, a, v);
-          tc_unit_finish<1>(g, tl, u, gi, b0, v, false, wl, s);
+          tc_unit_finish<1, TERMS>(g, tl, u, gi, b0, v, false, wl, s);
         }
       } else {
         uint32_t v[8];
         tc_layer0_sums<8>(tl, NP, 16 * g.KSf, nv, a, v);
-        tc_tail_finish(g, tl, gi, b0, v, false, wl, s);
+        tc_tail_finish<TERMS>(g, tl, gi, b0, v, false, wl, s);
       }
     }
     tl.unit_idx += (unsigned)UT;
@@ -412,6 +508,7 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
   for (int layer = 0; layer < g.L; ++layer) {
     const float* bias = tl.sp + (size_t)(3 + layer) * NP;
     const bool last = layer + 1 == g.L;
+    const float dscale = TERMS == 3 ? 1.0f : tl.sp[tc_scale_index(g, layer)];
     const uint32_t dcol = tc_wait_d(g, tl, !last);   // the output layer produces no units: no stagger
     { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
     for (int u = tl.group; u < UT; u += G) {
@@ -421,18 +518,18 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
           uint32_t v[32];
           tc::ld32(tl.taddr + dcol + 32 * u, v);
           tc::wait_ld();
-          tc_unit_finish<2>(g, tl, u, gi, bias, v, last, wl, s);
+          tc_unit_finish<2, TERMS>(g, tl, u, gi, bias, v, last, wl, s, dscale);
         } else {
           uint32_t v[16];
           tc::ld16(tl.taddr + dcol + 32 * u, v);
           tc::wait_ld();
-          tc_unit_finish<1>(g, tl, u, gi, bias, v, last, wl, s);
+          tc_unit_finish<1, TERMS>(g, tl, u, gi, bias, v, last, wl, s, dscale);
         }
       } else {
         uint32_t v[8];
         tc::ld8(tl.taddr + dcol + 16 * g.KSf, v);
         tc::wait_ld();
-        tc_tail_finish(g, tl, gi, bias, v, last, wl, s);
+        tc_tail_finish<TERMS>(g, tl, gi, bias, v, last, wl, s, dscale);
       }
     }
     if (!last) tl.unit_idx += (unsigned)UT;
@@ -445,14 +542,14 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
 }
 
 // Owner-side wrapper: publish the inputs, run the evaluation with the helper groups, collect.
-template <int G, typename Hook = TcNoHook>
+template <int G, int TERMS = 3, typename Hook = TcNoHook>
 __device__ __forceinline__ float tc_owner_eval(const TcGeom& g, TcLane& tl, float nv, float a,
                                                Hook hook = Hook()) {
   *reinterpret_cast<float2*>(tl.xin + 2 * tl.lane) = make_float2(nv, a);
   long long t0 = clock64();
   if (G > 1) lanes_sync<G>();        // inputs visible to the helper groups (cmd word = run)
   { const long long t1 = clock64(); tl.c_sync_a += t1 - t0; }
-  tc_mlp_eval<G, Hook>(g, tl, hook);
+  tc_mlp_eval<G, TERMS, Hook>(g, tl, hook);
   t0 = clock64();
   if (G > 1) lanes_sync<G>();        // partial sums visible
   { const long long t1 = clock64(); tl.c_sync_b += t1 - t0; }
@@ -515,9 +612,11 @@ __device__ __forceinline__ void tc_release_engines(const TcLane& tl) {
 // MMA issuer.  The whole warp runs the loop (warp-uniform control flow and operands => the descriptors
 // live in uniform registers and each MMA is one UTCHMMA); one elected lane issues the MMAs and commits.
 // A layer pass = the units 0 .. UT-1 in order; every unit is issued as soon as its slot is filled.
+template <int TERMS = 3>
 __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& c, uint32_t tbase, bool timing) {
   const unsigned stages = (unsigned)g.stages;
-  const uint32_t idesc = tc::idesc_bf16_f32(kTcM, g.NP);
+  constexpr bool f16 = TERMS == 2;      // compile time: the six / three MMAs stay back-to-back UTCHMMAs
+  const uint32_t idesc = f16 ? tc::idesc_f16_f32(kTcM, g.NP) : tc::idesc_bf16_f32(kTcM, g.NP);
   const uint64_t desc0 = tc::smem_desc(smem_u32(c.ring), 128, 256);
   const uint32_t blk16 = (uint32_t)g.block_bytes >> 4, stage16 = (uint32_t)g.stage_bytes >> 4;
   const int UT = g.units + g.tail;
@@ -528,13 +627,13 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
     const uint32_t dcol = tbase + ((pass & 1u) ? (uint32_t)g.NP : 0u);
     bool first = true;
     for (int u = 0; u < UT; ++u, ++gi) {
-      const unsigned slot = gi & 1u;
+      const unsigned slot = gi % (unsigned)g.ring_slots;
       { const long long c1 = clock64(); e_issue += c1 - ec; ec = c1; }
       mbar_wait(&c.unit_ready[u], pass & 1u);
       if (*c.stop_flag) { stop = true; break; }
       tc::fence_after_sync();
       { const long long c1 = clock64(); e_wait += c1 - ec; if (u == 0) { e_wait0 += c1 - ec; if (pass % (unsigned)g.L == 0) e_wait00 += c1 - ec; } ec = c1; }
-      const uint32_t a_slot = tbase + (uint32_t)g.col_ring + 48u * slot;
+      const uint32_t a_slot = tbase + (uint32_t)g.col_ring + (uint32_t)g.unit_cols * slot;
       const bool is_tail = u >= g.units;
       const int nk = is_tail ? 1 : ((2 * u + 1 < g.KSf) ? 2 : 1);
 #pragma unroll 1
@@ -544,7 +643,19 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
         if (tc::elect_one()) {
           const uint64_t b1 = desc0 + (uint64_t)(s * stage16);
           const uint64_t b2 = b1 + blk16, b3 = b2 + blk16;
-          if (!is_tail) {
+          if (f16) {
+            // fp16x2: a1 b1 + a2 b1 + a1 b2; tail A block [a1t | a2t] against [b1t | b1t], [b2t | 0]
+            if (!is_tail) {
+              const uint32_t dt = nk == 2 ? 16u : 8u;
+              const uint32_t a1 = a_slot + 8u * (uint32_t)jj;
+              tc::mma_ts(dcol, a1, b1, idesc, first ? 0u : 1u);
+              tc::mma_ts(dcol, a1 + dt, b1, idesc, 1u);
+              tc::mma_ts(dcol, a1, b2, idesc, 1u);
+            } else {
+              tc::mma_ts(dcol, a_slot, b1, idesc, first ? 0u : 1u);
+              tc::mma_ts(dcol, a_slot, b2, idesc, 1u);
+            }
+          } else if (!is_tail) {
             const uint32_t dt = nk == 2 ? 16u : 8u;
             const uint32_t a1 = a_slot + 8u * (uint32_t)jj;
             tc::mma_ts(dcol, a1, b1, idesc, first ? 0u : 1u);
@@ -603,7 +714,27 @@ __device__ __forceinline__ void tc_producer_thread(const TcGeom& g, const TcEngi
     mbar_wait(&c.bar_full[q % stages], (q / stages) & 1u);
 }
 
-template <typename S, int G>
+// element i = (row, c) of the zero-padded small-parameter block kept in shared memory: rows w0a | w0b |
+// b0 | L x hidden bias | w_last, then b_last and the per-layer accumulator scales.  The fp16x2 path
+// works on 16 x the activations (kTcActShift): w0, b0 and the hidden biases are stored x 16, w_last
+// x 1/16 (exact), and D of layer l is multiplied by scales[l] = 2^-k_l (the weight image holds
+// W_l 2^k_l, see ikr_tc_pack_kernel).
+template <int TERMS>
+__device__ __forceinline__ float tc_small_param(const TcGeom& g, const MlpView& mlp, const float* P,
+                                                const float* scales, int i, int row, int c, int NP,
+                                                int npad, int n) {
+  const float up = TERMS == 2 ? (float)(1 << kTcActShift) : 1.0f;
+  float v = 0.0f;
+  if (row < 3) { if (c < n) v = P[mlp.off_w0 + (long long)row * npad + c] * up; }
+  else if (row < 3 + g.L) { if (c < n) v = P[mlp.off_bh + (long long)(row - 3) * npad + c] * up; }
+  else if (row == 3 + g.L) { if (c < n) v = P[mlp.off_wl + c] / up; }
+  else if (i == (4 + g.L) * NP) v = P[mlp.off_wl + npad];
+  else if (i >= tc_scale_index(g, 0) && i < tc_scale_index(g, 0) + g.L)
+    v = TERMS == 2 ? scales[i - tc_scale_index(g, 0)] : 1.0f;
+  return v;
+}
+
+template <typename S, int G, int TERMS>
 __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const TcFwdParams tp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const FwdParams& p = tp.f;
@@ -636,12 +767,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
     const int NP = g.NP, npad = p.mlp.npad, n = g.n;
     for (int i = tid; i < g.small_elems; i += tc_threads(G)) {
       const int row = i / NP, c = i - row * NP;
-      float v = 0.0f;
-      if (row < 3) { if (c < n) v = P[p.mlp.off_w0 + (long long)row * npad + c]; }
-      else if (row < 3 + g.L) { if (c < n) v = P[p.mlp.off_bh + (long long)(row - 3) * npad + c]; }
-      else if (row == 3 + g.L) { if (c < n) v = P[p.mlp.off_wl + c]; }
-      else if (i == (4 + g.L) * NP) v = P[p.mlp.off_wl + npad];
-      sp[i] = v;
+      sp[i] = tc_small_param<TERMS>(g, p.mlp, P, tp.scales, i, row, c, NP, npad, n);
     }
   }
   tc::fence_before_sync();
@@ -650,7 +776,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
   const uint32_t tbase = *tmem_slot;
 
   if (warp == kMmaWarp) {
-    tc_mma_warp(g, eng, tbase, tp.timing && blockIdx.x == 0);
+    tc_mma_warp<TERMS>(g, eng, tbase, tp.timing && blockIdx.x == 0);
   } else if (warp == kLoadWarp) {
     if ((tid & 31) == 0) tc_producer_thread(g, eng, reinterpret_cast<const unsigned char*>(tp.img),
                                             (unsigned)(g.L * g.KST));
@@ -677,7 +803,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
       while (true) {
         lanes_sync<G>();
         if (*cmd_exit) break;
-        tc_mlp_eval<G>(g, tl);
+        tc_mlp_eval<G, TERMS>(g, tl);
         lanes_sync<G>();
       }
     } else {
@@ -765,13 +891,13 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
         double nv, ain;
         if (p.method == 0) {
           init_prepare_f0<S>(L, cfg, &nv, &ain);
-          float out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+          float out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain);
           init_store_f0<S>(L, cfg, (double)out);
           if (cfg.first_step > 0) {
             L.dt = cfg.first_step;
           } else {
             init_prepare_f1<S>(L, cfg, &nv, &ain);
-            out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+            out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain);
             init_store_f1<S>(L, cfg, (double)out);
           }
           if (T <= 1 && lane_active(L)) L.status = LANE_DONE;
@@ -785,7 +911,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
             for (int s = 0; s < 6; ++s) {
               dp_prepare_stage_cached<S>(L, cfg, s, &nv, &ain, tcache);
               // while the MMAs of this stage run: V(t) and the HH rates of the next stage
-              out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain, [&]() {
+              out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain, [&]() {
                 if (s < 5 && lane_active(L)) dp_prefetch_stage_time<S>(L, cfg, s + 1, tcache);
               });
               dp_store_stage<S>(L, cfg, s, (double)out);
@@ -800,8 +926,13 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
 #pragma unroll 1
             for (int s = 0; s < 4; ++s) {
               rk4_prepare_stage<S>(L, cfg, s, g0, g1, p.time_f32 != 0, p.rk4_perturb != 0, &nv, &ain);
-              const float out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain);
+              const float out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain);
               rk4_store_stage<S>(L, cfg, s, (double)out);
+            }
+            if (lane_active(L)) {
+              // step checkpoint for the backward sweep: (g0, g1), y0, k1..k4
+              L.t0 = g0; L.dt = g1;
+              if (!ckpt(L.n_acc, L)) L.status = LANE_CKPT_OVERFLOW;
             }
             rk4_finish_step<S>(L, g0, g1, p.time_f32 != 0, job.t_out, T, emit);
           }
@@ -847,7 +978,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
 // refill, runs its two start-up evaluations.  Every lane's arithmetic is independent of its slot,
 // so results are bit-identical to the tile-scheduled kernel.
 // =============================================================================================
-template <typename S, int G>
+template <typename S, int G, int TERMS>
 __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(const TcFwdParams tp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const FwdParams& p = tp.f;
@@ -877,12 +1008,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
     const int NP = g.NP, npad = p.mlp.npad, n = g.n;
     for (int i = tid; i < g.small_elems; i += tc_threads(G)) {
       const int row = i / NP, c = i - row * NP;
-      float v = 0.0f;
-      if (row < 3) { if (c < n) v = P[p.mlp.off_w0 + (long long)row * npad + c]; }
-      else if (row < 3 + g.L) { if (c < n) v = P[p.mlp.off_bh + (long long)(row - 3) * npad + c]; }
-      else if (row == 3 + g.L) { if (c < n) v = P[p.mlp.off_wl + c]; }
-      else if (i == (4 + g.L) * NP) v = P[p.mlp.off_wl + npad];
-      sp[i] = v;
+      sp[i] = tc_small_param<TERMS>(g, p.mlp, P, tp.scales, i, row, c, NP, npad, n);
     }
   }
   // job descriptors: shared-memory copy of the inline table (every lane reads its job every round)
@@ -902,7 +1028,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
   const uint32_t tbase = *tmem_slot;
 
   if (warp == kMmaWarp) {
-    tc_mma_warp(g, eng, tbase, tp.timing && blockIdx.x == 0);
+    tc_mma_warp<TERMS>(g, eng, tbase, tp.timing && blockIdx.x == 0);
   } else if (warp == kLoadWarp) {
     if ((tid & 31) == 0) tc_producer_thread(g, eng, reinterpret_cast<const unsigned char*>(tp.img),
                                             (unsigned)(g.L * g.KST));
@@ -926,7 +1052,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
       while (true) {
         lanes_sync<G>();
         if (*cmd_exit) break;
-        tc_mlp_eval<G>(g, tl);
+        tc_mlp_eval<G, TERMS>(g, tl);
         lanes_sync<G>();
       }
     } else {
@@ -992,7 +1118,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
             else if (what == 2) init_prepare_f0<S>(L, c, &nv, &ain);
             else init_prepare_f1<S>(L, c, &nv, &ain);
           }
-          const float out = tc_owner_eval<G>(g, tl, (float)nv, (float)ain, [&]() {
+          const float out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain, [&]() {
             if (what == 1 && s < 5) dp_prefetch_stage_time<S>(L, c, s + 1, tcache);
           });
           if (what == 1) dp_store_stage<S>(L, c, s, (double)out);

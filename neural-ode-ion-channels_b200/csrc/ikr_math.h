@@ -910,5 +910,89 @@ IKR_HD void bdp_f0_finish(BLane<S>& B, S mlp_grad_a, S g0a, S g0r) {
   B.phase = 2;
 }
 
+// ==========================================================================================
+// Discrete adjoint of one rk4 (3/8 rule) step on the fixed grid -- same semantics as above (PyTorch
+// autograd through torchdiffeq's fixed-grid solver: the grid and the interpolation abscissae are
+// constants).  Checkpoint of a step: ckpt_t = (g0, g1), ckpt_y = (y0; k1..k4 in the first four k
+// slots).  BLane.t0 / BLane.dt hold g0 / g1.  No FSAL: every step starts from y0 alone.
+//   Y_0 = y0, Y_1 = y0 + dt k1 / 3, Y_2 = y0 + dt (k2 - k1 / 3), Y_3 = y0 + dt (k1 - k2 + k3),
+//   y1 = y0 + (k1 + 3 (k2 + k3) + k4) dt / 8;  outputs inside (g0, g1) are y0 + slope (y1 - y0).
+// ==========================================================================================
+template <typename S, typename Grad>
+IKR_HD void brk4_seed_step(BLane<S>& B, const double* t_out, bool tf32, Grad grad) {
+  const double g0 = B.t0, g1 = B.dt;
+  S ly1a = B.lya, ly1r = B.lyr;       // adjoint of y1 from the later steps
+  S ly0a = (S)0, ly0r = (S)0;
+  while (B.out_idx >= 1 && t_out[B.out_idx] > g0) {
+    S ga, gr;
+    grad(B.out_idx, &ga, &gr);
+    const double tj = t_out[B.out_idx];
+    if (tj == g1) {
+      ly1a = ly1a + ga; ly1r = ly1r + gr;
+    } else {
+      const S slope = tf32 ? (S)(((float)tj - (float)g0) / ((float)g1 - (float)g0))
+                           : (S)((tj - g0) / (g1 - g0));
+      ly1a = ly1a + slope * ga; ly1r = ly1r + slope * gr;
+      ly0a = ly0a + (ga - slope * ga); ly0r = ly0r + (gr - slope * gr);
+    }
+    B.out_idx -= 1;
+  }
+  const S dt = rk4_dt<S>(g0, g1, tf32);
+  const S ga = (ly1a * (S)0.125) * dt, gr = (ly1r * (S)0.125) * dt;   // adjoint of the k sum
+  for (int j = 0; j < 7; ++j) { B.lka[j] = (S)0; B.lkr[j] = (S)0; }
+  B.lka[0] = ga; B.lka[3] = ga; B.lka[1] = (S)3 * ga; B.lka[2] = (S)3 * ga;
+  B.lkr[0] = gr; B.lkr[3] = gr; B.lkr[1] = (S)3 * gr; B.lkr[2] = (S)3 * gr;
+  B.lya = ly0a + ly1a; B.lyr = ly0r + ly1r;
+  B.lfa = (S)0; B.lfr = (S)0;
+}
+
+// stage s (3..0): MLP inputs, upstream gradient of the MLP output (adjoint of k_{s+1} = ka[s]) and
+// the HH Jacobian terms
+template <typename S>
+IKR_HD void brk4_stage_inputs(BLane<S>& B, const SolverCfg& c, int s, bool tf32, bool perturb,
+                              double* nv, double* a_in, double* up) {
+  const double ti = rk4_stage_time<S>(s, B.t0, B.dt, tf32, perturb);
+  const S dt = rk4_dt<S>(B.t0, B.dt, tf32);
+  const S Ya = rk4_stage_state<S>(s, B.ya, B.ka, dt);
+  double v;
+  bool in_table = table_voltage(c.tab, ti, &v);
+  B.jr = (S)hh_drdt_dr(c.hp, v, in_table);
+  B.ja = c.nn_d ? (S)hh_dadt_da(c.hp, v, in_table) : (S)0;
+  *nv = mlp_input_nv(v, in_table, c.vrange, c.mlp_is_f64 != 0);
+  *a_in = (double)Ya;
+  *up = adj_mlp_upstream((double)B.lka[s], c);
+}
+
+template <typename S>
+IKR_HD void brk4_reverse_stage(BLane<S>& B, int s, bool tf32, S mlp_grad_a) {
+  const S lYa = mlp_grad_a + B.lka[s] * B.ja;
+  const S lYr = B.lkr[s] * B.jr;
+  B.lya = B.lya + lYa; B.lyr = B.lyr + lYr;
+  const S dt = rk4_dt<S>(B.t0, B.dt, tf32);
+  const S third = (S)(1.0 / 3.0);
+  if (s == 1) {
+    B.lka[0] = B.lka[0] + (dt * lYa) * third; B.lkr[0] = B.lkr[0] + (dt * lYr) * third;
+  } else if (s == 2) {
+    B.lka[1] = B.lka[1] + dt * lYa; B.lkr[1] = B.lkr[1] + dt * lYr;
+    B.lka[0] = B.lka[0] - (dt * lYa) * third; B.lkr[0] = B.lkr[0] - (dt * lYr) * third;
+  } else if (s == 3) {
+    B.lka[0] = B.lka[0] + dt * lYa; B.lkr[0] = B.lkr[0] + dt * lYr;
+    B.lka[1] = B.lka[1] - dt * lYa; B.lkr[1] = B.lkr[1] - dt * lYr;
+    B.lka[2] = B.lka[2] + dt * lYa; B.lkr[2] = B.lkr[2] + dt * lYr;
+  }
+}
+
+template <typename S>
+IKR_HD void brk4_finish_step(BLane<S>& B) {
+  B.n_left -= 1;
+  if (B.n_left <= 0) B.phase = 1;
+}
+// after the first step has been reversed: the first output sample is y0 itself
+template <typename S>
+IKR_HD void brk4_finish(BLane<S>& B, S g0a, S g0r) {
+  B.lya = B.lya + g0a; B.lyr = B.lyr + g0r;
+  B.phase = 2;
+}
+
 }  // namespace ikr
 #endif  // IKR_MATH_H_

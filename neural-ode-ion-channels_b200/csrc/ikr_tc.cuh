@@ -119,6 +119,10 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
          | ((uint32_t)(N >> 3) << 17)   // N / 8
          | ((uint32_t)(M >> 4) << 24);  // M / 16
 }
+// FP16 x FP16 -> FP32, both operands K-major (format code 0 in both operand fields)
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // same with both operands MN-major (the reduction index is the slow one in shared memory)
 __host__ __device__ constexpr uint32_t idesc_bf16_f32_mn(int M, int N) {
   return idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16);
@@ -236,6 +240,47 @@ __device__ __forceinline__ void split3t(f32x2_t h, uint32_t& w1, uint32_t& w2, u
   r = sub2(r, p2(__uint_as_float(ua & 0xFFFF0000u), __uint_as_float(ub & 0xFFFF0000u)));
   u2(r, a, b);
   w3 = __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
+}
+
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// ---- fp32 -> two fp16 terms ---------------------------------------------------------------------------
+// x = t1 + t2 + e with t1 = rn_f16(x), t2 = rn_f16(x - t1): |e| <= 2^-24 |x| while t2 is a normal fp16
+// number (|x| >= 2^-2 after the caller's power-of-two scaling), |e| <= 2^-25 absolute below that.  With
+// both operands split this way the three products t1 u1 + t2 u1 + t1 u2 carry an fp32 product to
+// ~3 x 2^-24 relative -- the same bound as the six-product bf16x3 scheme -- at half the MMAs.
+// The caller scales its values by a power of two (exact) so that they sit inside the fp16 range.
+// The conversion SATURATES (a value beyond +-65504 becomes +-65504, never inf): an adaptive solver
+// probes wild trial states (a stage state far outside [0, 1] after a tenfold step growth) whose
+// activations can leave the range; the reference computes a finite, huge derivative there and rejects
+// the step, and so must this path -- an inf would turn into NaN inside the MMA (inf - inf) and poison
+// the step-size controller instead.  Values on accepted steps are 50 x inside the range.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ f32x2_t unpack_f16x2(uint32_t w) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, h;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "cvt.f32.f16 %0, l;\n\t"
+      "cvt.f32.f16 %1, h;\n\t}"
+      : "=f"(lo), "=f"(hi)
+      : "r"(w));
+  return p2(lo, hi);
+}
+__device__ __forceinline__ void split2h(f32x2_t h, uint32_t& w1, uint32_t& w2) {
+  float a, b;
+  u2(h, a, b);
+  w1 = pack_f16x2(a, b);
+  const f32x2_t r = sub2(h, unpack_f16x2(w1));
+  u2(r, a, b);
+  w2 = pack_f16x2(a, b);
 }
 
 }  // namespace tc

@@ -39,7 +39,7 @@ from .protocols import compact_table
 _ADAPTIVE_OPTS = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps'}
 _FIXED_OPTS = {'step_size', 'perturb'}
 _EXT_OPTS = {'tile_m', 'check_status', 'compact_table', 'ckpt_cap', 'lane_pool', 'tensor_cores',
-             'tc_groups', 'tc_timing', 'ping_pong'}
+             'tc_groups', 'tc_timing', 'ping_pong', 'tc_split'}
 
 
 # =============================================================================================
@@ -164,13 +164,16 @@ def _make_desc(spec: ModelSpec, state_dtype, method, rtol, atol, opts, time_f32=
     # output-layer summation order); bit 6 / 7: forbid / force the two-tile ping-pong kernel
     lp = opts.get('lane_pool', None)
     pp = opts.get('ping_pong', None)
+    if opts.get('tc_split', None) not in (None, 'fp16x2', 'bf16x3'):
+        raise ValueError("odeint: tc_split must be 'fp16x2' or 'bf16x3'")
     groups = int(opts.get('tc_groups', 0) or 0)
     if groups not in (0, 1, 2, 3):
         raise ValueError('odeint: tc_groups must be 1, 2 or 3')
     d.reserved = ((1 if lp else 0) | (4 if lp is False else 0) |
                   (0 if opts.get('tensor_cores', True) else 2) |
                   (8 if opts.get('tc_timing', False) else 0) | (groups << 4) |
-                  (64 if pp is False else 0) | (128 if pp else 0))
+                  (64 if pp is False else 0) | (128 if pp else 0) |
+                  (256 if opts.get('tc_split', None) == 'bf16x3' else 0))
     return d
 
 

@@ -35,6 +35,7 @@ for _ in range(2):
     ev[0].record()
     opts = {'check_status': False, 'tensor_cores': not os.environ.get('NO_TC'),
                                    'tc_timing': bool(os.environ.get('TC_TIMING')),
+                                   'tc_split': os.environ.get('TC_SPLIT') or None,
                                    'tc_groups': int(os.environ.get('TC_GROUPS', '0')),
                                    'ping_pong': {'1': True, '0': False}.get(os.environ.get('PP', ''), None),
             'lane_pool': {'1': True, '0': False}.get(os.environ.get('POOL', ''), None)}

@@ -31,6 +31,7 @@ with torch.no_grad():
                           options={'lane_pool': {'1': True, '0': False}.get(os.environ.get('POOL', ''), None),
                                    'tensor_cores': not os.environ.get('NO_TC'),
                                    'tc_timing': bool(os.environ.get('TC_TIMING')),
+                                   'tc_split': os.environ.get('TC_SPLIT') or None,
                                    'tc_groups': int(os.environ.get('TC_GROUPS', '0')),
                                    'ping_pong': {'1': True, '0': False}.get(os.environ.get('PP', ''), None)})
         e1.record()

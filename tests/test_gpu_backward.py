@@ -251,3 +251,81 @@ def test_full_size_training_batch_4096_properties():
     fb, fs = _flat(g_b), _flat(g_s)
     assert np.isfinite(fb).all()
     assert np.abs(fb - 16 * fs).max() <= 1e-4 * np.abs(fb).max()
+
+
+# ---------------------------------------------------------------------------------------------
+# rk4 (3/8 rule, fixed grid) backward -- VERDICT r1 missing #4
+# ---------------------------------------------------------------------------------------------
+def _oracle_grads_rk4(ofunc, y0, t, loss_fn, options=None):
+    params = list(ofunc.net.parameters())
+    for p in params:
+        p.requires_grad_(True)
+        p.grad = None
+    gy0, losses = [], []
+    for b in range(y0.shape[0]):
+        yb = y0[b:b + 1].clone().requires_grad_(True)
+        y = ro.odeint(ofunc, yb, t, method='rk4', options=options)
+        lb = loss_fn(b, y[:, 0, :])
+        lb.backward()
+        gy0.append(yb.grad.reshape(-1).double())
+        losses.append(float(lb.detach()))
+    g = torch.cat([p.grad.reshape(-1).double() for p in params]).numpy()
+    for p in params:
+        p.requires_grad_(False)
+        p.grad = None
+    return g, torch.stack(gy0).numpy(), np.array(losses)
+
+
+@pytest.mark.parametrize('study,step_size', [('s1', None), ('d2', None), ('d2', 0.7)])
+def test_rk4_autograd_fp64_matches_oracle(study, step_size):
+    """`odeint(..., method='rk4')` with parameters that require grad: gradient w.r.t. the MLP
+    parameters and y0 against PyTorch autograd through the oracle's fixed-grid solver, fp64 state +
+    fp64 MLP, <= 1e-8 of the largest entry; with `step_size` the outputs are interpolated between
+    grid points (their adjoints split between the two ends of the step)."""
+    func, ofunc, _ = _setup(study, True)
+    t = torch.linspace(0., 60., 31, dtype=torch.float64) if step_size is None else \
+        torch.linspace(0., 21., 8, dtype=torch.float64)
+    opts = None if step_size is None else {'step_size': step_size}
+    y0 = torch.tensor([[0.02, 0.97], [0.0, 1.0], [0.3, 0.6]], dtype=torch.float64)
+    rng = np.random.RandomState(14)
+    w = torch.from_numpy(rng.randn(len(t), 3, 2))
+    func.cuda()
+    for p in func.net.parameters():
+        p.requires_grad_(True)
+    y0g = y0.cuda().requires_grad_(True)
+    y = ikr.odeint(func, y0g, t, method='rk4', options=opts)
+    (y * w.cuda()).sum().backward()
+    got = _flat([p.grad for p in func.net.parameters()])
+    got_y0 = y0g.grad.cpu().numpy()
+    want, want_y0, _ = _oracle_grads_rk4(ofunc, y0, t, lambda b, yb: (yb * w[:, b, :]).sum(), opts)
+    assert np.abs(got - want).max() <= 1e-8 * np.abs(want).max()
+    assert np.abs(got_y0 - want_y0).max() <= 1e-8 * np.abs(want_y0).max()
+
+
+def test_rk4_fused_loss_fp32_tensor_core_backward():
+    """rk4 training step on the tensor cores (fp32 as shipped, fused SSE loss, B = 40): loss and
+    gradient against oracle autograd, 1e-4 of each parameter block's largest entry."""
+    func, ofunc, _ = _setup('d2', False)
+    t = torch.linspace(0., 40., 41)
+    B = 40
+    rng = np.random.RandomState(15)
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.9, 1, B)], 1), dtype=torch.float32)
+    data = torch.from_numpy((rng.randn(len(t), B) * 0.1).astype(np.float32))
+    func.cuda()
+    total, per, grads, res = ikr.loss_and_grad(func, y0.cuda(), t, data, method='rk4', want_y0=True)
+    assert res.geometry['tensor_cores']
+    v = torch.from_numpy(np.interp(t.double().numpy(), *protocols.ap2hz()))
+
+    def loss_fn(b, yb):
+        cur = (yb[:, 0] * yb[:, 1]).double() * (v + 86.0)
+        return ((cur - data[:, b].double()) ** 2).sum()
+
+    want, want_y0, want_l = _oracle_grads_rk4(ofunc, y0, t, loss_fn)
+    got = _flat(grads)
+    assert np.abs(per.cpu().numpy() - want_l).max() <= 1e-5 * np.abs(want_l).max()
+    n, o = 200, 0
+    for size in [2 * n, n] + [n * n, n] * 5 + [n, 1]:
+        ref = np.abs(want[o:o + size]).max()
+        assert np.abs(got[o:o + size] - want[o:o + size]).max() <= 1e-4 * ref
+        o += size
+    assert np.abs(res.grad_y0.cpu().numpy() - want_y0).max() <= 1e-4 * np.abs(want_y0).max()

@@ -234,3 +234,31 @@ def test_tc_lane_pool_kernel_equals_tile_scheduled_kernel():
             k = int(ra.stats[bb, 0])
             assert torch.equal(ra.ckpt[1][:k, bb], rb.ckpt[1][:k, bb])
             assert torch.equal(ra.ckpt[0][:k, bb], rb.ckpt[0][:k, bb])
+
+
+def test_fp16x2_split_survives_wild_trial_steps():
+    """The default operand split of the tensor-core forward (fp16x2, three MMAs per fp32 product)
+    saturates instead of overflowing: a first step of 2,000 ms throws the stage states far outside
+    [0, 1] (hidden activations beyond the fp16 range); the reference computes finite garbage there
+    and rejects the step, and so must this path -- every lane ends with status ok and the traces
+    agree with the bf16x3 split and the FFMA2 kernel at the solver's fp32 noise level."""
+    func, _ = _pair('d1')
+    t_tab, v_tab = protocols.pr3_activation(20)
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 8000., 801)
+    rng = np.random.RandomState(12)
+    B = 256
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1),
+                      dtype=torch.float32).cuda()
+    out = {}
+    for name, o in (('fp16x2', {'tc_split': 'fp16x2'}), ('bf16x3', {'tc_split': 'bf16x3'}),
+                    ('ffma', {'tensor_cores': False})):
+        r = ikr.integrate(func, y0, t, options=dict(o, first_step=2000.0, check_status=False))
+        assert int((r.stats[:, 3] != 0).sum()) == 0, name
+        assert int(r.stats[:, 1].min()) >= 1          # the wild first step was rejected
+        out[name] = r.y
+    assert out['fp16x2'].isfinite().all()
+    assert (out['fp16x2'] - out['ffma']).abs().max().item() < 5e-4
+    assert (out['bf16x3'] - out['ffma']).abs().max().item() < 5e-4
+    g = ikr.integrate(func, y0[:4], t).geometry
+    assert g['mma_split'] == 'fp16x2 split' and g['mma_products'] == 3
