@@ -261,6 +261,13 @@ struct TcLane {
   unsigned phase_d;      // parity of the next d_ready completion
   unsigned n_pass;       // layer passes whose D this thread has consumed: D of the next one is in buffer n_pass & 1
   unsigned unit_idx;     // global sequence number of the first unit of the pass being produced
+  unsigned upass;        // passes produced so far (unit_idx = upass * units per pass)
+  unsigned ring_base;    // unit_idx mod ring slots
+  // two-tile kernel (ikr_forward_tc_pp.cuh) only, null / 0 elsewhere:
+  uint64_t* last_d_bar;          // arrive (one per warp) once the D of an evaluation's LAST pass is there
+  uint64_t* gate_bar;            // the first unit store of an evaluation waits for this barrier phase
+  unsigned gate_parity;
+  mutable int gate_pending;
   int group;             // column group 0..G-1
   int lane;              // TMEM lane 0..127
   const float* sp;       // small parameters (stride NP): w0a | w0b | b0 | L x bias | w_last, b_last
@@ -291,24 +298,48 @@ __device__ __forceinline__ float tc_leaky(float x, float slope) { return x > 0.0
 #endif
 constexpr unsigned kTcStaggerNs = IKR_TC_STAGGER_NS;   // start delay per column group after d_ready
 constexpr int kTcMaxUnits = 8;     // NP <= 208: at most 7 units of two K-steps + the tail
-__device__ __forceinline__ uint32_t tc_unit_slot_col(const TcGeom& g, unsigned gi) {
-  return (uint32_t)g.col_ring + (uint32_t)g.unit_cols * (gi % (unsigned)g.ring_slots);
+// ring geometry is a compile-time function of the operand split (a runtime modulo in the MMA warp's
+// unit loop costs ~70 cycles per k-step: measured)
+template <int TERMS>
+__host__ __device__ constexpr unsigned tc_ring_slots() { return TERMS == 2 ? 3u : 2u; }
+// slot of unit u of the pass this thread is producing (tl.ring_base = first unit of the pass mod R)
+template <int TERMS = 3>
+__device__ __forceinline__ uint32_t tc_unit_slot_col(const TcGeom& g, const TcLane& tl, int u) {
+  constexpr unsigned R = tc_ring_slots<TERMS>();
+  return (uint32_t)g.col_ring + (uint32_t)(16 * TERMS) * ((tl.ring_base + (unsigned)u) % R);
 }
-__device__ __forceinline__ void tc_unit_acquire(const TcGeom& g, const TcLane& tl, unsigned gi) {
-  const unsigned UT = (unsigned)(g.units + g.tail), R = (unsigned)g.ring_slots;
-  // UT < R: unit gi - R belongs to a pass whose D this thread has already consumed (all done), and a
-  // parity wait two phases behind the barrier would alias
-  if (gi >= R && UT >= R) {
-    const unsigned prev = gi - R;
-    mbar_wait(&tl.unit_done[prev % UT], (prev / UT) & 1u);
-    tc::fence_after_sync();
+// wait until the MMAs of the unit that used this slot before (R units earlier) are done
+template <int TERMS = 3>
+__device__ __forceinline__ void tc_unit_acquire(const TcGeom& g, const TcLane& tl, int u) {
+  constexpr unsigned R = tc_ring_slots<TERMS>();
+  const unsigned UT = (unsigned)(g.units + g.tail);
+  if (tl.gate_pending) {
+    // two-tile kernel: every pass of the other tile's evaluation must be complete before this
+    // thread looks at the ring barriers again (their parities only tell neighbouring phases apart)
+    mbar_wait(tl.gate_bar, tl.gate_parity);
+    tl.gate_pending = 0;
   }
+  // UT < R: that unit belongs to a pass whose D this thread has already consumed (all done), and a
+  // parity wait two phases behind the barrier would alias
+  if (UT < R) return;
+  if ((unsigned)u >= R) mbar_wait(&tl.unit_done[(unsigned)u - R], tl.upass & 1u);
+  else if (tl.upass > 0u) mbar_wait(&tl.unit_done[(unsigned)u + UT - R], (tl.upass - 1u) & 1u);
+  else return;
+  tc::fence_after_sync();
 }
-__device__ __forceinline__ void tc_unit_publish(const TcGeom& g, const TcLane& tl, unsigned gi) {
+__device__ __forceinline__ void tc_unit_publish(const TcGeom& g, const TcLane& tl, int u) {
   tc::wait_st();
   tc::fence_before_sync();
   __syncwarp();
-  if ((tl.lane & 31) == 0) mbar_arrive(&tl.unit_ready[gi % (unsigned)(g.units + g.tail)]);
+  if ((tl.lane & 31) == 0) mbar_arrive(&tl.unit_ready[u]);
+}
+// this thread has produced its units of a pass
+template <int TERMS = 3>
+__device__ __forceinline__ void tc_pass_advance(TcLane& tl, int UT) {
+  constexpr unsigned R = tc_ring_slots<TERMS>();
+  tl.unit_idx += (unsigned)UT;
+  tl.upass += 1u;
+  tl.ring_base = (tl.ring_base + (unsigned)UT) % R;
 }
 // unit u of a pass belongs to column group u % G; the tail is unit number g.units
 template <int G>
@@ -349,8 +380,8 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
       if (TERMS == 3) tc::split3t(h[q], w12[q], w12[8 * NK + q], w3[q]);
       else tc::split2h(h[q], w12[q], w12[8 * NK + q]);
     }
-    tc_unit_acquire(g, tl, gi);
-    const uint32_t dst = tl.taddr + tc_unit_slot_col(g, gi);
+    tc_unit_acquire<TERMS>(g, tl, u);
+    const uint32_t dst = tl.taddr + tc_unit_slot_col<TERMS>(g, tl, u);
     if (NK == 2) {
       tc::st32(dst, reinterpret_cast<uint32_t(&)[32]>(w12));
       if (TERMS == 3) tc::st16(dst + 32, reinterpret_cast<uint32_t(&)[16]>(w3));
@@ -358,7 +389,7 @@ __device__ __forceinline__ void tc_unit_finish(const TcGeom& g, const TcLane& tl
       tc::st16(dst, reinterpret_cast<uint32_t(&)[16]>(w12));
       if (TERMS == 3) tc::st8(dst + 16, reinterpret_cast<uint32_t(&)[8]>(w3));
     }
-    tc_unit_publish(g, tl, gi);
+    tc_unit_publish(g, tl, u);
   } else {
 #pragma unroll
     for (int q = 0; q < 4 * NK; ++q) {
@@ -407,10 +438,10 @@ __device__ __forceinline__ void tc_tail_finish(const TcGeom& g, const TcLane& tl
         tc::split2h(h[q], t[q], t[4 + q]);
       }
     }
-    tc_unit_acquire(g, tl, gi);
-    if (TERMS == 3) tc::st16(tl.taddr + tc_unit_slot_col(g, gi), t);
-    else tc::st8(tl.taddr + tc_unit_slot_col(g, gi), reinterpret_cast<uint32_t(&)[8]>(t));
-    tc_unit_publish(g, tl, gi);
+    tc_unit_acquire<TERMS>(g, tl, g.units);
+    if (TERMS == 3) tc::st16(tl.taddr + tc_unit_slot_col<TERMS>(g, tl, g.units), t);
+    else tc::st8(tl.taddr + tc_unit_slot_col<TERMS>(g, tl, g.units), reinterpret_cast<uint32_t(&)[8]>(t));
+    tc_unit_publish(g, tl, g.units);
   } else {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -469,7 +500,7 @@ __device__ __forceinline__ uint32_t tc_wait_d(const TcGeom& g, TcLane& tl, bool 
 // partial output sums land in tl.part (caller syncs).  Group c produces the units u = c (mod G) of
 // every pass.  `hook` runs after this thread's layer-0 units are published, i.e. while the MMAs of
 // layer 1 execute: the owners use it to compute time-only RHS terms of the next stage ahead.
-template <int G, int TERMS = 3, typename Hook = TcNoHook>
+template <int G, int TERMS = 3, bool SOLO_L0 = false, typename Hook = TcNoHook>
 __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook hook = Hook()) {
   const int NP = g.NP;
   const float2 in = *reinterpret_cast<const float2*>(tl.xin + 2 * tl.lane);
@@ -482,7 +513,9 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
   {
     const float* b0 = tl.sp + 2 * NP;
     if (tl.group > 0) __nanosleep(kTcStaggerNs * (unsigned)tl.group);
-    for (int u = tl.group; u < UT; u += G) {
+    // SOLO_L0 (two-tile kernel): column group 0 produces every unit of the first pass, the other
+    // groups are still busy with the previous evaluation's output reduction
+    for (int u = SOLO_L0 ? (tl.group == 0 ? 0 : UT) : tl.group; u < UT; u += SOLO_L0 ? 1 : G) {
       const unsigned gi = tl.unit_idx + (unsigned)u;
       if (u < g.units) {
         if (2 * u + 1 < g.KSf) {
@@ -500,7 +533,7 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
         tc_tail_finish<TERMS>(g, tl, gi, b0, v, false, wl, s);
       }
     }
-    tl.unit_idx += (unsigned)UT;
+    tc_pass_advance<TERMS>(tl, UT);
   }
   { const long long c1 = clock64(); tl.c_l0 += c1 - c0; c0 = c1; }
   hook();
@@ -510,6 +543,10 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
     const bool last = layer + 1 == g.L;
     const float dscale = TERMS == 3 ? 1.0f : tl.sp[tc_scale_index(g, layer)];
     const uint32_t dcol = tc_wait_d(g, tl, !last);   // the output layer produces no units: no stagger
+    if (last && tl.last_d_bar != nullptr) {
+      __syncwarp();
+      if ((tl.lane & 31) == 0) mbar_arrive(tl.last_d_bar);
+    }
     { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
     for (int u = tl.group; u < UT; u += G) {
       const unsigned gi = tl.unit_idx + (unsigned)u;
@@ -532,7 +569,7 @@ __device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook ho
         tc_tail_finish<TERMS>(g, tl, gi, bias, v, last, wl, s, dscale);
       }
     }
-    if (!last) tl.unit_idx += (unsigned)UT;
+    if (!last) tc_pass_advance<TERMS>(tl, UT);
     { const long long c1 = clock64(); tl.c_epi += c1 - c0; if (last) tl.c_last += c1 - c0; c0 = c1; }
   }
 #ifdef IKR_TC_TRACE
@@ -549,7 +586,7 @@ __device__ __forceinline__ float tc_owner_eval(const TcGeom& g, TcLane& tl, floa
   long long t0 = clock64();
   if (G > 1) lanes_sync<G>();        // inputs visible to the helper groups (cmd word = run)
   { const long long t1 = clock64(); tl.c_sync_a += t1 - t0; }
-  tc_mlp_eval<G, TERMS, Hook>(g, tl, hook);
+  tc_mlp_eval<G, TERMS, false, Hook>(g, tl, hook);
   t0 = clock64();
   if (G > 1) lanes_sync<G>();        // partial sums visible
   { const long long t1 = clock64(); tl.c_sync_b += t1 - t0; }
@@ -601,6 +638,12 @@ __device__ __forceinline__ void tc_lane_attach(TcLane& tl, const TcEngineCtx& e)
   tl.phase_d = 0;
   tl.n_pass = 0;
   tl.unit_idx = 0;
+  tl.upass = 0;
+  tl.ring_base = 0;
+  tl.last_d_bar = nullptr;
+  tl.gate_bar = nullptr;
+  tl.gate_parity = 0;
+  tl.gate_pending = 0;
 }
 // after the stop flag is set: the four warps of group 0 (the producers of unit 0) complete one more
 // phase of unit_ready[0], on which the MMA warp is waiting between passes (it sees the flag and leaves)
@@ -627,13 +670,13 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
     const uint32_t dcol = tbase + ((pass & 1u) ? (uint32_t)g.NP : 0u);
     bool first = true;
     for (int u = 0; u < UT; ++u, ++gi) {
-      const unsigned slot = gi % (unsigned)g.ring_slots;
+      const unsigned slot = gi % tc_ring_slots<TERMS>();
       { const long long c1 = clock64(); e_issue += c1 - ec; ec = c1; }
       mbar_wait(&c.unit_ready[u], pass & 1u);
       if (*c.stop_flag) { stop = true; break; }
       tc::fence_after_sync();
       { const long long c1 = clock64(); e_wait += c1 - ec; if (u == 0) { e_wait0 += c1 - ec; if (pass % (unsigned)g.L == 0) e_wait00 += c1 - ec; } ec = c1; }
-      const uint32_t a_slot = tbase + (uint32_t)g.col_ring + (uint32_t)g.unit_cols * slot;
+      const uint32_t a_slot = tbase + (uint32_t)g.col_ring + (uint32_t)(16 * TERMS) * slot;
       const bool is_tail = u >= g.units;
       const int nk = is_tail ? 1 : ((2 * u + 1 < g.KSf) ? 2 : 1);
 #pragma unroll 1
@@ -797,6 +840,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
     tl.trace_eval = 0;
 #endif
     const long long c_begin = clock64();
+    long long c_finish = 0;
 
     if (tl.group > 0) {
       // ---- helper groups: evaluate on command until the owners say exit -----------------------------
@@ -916,7 +960,9 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
               });
               dp_store_stage<S>(L, cfg, s, (double)out);
             }
+            const long long cf0 = clock64();
             dp_finish_step<S>(L, cfg, job.t_out, T, emit, ckpt);
+            c_finish += clock64() - cf0;
           }
         } else {
           if (T <= 1 && lane_active(L)) L.status = LANE_DONE;
@@ -953,9 +999,9 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
       if (tp.timing && blockIdx.x == 0 && tid == 0) {
         const long long tot = clock64() - c_begin;
         printf("[tc timing] owner 0: total %lld cycles: layer0 %lld, wait_d %lld, epilogue %lld (output layer %lld), "
-               "barrier A %lld, barrier B %lld, solver %lld\n",
+               "barrier A %lld, barrier B %lld, solver %lld (of which dp_finish_step %lld)\n",
                tot, tl.c_l0, tl.c_wait, tl.c_epi, tl.c_last, tl.c_sync_a, tl.c_sync_b,
-               tot - tl.c_l0 - tl.c_wait - tl.c_epi - tl.c_sync_a - tl.c_sync_b);
+               tot - tl.c_l0 - tl.c_wait - tl.c_epi - tl.c_sync_a - tl.c_sync_b, c_finish);
       }
       // release the helper groups and the engine warps
       if (tid == 0) { *cmd_exit = 1; *stop_flag = 1; }

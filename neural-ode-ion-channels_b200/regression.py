@@ -56,9 +56,10 @@ def mse_loss_and_grad(func, x_av, y_dadt, *, device=None, accumulate=False):
 
 
 def fit_regression(func, v, a, dadt, *, n_iter=4000, lr=0.001, step_size=100, gamma=0.9,
-                   log_every=400, log=None):
+                   log_every=400, log=None, stop_below=None):
     """The reference's regression loop (``train-s1.py:885-909``): keep 0 < a < 1, Adam(lr) with
-    StepLR(step_size, gamma), ``n_iter`` full-batch iterations.  Returns the list of logged losses."""
+    StepLR(step_size, gamma), ``n_iter`` full-batch iterations (fewer when a logged loss falls below
+    ``stop_below``).  Returns the list of logged losses."""
     describe(func)
     dev = next(func.net.parameters()).device
     vr = float(func.vrange) if not isinstance(func.vrange, torch.Tensor) else float(func.vrange.reshape(-1)[0])
@@ -79,6 +80,8 @@ def fit_regression(func, v, a, dadt, *, n_iter=4000, lr=0.001, step_size=100, ga
             history.append(float(loss))
             if log is not None:
                 log('Iter %d LR %g Loss %g' % (itr, opt.param_groups[0]['lr'], history[-1]))
+            if stop_below is not None and history[-1] < stop_below:
+                break
     func._ikr_regression_optimizer = opt
     return history
 

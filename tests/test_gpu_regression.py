@@ -83,3 +83,29 @@ def test_fit_regression_follows_the_reference_loop():
         ck = torch.load(path, weights_only=False)
         assert set(ck) == {'epoch', 'state_dict', 'optimizer', 'loss'} and ck['epoch'] == 60
         assert set(ck['state_dict']) == set(f_ref.state_dict())
+
+
+def test_d2_regression_fit_reaches_the_reference_logged_loss():
+    """The reference's own d2 fit (train-d2.py:880-915, data d2/{v,a,dadt}.pt, curve d2/log:4-24):
+    NN-d network initialised N(0, 1e-3^2), Adam(1e-3) + StepLR(400, 0.9), full batch of the 69,361
+    stored points, loss = sum (net(x) / netscale + HH(a, V) - da/dt)^2.  Every iteration's loss and
+    gradient come from the tensor-core kernels (adjoint MMAs bf16x3, weight-gradient GEMM with bf16x2
+    products).  The first loss must equal the logged 0.065354 (the network starts at ~0, so this pins
+    data + HH term + reduction), and the fit must get below the reference's target loss 0.015568 --
+    the logged run sat on the 0.0652 plateau for 4,000 iterations and ended at 0.014476 after 8,000;
+    when the plateau is left depends on the random initialisation, so the loop may run to 16,000."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'd2_regression.npz'))
+    torch.manual_seed(0)
+    func = ikr.ODEFuncNNd(params='d').cuda()
+    v = torch.from_numpy(gold['v']).double().cuda()
+    a = torch.from_numpy(gold['a']).double().cuda()
+    dadt = torch.from_numpy(gold['dadt']).double().cuda()
+    with torch.no_grad():
+        hh = func._dadt(a, v)                  # k1 (1 - a) - k2 a, train-d2.py:247-250
+    target = float(gold['logged_target'])
+    hist = ikr.fit_regression(func, v, a, dadt - hh, n_iter=16001, lr=1e-3, step_size=400, gamma=0.9,
+                              log_every=400, stop_below=target)
+    print('d2 regression fit, loss every 400 iterations:', ['%.6f' % h for h in hist])
+    assert abs(hist[0] - float(gold['logged_first'])) < 2e-5, hist[0]
+    assert hist[-1] < target, hist
