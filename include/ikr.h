@@ -77,7 +77,8 @@ typedef struct ikr_desc {
                              bit 3: debug, CTA 0 prints its phase clocks (device printf);
                              bits 4-5: epilogue column groups of the tensor-core kernels, 1..3
                              (0 = default 3; fixes the output-layer summation order, i.e. results);
-                             bit 6: never use the two-tile ping-pong kernel; bit 7: force it;
+                             bit 6: never use the two-tile ping-pong kernel; bit 7: use it (experimental,
+                             never chosen automatically);
                              bit 8: tensor-core forward with the bf16x3 operand split (six MMAs per
                              fp32 product, any activation range) instead of the default fp16x2
                              split (three MMAs; hidden activations must stay below 65504 / 16 in

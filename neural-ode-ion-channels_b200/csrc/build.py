@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     # link the CUDA runtime dynamically: the process already holds libcudart.so.12 (torch's), and the
     # shipped binary then carries none of the runtime's unused entry-point names
     '-cudart', 'shared', '-Xlinker', '-rpath,/usr/local/cuda/lib64',
+    '-split-compile', '0',   # optimise the kernels of this one translation unit in parallel
 ]
 
 

@@ -10,6 +10,7 @@
 #include "../../include/ikr.h"
 #include "ikr_backward.cuh"
 #include "ikr_regress_tc.cuh"
+#include "ikr_forward_tc_pp.cuh"
 #include "ikr_hh.cuh"
 #include "ikr_markov.cuh"
 
@@ -268,6 +269,49 @@ bool use_pool_tc(const ikr_desc* d, long long b_total, int sms) {
   if (d->method != IKR_DOPRI5 || (d->reserved & 4)) return false;
   if (d->reserved & 1) return true;
   return b_total > (long long)kTcM * sms;   // more than one tile per SM
+}
+
+// Two-tile ping-pong lane pool (ikr_forward_tc_pp.cuh): dopri5 on the tensor cores, two tiles per CTA
+// whose evaluations alternate on the tensor pipe.  EXPERIMENTAL in this round: bit-identical to the
+// two-group tile kernel in the tests, but its first pass (layer 0 by one column group) does not
+// keep up with the MMAs yet, so it is opt-in only (desc.reserved bit 7), never chosen automatically.
+bool use_pp_tc(const ikr_desc* d, long long /*b_total*/, int /*sms*/, int /*n_jobs*/) {
+  if (d->method != IKR_DOPRI5 || (d->reserved & (64 | 4))) return false;
+  return (d->reserved & 128) != 0;
+}
+
+struct TcPpPlan {
+  bool ok;
+  TcGeom g;
+  size_t smem;
+};
+TcPpPlan make_tc_pp_plan(const ikr_desc* d, const TcPlan& fw) {
+  TcPpPlan t;
+  t.ok = false;
+  t.g = fw.g;
+  t.smem = 0;
+  if (!fw.ok || fw.g.units + fw.g.tail < 2) return t;   // two column groups need two units per pass
+  const size_t fixed = d->state_dtype == IKR_F32 ? TcPpSmemLayout<float>(t.g, 0).total
+                                                  : TcPpSmemLayout<double>(t.g, 0).total;
+  if (fixed + (size_t)kTcMinStages * t.g.stage_bytes > kSmemLimit) return t;
+  int stages = (int)((kSmemLimit - fixed) / t.g.stage_bytes);
+  if (stages > kTcMaxStages) stages = kTcMaxStages;
+  t.g.stages = stages;
+  t.smem = fixed + (size_t)stages * t.g.stage_bytes;
+  t.ok = true;
+  return t;
+}
+
+template <typename S>
+int launch_forward_tc_pp(const TcFwdParams& tp, const TcPpPlan& t, int grid, cudaStream_t st) {
+  auto kern = tp.g.terms == 2 ? ikr_forward_tc_pp_kernel<S, 2> : ikr_forward_tc_pp_kernel<S, 3>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return IKR_ERR_LAUNCH;
+  }
+  kern<<<grid, tc_threads(3), t.smem, st>>>(tp);
+  return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
 }
 
 size_t fwd_fixed_workspace(int n_jobs) {
@@ -835,9 +879,19 @@ int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int
     out[0] = tl; out[1] = tc_threads(tcp.groups); out[2] = tiles < sms ? tiles : sms; out[3] = (int64_t)tcp.smem;
     out[4] = tiles; out[5] = 16; out[6] = tcp.g.KST; out[7] = sms;
     out[8] = pool ? 1 : 0;
+    if (use_pp_tc(d, b_total, sms, n_jobs) && make_tc_pp_plan(d, tcp).ok) {
+      const TcPpPlan ppl = make_tc_pp_plan(d, tcp);
+      const long long ctas = (b_total + 2 * kTcM - 1) / (2 * kTcM);
+      out[8] = 2;
+      out[1] = tc_threads(3);
+      out[2] = ctas < sms ? ctas : sms;
+      out[3] = (int64_t)ppl.smem;
+      out[4] = (b_total + tl - 1) / tl;
+      out[11] = 2;
+    }
     out[9] = tcp.g.terms == 2 ? 3 : 2;   // (ikr_tc_absmax_kernel +) ikr_tc_pack_kernel + the forward kernel
     out[10] = 1;
-    out[11] = tcp.groups;
+    if (out[8] != 2) out[11] = tcp.groups;
     out[12] = tcp.g.terms == 2 ? 3 : 6;  // 16-bit MMAs per fp32 product
     return 0;
   }
@@ -979,6 +1033,18 @@ int ikr_forward(const ikr_desc* d, const ikr_io* jobs, int32_t n_jobs, void* wor
     }
     ikr_tc_pack_kernel<<<g.sms, 256, 0, st>>>(pk);
     if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
+    if (use_pp_tc(d, traj, g.sms, n_jobs)) {
+      const TcPpPlan ppl = make_tc_pp_plan(d, tcp);
+      if (ppl.ok) {
+        tp.g = ppl.g;
+        // 256 lane slots per CTA; the queue hands out trajectories, so the grid only needs to cover them
+        const long long ctas = (traj + 2 * kTcM - 1) / (2 * kTcM);
+        const int grid = (int)(ctas < g.sms ? ctas : g.sms);
+        tp.f.n_tiles = (traj + kTcM - 1) / kTcM;
+        if (d->state_dtype == IKR_F32) return launch_forward_tc_pp<float>(tp, ppl, grid, st);
+        return launch_forward_tc_pp<double>(tp, ppl, grid, st);
+      }
+    }
     if (d->state_dtype == IKR_F32) return launch_forward_tc<float>(tp, tcp, g.grid, st, pool);
     return launch_forward_tc<double>(tp, tcp, g.grid, st, pool);
   }

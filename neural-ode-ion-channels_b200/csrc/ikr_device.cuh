@@ -7,6 +7,7 @@
 #define IKR_DEVICE_CUH_
 
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdint.h>
 
 #include "ikr_math.h"
@@ -44,10 +45,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef IKR_MBAR_DEBUG
+// bring-up build: a wait that does not end within ~2 s reports where it sits and aborts the kernel
+__device__ __noinline__ void mbar_wait_dbg(uint64_t* bar, unsigned parity, int line) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("[mbar timeout] line %d block %d thread %d bar smem 0x%x parity %u\n", line, (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+#define mbar_wait(bar, parity) mbar_wait_dbg(bar, parity, __LINE__)
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+#endif
 // wait that yields the issue slots between polls (long waits of many threads on one barrier)
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity, unsigned ns) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(ns);

@@ -268,6 +268,7 @@ struct TcLane {
   uint64_t* gate_bar;            // the first unit store of an evaluation waits for this barrier phase
   unsigned gate_parity;
   mutable int gate_pending;
+  mutable long long c_gate;      // cycles spent waiting at the gate (timing runs)
   int group;             // column group 0..G-1
   int lane;              // TMEM lane 0..127
   const float* sp;       // small parameters (stride NP): w0a | w0b | b0 | L x bias | w_last, b_last
@@ -316,8 +317,10 @@ __device__ __forceinline__ void tc_unit_acquire(const TcGeom& g, const TcLane& t
   if (tl.gate_pending) {
     // two-tile kernel: every pass of the other tile's evaluation must be complete before this
     // thread looks at the ring barriers again (their parities only tell neighbouring phases apart)
+    const long long tg0 = clock64();
     mbar_wait(tl.gate_bar, tl.gate_parity);
     tl.gate_pending = 0;
+    tl.c_gate += clock64() - tg0;
   }
   // UT < R: that unit belongs to a pass whose D this thread has already consumed (all done), and a
   // parity wait two phases behind the barrier would alias
@@ -644,6 +647,7 @@ __device__ __forceinline__ void tc_lane_attach(TcLane& tl, const TcEngineCtx& e)
   tl.gate_bar = nullptr;
   tl.gate_parity = 0;
   tl.gate_pending = 0;
+  tl.c_gate = 0;
 }
 // after the stop flag is set: the four warps of group 0 (the producers of unit 0) complete one more
 // phase of unit_ready[0], on which the MMA warp is waiting between passes (it sees the flag and leaves)

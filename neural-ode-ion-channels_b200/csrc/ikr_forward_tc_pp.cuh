@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
   const uint32_t tbase = *tmem_slot;
 
   if (warp == kMmaWarp) {
-    tc_mma_warp<TERMS>(g, eng, tbase, false);
+    tc_mma_warp<TERMS>(g, eng, tbase, tp.timing && blockIdx.x == 0);
   } else if (warp == kLoadWarp) {
     if ((tid & 31) == 0) tc_producer_thread(g, eng, reinterpret_cast<const unsigned char*>(tp.img),
                                             (unsigned)(g.L * g.KST));
@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
       Lane<S>* lanes = reinterpret_cast<Lane<S>*>(smem_raw + lay.off_lanes);
       double* obs = reinterpret_cast<double*>(smem_raw + lay.off_obs);
       LaneAux<S>* aux = reinterpret_cast<LaneAux<S>*>(smem_raw + lay.off_aux);
+      long long c_acct = 0, c_eval = 0, c_collect = 0, c_opart = 0;
+      const long long c_begin = clock64();
       unsigned ph_other_xin = 0u, ph_other_part = 0u, ph_other_last = 0u, ph_my_part = 0u;
       bool other_gone = false, first_eval = true;
       tl.last_d_bar = &d_last[Z];
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
       // One evaluation of this tile, interleaved with the other tile's (see the file header)
       auto owner_eval = [&](float nv, float a, auto hook) -> float {
         bool wait_other_part = false;
+        long long ct = clock64();
         if (!other_gone && !(first_eval && Z == 0)) {
           // the other tile's evaluation that precedes this one in the global sequence
           mbar_wait(&xin_ready[O], ph_other_xin);
@@ -225,21 +228,26 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
           }
         }
         first_eval = false;
+        { const long long c1 = clock64(); c_acct += c1 - ct; ct = c1; }
         *reinterpret_cast<float2*>(tl.xin + 2 * tl.lane) = make_float2(nv, a);
         __syncwarp();
         if ((tl.lane & 31) == 0) mbar_arrive(&xin_ready[Z]);
         tc_mlp_eval<2, TERMS, true>(g, tl, [&]() {
           // before the units of pass 2 (its MMAs overwrite the D the other tile's output reduction read)
           if (wait_other_part) {
+            const long long c0 = clock64();
             mbar_wait(&part_ready[O], ph_other_part);
             ph_other_part ^= 1u;
+            c_opart += clock64() - c0;
           }
           hook();
         });
+        { const long long c1 = clock64(); c_eval += c1 - ct; ct = c1; }
         __syncwarp();
         if ((tl.lane & 31) == 0) mbar_arrive(&part_ready[Z]);
         mbar_wait(&part_ready[Z], ph_my_part);
         ph_my_part ^= 1u;
+        c_collect += clock64() - ct;
         return tl.part[tl.lane] + tl.part[kTcM + tl.lane] + tl.sp[(size_t)(4 + g.L) * g.NP];
       };
 
@@ -383,6 +391,13 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
           A.mode = POOL_STEP;
           if (job.T <= 1 && lane_active(L)) L.status = LANE_DONE;
         }
+      }
+      if (tp.timing && blockIdx.x == 0 && tl.lane == 0) {
+        const long long tot = clock64() - c_begin;
+        printf("[pp timing] owner of tile %d: total %lld cycles: accounting wait %lld, evaluation %lld (gate wait %lld, "
+               "other-part wait %lld, wait_d %lld, layer0 %lld, epilogue %lld), collect %lld, solver+boundary %lld\n",
+               Z, tot, c_acct, c_eval, tl.c_gate, c_opart, tl.c_wait, tl.c_l0, tl.c_epi, c_collect,
+               tot - c_acct - c_eval - c_collect);
       }
       // this tile is finished: leave the alternation (the helper and the other owner see dead[Z] at
       // this tile's next turn)

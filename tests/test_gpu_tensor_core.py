@@ -262,3 +262,36 @@ def test_fp16x2_split_survives_wild_trial_steps():
     assert (out['bf16x3'] - out['ffma']).abs().max().item() < 5e-4
     g = ikr.integrate(func, y0[:4], t).geometry
     assert g['mma_split'] == 'fp16x2 split' and g['mma_products'] == 3
+
+
+@pytest.mark.parametrize('sizes', [(37, 300, 5), (130,), (1, 1), (700, 513)])
+def test_ping_pong_kernel_equals_two_group_tile_kernel(sizes):
+    """The two-tile ping-pong lane pool (two tiles per CTA whose evaluations alternate on the tensor
+    pipe; every evaluation produced by two column groups) reproduces the tile-scheduled kernel run
+    with two column groups bit for bit -- states, currents, losses, statistics and step checkpoints --
+    for mixed jobs, a tile that runs dry long before the other, and CTAs with a single trajectory."""
+    func, _ = _pair('d1')
+    rng = np.random.RandomState(21)
+    protos = [(*protocols.ap2hz(), 101), (*protocols.pr3_activation(20), 81),
+              (*protocols.pr5_deactivation(-60), 41)]
+    jobs = []
+    for k, B in enumerate(sizes):
+        tt, vv, T = protos[k % 3]
+        y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1),
+                          dtype=torch.float32).cuda()
+        t = torch.linspace(0., 2. * (T - 1), T)
+        g = torch.tensor(rng.lognormal(0, 0.2, B), dtype=torch.float32)
+        jobs.append(dict(protocol=(tt, vv), y0=y0, t=t, g=g, data=torch.zeros(T),
+                         want_current=True, want_ckpt=True))
+    a = ikr.integrate_many(func, jobs, options={'tc_groups': 2, 'lane_pool': False})
+    b = ikr.integrate_many(func, jobs, options={'ping_pong': True})
+    assert a[0].geometry['scheduling'].startswith('tile queue') and a[0].geometry['column_groups'] == 2
+    assert b[0].geometry['scheduling'].startswith('two-tile ping-pong')
+    for ra, rb in zip(a, b):
+        assert torch.equal(ra.stats, rb.stats)
+        assert torch.equal(ra.y, rb.y) and torch.equal(ra.current, rb.current)
+        assert torch.equal(ra.sse, rb.sse) and torch.equal(ra.sae, rb.sae)
+        for bb in range(0, ra.stats.shape[0], 7):
+            k = int(ra.stats[bb, 0])
+            assert torch.equal(ra.ckpt[1][:k, bb], rb.ckpt[1][:k, bb])
+            assert torch.equal(ra.ckpt[0][:k, bb], rb.ckpt[0][:k, bb])
