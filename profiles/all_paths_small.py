@@ -27,8 +27,18 @@ with torch.no_grad():
     print('forward pool', int(r.stats[:, 2].sum()))
     r = ikr.integrate(f, y0, t, method='rk4')
     print('forward rk4', int(r.stats[:, 2].sum()))
+    r = ikr.integrate(f, y0, t, data=data, options={'tc_split': 'bf16x3'})
+    print('forward bf16x3 split', r.geometry['mma_split'], int(r.stats[:, 2].sum()))
+    r = ikr.integrate(f, torch.cat([y0, y0, y0]), t, data=data, options={'ping_pong': True})
+    print('forward two-tile ping-pong', r.geometry['scheduling'], int(r.stats[:, 2].sum()))
+    r = ikr.integrate(f, y0, t, data=data, options={'tensor_cores': False})
+    print('forward FFMA2', int(r.stats[:, 2].sum()))
 total, per, grads, res = ikr.loss_and_grad(f, y0, t, data, want_y0=True)
 print('backward', float(total), float(max(g.abs().max() for g in grads)))
+total, per, grads, res = ikr.loss_and_grad(f, y0, t, data, method='rk4', want_y0=True)
+print('backward rk4', float(total), float(max(g.abs().max() for g in grads)))
+total, per, grads, res = ikr.loss_and_grad(f, y0[:40], t, data, options={'tensor_cores': False})
+print('backward FFMA2', float(total), float(max(g.abs().max() for g in grads)))
 x = torch.rand(300, 2).cuda()
 yy = torch.rand(300).cuda() * 1e-3
 loss, g = ikr.mse_loss_and_grad(f, x, yy)
