@@ -706,19 +706,19 @@ def run_b200(args):
     for prm in func.parameters():
         prm.requires_grad_(False)
     jobs_dev, jobs_host, tgrids = [], [], []
-    for (fam, name, t_tab, v_tab, t_out), nb in zip(wl, sizes):
+    # synthetic "measured" traces: nominal trajectory of every protocol (one launch for all five) +
+    # N(0, 0.1^2) noise (train-s1.py:40)
+    tgrids = [torch.tensor(w[4], dtype=torch.float32) for w in wl]
+    nominal = ikr.integrate_many(func, [dict(protocol=(w[2], w[3]), t=t, y0=torch.tensor([[0., 1.]], device=dev),
+                                             E=-86.0, want_current=True, want_y=False)
+                                        for w, t in zip(wl, tgrids)])
+    for (fam, name, t_tab, v_tab, t_out), nb, t, nom in zip(wl, sizes, tgrids, nominal):
         y0 = np.stack([rng.uniform(0, 0.05, nb), rng.uniform(0.95, 1.0, nb)], 1).astype(np.float32)
         g = rng.lognormal(0.0, 0.2, nb).astype(np.float32)
         hy, hg = torch.from_numpy(y0).pin_memory(), torch.from_numpy(g).pin_memory()
-        t = torch.tensor(t_out, dtype=torch.float32)
-        tgrids.append(t)
-        # synthetic "measured" trace: nominal trajectory + N(0, 0.1^2) noise (train-s1.py:40)
-        func.set_fixed_form_voltage_protocol(t_tab, v_tab)
-        nominal = ikr.integrate(func, torch.tensor([[0., 1.]], device=dev), t, want_current=True,
-                                want_y=False, E=-86.0)
         noise = torch.from_numpy(np.random.RandomState(7).normal(0, 0.1, len(t_out))
                                  .astype(np.float32)).to(dev)
-        d = (nominal.current[:, 0] + noise).contiguous()
+        d = (nom.current[:, 0] + noise).contiguous()
         common = dict(protocol=(t_tab, v_tab), t=t, E=-86.0, data=d, want_y=False)
         jobs_dev.append(dict(common, y0=hy.to(dev), g=hg.to(dev)))
         jobs_host.append(dict(common, y0=hy, g=hg))

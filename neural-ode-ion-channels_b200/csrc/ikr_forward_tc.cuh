@@ -498,87 +498,113 @@ __device__ __forceinline__ uint32_t tc_wait_d(const TcGeom& g, TcLane& tl, bool 
   return col;
 }
 
-// One MLP evaluation of the 128-trajectory tile, executed by EVERY lane thread (all G groups, masked
-// lanes included).  The caller has published (nv, a) in tl.xin and passed the lanes barrier; the
-// partial output sums land in tl.part (caller syncs).  Group c produces the units u = c (mod G) of
-// every pass.  `hook` runs after this thread's layer-0 units are published, i.e. while the MMAs of
-// layer 1 execute: the owners use it to compute time-only RHS terms of the next stage ahead.
-template <int G, int TERMS = 3, bool SOLO_L0 = false, typename Hook = TcNoHook>
-__device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook hook = Hook()) {
+// ---- the three parts of one MLP evaluation (tc_mlp_eval = layer0 + hook + hidden + output) ----------
+// layer 0: this thread's units (u = tl.group mod G) of the first pass, from (nv, a) in tl.xin
+template <int G, int TERMS>
+__device__ __forceinline__ void tc_eval_layer0(const TcGeom& g, TcLane& tl) {
   const int NP = g.NP;
   const float2 in = *reinterpret_cast<const float2*>(tl.xin + 2 * tl.lane);
   const float nv = in.x, a = in.y;
   const int UT = g.units + g.tail;
   float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   const float* wl = tl.sp + (size_t)(3 + g.L) * NP;
-  long long c0 = clock64();
-  // ---- layer 0 ------------------------------------------------------------------------------
-  {
-    const float* b0 = tl.sp + 2 * NP;
-    if (tl.group > 0) __nanosleep(kTcStaggerNs * (unsigned)tl.group);
-    // SOLO_L0 (two-tile kernel): column group 0 produces every unit of the first pass, the other
-    // groups are still busy with the previous evaluation's output reduction
-    for (int u = SOLO_L0 ? (tl.group == 0 ? 0 : UT) : tl.group; u < UT; u += SOLO_L0 ? 1 : G) {
-      const unsigned gi = tl.unit_idx + (unsigned)u;
-      if (u < g.units) {
-        if (2 * u + 1 < g.KSf) {
-          uint32_t v[32];
-          tc_layer0_sums<32>(tl, NP, 32 * u, nv, a, v);
-          tc_unit_finish<2, TERMS>(g, tl, u, gi, b0, v, false, wl, s);
-        } else {
-          uint32_t v[16];
-          tc_layer0_sums<16>(tl, NP, 32 * u, nv, a, v);
-          tc_unit_finish<1, TERMS>(g, tl, u, gi, b0, v, false, wl, s);
-        }
+  const float* b0 = tl.sp + 2 * NP;
+  if (tl.group > 0) __nanosleep(kTcStaggerNs * (unsigned)tl.group);
+  for (int u = tl.group; u < UT; u += G) {
+    const unsigned gi = tl.unit_idx + (unsigned)u;
+    if (u < g.units) {
+      if (2 * u + 1 < g.KSf) {
+        uint32_t v[32];
+        tc_layer0_sums<32>(tl, NP, 32 * u, nv, a, v);
+        tc_unit_finish<2, TERMS>(g, tl, u, gi, b0, v, false, wl, s);
       } else {
-        uint32_t v[8];
-        tc_layer0_sums<8>(tl, NP, 16 * g.KSf, nv, a, v);
-        tc_tail_finish<TERMS>(g, tl, gi, b0, v, false, wl, s);
+        uint32_t v[16];
+        tc_layer0_sums<16>(tl, NP, 32 * u, nv, a, v);
+        tc_unit_finish<1, TERMS>(g, tl, u, gi, b0, v, false, wl, s);
       }
+    } else {
+      uint32_t v[8];
+      tc_layer0_sums<8>(tl, NP, 16 * g.KSf, nv, a, v);
+      tc_tail_finish<TERMS>(g, tl, gi, b0, v, false, wl, s);
     }
-    tc_pass_advance<TERMS>(tl, UT);
   }
-  { const long long c1 = clock64(); tl.c_l0 += c1 - c0; c0 = c1; }
-  hook();
-  // ---- hidden layers: read D, bias + LeakyReLU, produce the next A units (or reduce the output) ---
-  for (int layer = 0; layer < g.L; ++layer) {
-    const float* bias = tl.sp + (size_t)(3 + layer) * NP;
-    const bool last = layer + 1 == g.L;
-    const float dscale = TERMS == 3 ? 1.0f : tl.sp[tc_scale_index(g, layer)];
-    const uint32_t dcol = tc_wait_d(g, tl, !last);   // the output layer produces no units: no stagger
-    if (last && tl.last_d_bar != nullptr) {
-      __syncwarp();
-      if ((tl.lane & 31) == 0) mbar_arrive(tl.last_d_bar);
-    }
-    { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
-    for (int u = tl.group; u < UT; u += G) {
-      const unsigned gi = tl.unit_idx + (unsigned)u;
-      if (u < g.units) {
-        if (2 * u + 1 < g.KSf) {
-          uint32_t v[32];
-          tc::ld32(tl.taddr + dcol + 32 * u, v);
-          tc::wait_ld();
-          tc_unit_finish<2, TERMS>(g, tl, u, gi, bias, v, last, wl, s, dscale);
-        } else {
-          uint32_t v[16];
-          tc::ld16(tl.taddr + dcol + 32 * u, v);
-          tc::wait_ld();
-          tc_unit_finish<1, TERMS>(g, tl, u, gi, bias, v, last, wl, s, dscale);
-        }
-      } else {
-        uint32_t v[8];
-        tc::ld8(tl.taddr + dcol + 16 * g.KSf, v);
+  tc_pass_advance<TERMS>(tl, UT);
+}
+// one epilogue over the D of a pass: `last` reduces against w_last into s, else produces the next units
+template <int G, int TERMS>
+__device__ __forceinline__ void tc_eval_epilogue(const TcGeom& g, TcLane& tl, int layer, uint32_t dcol,
+                                                 bool last, float (&s)[4]) {
+  const int NP = g.NP, UT = g.units + g.tail;
+  const float* wl = tl.sp + (size_t)(3 + g.L) * NP;
+  const float* bias = tl.sp + (size_t)(3 + layer) * NP;
+  const float dscale = TERMS == 3 ? 1.0f : tl.sp[tc_scale_index(g, layer)];
+  for (int u = tl.group; u < UT; u += G) {
+    const unsigned gi = tl.unit_idx + (unsigned)u;
+    if (u < g.units) {
+      if (2 * u + 1 < g.KSf) {
+        uint32_t v[32];
+        tc::ld32(tl.taddr + dcol + 32 * u, v);
         tc::wait_ld();
-        tc_tail_finish<TERMS>(g, tl, gi, bias, v, last, wl, s, dscale);
+        tc_unit_finish<2, TERMS>(g, tl, u, gi, bias, v, last, wl, s, dscale);
+      } else {
+        uint32_t v[16];
+        tc::ld16(tl.taddr + dcol + 32 * u, v);
+        tc::wait_ld();
+        tc_unit_finish<1, TERMS>(g, tl, u, gi, bias, v, last, wl, s, dscale);
       }
+    } else {
+      uint32_t v[8];
+      tc::ld8(tl.taddr + dcol + 16 * g.KSf, v);
+      tc::wait_ld();
+      tc_tail_finish<TERMS>(g, tl, gi, bias, v, last, wl, s, dscale);
     }
-    if (!last) tc_pass_advance<TERMS>(tl, UT);
-    { const long long c1 = clock64(); tl.c_epi += c1 - c0; if (last) tl.c_last += c1 - c0; c0 = c1; }
   }
+  if (!last) tc_pass_advance<TERMS>(tl, UT);
+}
+// hidden layers 1 .. L-1 (their epilogues produce the units of the next pass), then the wait for the
+// D of the last pass; returns its TMEM column
+template <int G, int TERMS>
+__device__ __forceinline__ uint32_t tc_eval_hidden(const TcGeom& g, TcLane& tl, long long& c0) {
+  float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int layer = 0; layer + 1 < g.L; ++layer) {
+    const uint32_t dcol = tc_wait_d(g, tl, true);
+    { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
+    tc_eval_epilogue<G, TERMS>(g, tl, layer, dcol, false, s);
+    { const long long c1 = clock64(); tl.c_epi += c1 - c0; c0 = c1; }
+  }
+  const uint32_t dcol = tc_wait_d(g, tl, false);   // the output layer produces no units: no stagger
+  if (tl.last_d_bar != nullptr) {
+    __syncwarp();
+    if ((tl.lane & 31) == 0) mbar_arrive(tl.last_d_bar);
+  }
+  { const long long c1 = clock64(); tl.c_wait += c1 - c0; c0 = c1; }
+  return dcol;
+}
+// output layer: dot(h_L, w_last) over this thread's units -> tl.part
+template <int G, int TERMS>
+__device__ __forceinline__ void tc_eval_output(const TcGeom& g, TcLane& tl, uint32_t dcol) {
+  float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  tc_eval_epilogue<G, TERMS>(g, tl, g.L - 1, dcol, true, s);
 #ifdef IKR_TC_TRACE
   ++tl.trace_eval;
 #endif
   tl.part[tl.group * kTcM + tl.lane] = (s[0] + s[1]) + (s[2] + s[3]);
+}
+
+// One MLP evaluation of the 128-trajectory tile, executed by EVERY lane thread (all G groups, masked
+// lanes included).  The caller has published (nv, a) in tl.xin and passed the lanes barrier; the
+// partial output sums land in tl.part (caller syncs).  Group c produces the units u = c (mod G) of
+// every pass.  `hook` runs after this thread's layer-0 units are published, i.e. while the MMAs of
+// layer 1 execute: the owners use it to compute time-only RHS terms of the next stage ahead.
+template <int G, int TERMS = 3, typename Hook = TcNoHook>
+__device__ __forceinline__ void tc_mlp_eval(const TcGeom& g, TcLane& tl, Hook hook = Hook()) {
+  long long c0 = clock64();
+  tc_eval_layer0<G, TERMS>(g, tl);
+  { const long long c1 = clock64(); tl.c_l0 += c1 - c0; c0 = c1; }
+  hook();
+  const uint32_t dcol = tc_eval_hidden<G, TERMS>(g, tl, c0);
+  tc_eval_output<G, TERMS>(g, tl, dcol);
+  { const long long c1 = clock64(); tl.c_epi += c1 - c0; tl.c_last += c1 - c0; }
 }
 
 // Owner-side wrapper: publish the inputs, run the evaluation with the helper groups, collect.
@@ -589,7 +615,7 @@ __device__ __forceinline__ float tc_owner_eval(const TcGeom& g, TcLane& tl, floa
   long long t0 = clock64();
   if (G > 1) lanes_sync<G>();        // inputs visible to the helper groups (cmd word = run)
   { const long long t1 = clock64(); tl.c_sync_a += t1 - t0; }
-  tc_mlp_eval<G, TERMS, false, Hook>(g, tl, hook);
+  tc_mlp_eval<G, TERMS, Hook>(g, tl, hook);
   t0 = clock64();
   if (G > 1) lanes_sync<G>();        // partial sums visible
   { const long long t1 = clock64(); tl.c_sync_b += t1 - t0; }

@@ -14,9 +14,9 @@
 // Threads: 128 owners of X (group 0), 128 owners of Y (group 1), 128 helper threads (group 2), the MMA
 // warp and the weight-producer warp of ikr_forward_tc.cuh -- unchanged: they only see a stream of
 // passes.  An evaluation of tile Z is produced by TWO column groups, owner(Z) and the helper (units
-// u = 0, 2, 4, ... / 1, 3, 5, ...; the first pass -- layer 0 -- by the owner alone, the helper is still
-// reducing the other tile's output then), i.e. it IS the G = 2 evaluation of tc_mlp_eval: results are
-// bit-identical to the single-tile kernels run with two column groups.  The other owner group takes
+// u = 0, 2, 4, ... / 1, 3, 5, ...), i.e. it IS the G = 2 evaluation of tc_mlp_eval: results are
+// bit-identical to the single-tile kernels run with two column groups.  At a tile switch the helper
+// produces its share of the next evaluation's first pass BEFORE it reduces the finished tile's output.  The other owner group takes
 // no part in it -- that is when it runs its solver.
 //
 // Hand-shakes (mbarriers, all phases consumed in order by every waiter):
@@ -166,26 +166,59 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
 
     if (grp == 2) {
       // ============================ helper group: column group 1 of EVERY evaluation ================
+      // Software-pipelined across the tile switch: after the D of tile Z's last pass is there, the
+      // helper first produces its units of the NEXT evaluation's first pass (layer 0 of the other
+      // tile, whose inputs were published long ago) and only then reduces Z's output -- the MMAs of
+      // the next pass must not wait for an output reduction.  When the other tile is gone the next
+      // evaluation is Z's own, whose inputs need Z's output: classic order.
       tl.group = 1;
       unsigned ph[2] = {0u, 0u};
       bool gone[2] = {false, false};
-      int Z = 0;
-      while (true) {
-        mbar_wait(&xin_ready[Z], ph[Z]);
+      long long c0 = clock64();
+      // next_alive(Z): wait for tile Z's turn; false when Z has left the alternation
+      auto turn = [&](int Z) -> bool {
+        if (gone[Z]) return false;
+        mbar_wait_backoff(&xin_ready[Z], ph[Z], 32);
         ph[Z] ^= 1u;
-        if (dead[Z]) {
-          gone[Z] = true;
-          if (gone[Z ^ 1]) break;
-          Z ^= 1;
-          continue;
-        }
+        if (dead[Z]) { gone[Z] = true; return false; }
+        return true;
+      };
+      auto bind = [&](int Z) {
         tl.xin = xin_all + (size_t)Z * 2 * kTcM;
         tl.part = part_all + (size_t)Z * 2 * kTcM;
         tl.last_d_bar = &d_last[Z];
-        tc_mlp_eval<2, TERMS, true>(g, tl);
-        __syncwarp();
-        if ((tl.lane & 31) == 0) mbar_arrive(&part_ready[Z]);
-        if (!gone[Z ^ 1]) Z ^= 1;
+      };
+      int Z = 0;
+      bool running = turn(0);
+      if (!running) { Z = 1; running = turn(1); }
+      if (running) {
+        bind(Z);
+        tc_eval_layer0<2, TERMS>(g, tl);
+      }
+      while (running) {
+        const uint32_t dcol = tc_eval_hidden<2, TERMS>(g, tl, c0);     // evaluation of tile Z
+        float* part_z = tl.part;
+        const int O = Z ^ 1;
+        if (turn(O)) {
+          // pipelined switch: first pass of O's evaluation, then Z's output
+          bind(O);
+          tc_eval_layer0<2, TERMS>(g, tl);
+          tl.part = part_z;
+          tc_eval_output<2, TERMS>(g, tl, dcol);
+          __syncwarp();
+          if ((tl.lane & 31) == 0) mbar_arrive(&part_ready[Z]);
+          tl.part = part_all + (size_t)O * 2 * kTcM;
+          Z = O;
+        } else {
+          tc_eval_output<2, TERMS>(g, tl, dcol);
+          __syncwarp();
+          if ((tl.lane & 31) == 0) mbar_arrive(&part_ready[Z]);
+          running = turn(Z);
+          if (running) {
+            bind(Z);
+            tc_eval_layer0<2, TERMS>(g, tl);
+          }
+        }
       }
       // both tiles are finished: release the engine warps
       if (tl.lane == 0) *stop_flag = 1;
@@ -214,7 +247,7 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
         long long ct = clock64();
         if (!other_gone && !(first_eval && Z == 0)) {
           // the other tile's evaluation that precedes this one in the global sequence
-          mbar_wait(&xin_ready[O], ph_other_xin);
+          mbar_wait_backoff(&xin_ready[O], ph_other_xin, 32);
           ph_other_xin ^= 1u;
           if (dead[O]) other_gone = true;
           else {
@@ -232,7 +265,7 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
         *reinterpret_cast<float2*>(tl.xin + 2 * tl.lane) = make_float2(nv, a);
         __syncwarp();
         if ((tl.lane & 31) == 0) mbar_arrive(&xin_ready[Z]);
-        tc_mlp_eval<2, TERMS, true>(g, tl, [&]() {
+        tc_mlp_eval<2, TERMS>(g, tl, [&]() {
           // before the units of pass 2 (its MMAs overwrite the D the other tile's output reduction read)
           if (wait_other_part) {
             const long long c0 = clock64();

@@ -64,3 +64,43 @@ def test_shard_bounds_and_lpt():
     assert sorted(i for a in assign for i in a) == list(range(12))
     big = [next(r for r, a in enumerate(assign) if i in a) for i in (8, 6, 2)]
     assert len(set(big)) == 3
+
+
+def _flat_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from neural_ode_ion_channels_b200 import parallel
+    flat = torch.arange(10, dtype=torch.float64) * (rank + 1)
+    loss = torch.tensor(float(rank + 1), dtype=torch.float64)
+    out, tot = parallel.allreduce_flat(flat, loss)
+    # the architecture sweep of bench.py: 24 fits, longest first, every fit on exactly one rank
+    costs = [float((i * 7919) % 97 + 1) for i in range(24)]
+    assign = parallel.lpt_assign(costs, world)
+    q.put((rank, out.tolist(), float(tot), assign))
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_and_sweep_assignment_world2():
+    """bench.py's multi-GPU legs on the CPU: ONE flat all-reduce carries the gradient and the loss
+    (train / train1m legs), and the LPT assignment of the 24 sweep fits is a partition that every
+    rank computes identically (no collective on the sweep's data path)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    want = [3.0 * i for i in range(10)]
+    for rank, out, tot, assign in res:
+        assert out == want and tot == 3.0
+        assert sorted(i for part in assign for i in part) == list(range(24))
+    assert res[0][3] == res[1][3]
+    loads = [sum(float((i * 7919) % 97 + 1) for i in part) for part in res[0][3]]
+    total = sum(loads)
+    assert max(loads) <= total / 2 + 97            # LPT: within one largest item of the ideal split
