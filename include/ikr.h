@@ -82,7 +82,9 @@ typedef struct ikr_desc {
                              bit 8: tensor-core forward with the bf16x3 operand split (six MMAs per
                              fp32 product, any activation range) instead of the default fp16x2
                              split (three MMAs; hidden activations must stay below 65504 / 16 in
-                             magnitude -- beyond that the lane reports IKR_NONFINITE)               */
+                             magnitude -- beyond that the conversion saturates);
+                             bit 9: ikr_backward never overlaps the weight-gradient GEMM with the next
+                             adjoint round (default: on a second stream when the batch leaves SMs idle) */
 } ikr_desc;
 
 /* One JOB = one protocol table + one batch of trajectories, i.e. the shape of one reference

@@ -652,15 +652,67 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
 
   long long max_steps = bio->max_accepted_steps > 0 ? bio->max_accepted_steps : io->ckpt_cap;
   if (max_steps > io->ckpt_cap) max_steps = io->ckpt_cap;
-  const long long rounds = max_steps > 0 ? (max_steps + R - 1) / R : 1;
-  for (long long r = 0; r < rounds; ++r) {
-    if (cudaMemsetAsync(ws + pl.off_counters, 0, 256, st) != cudaSuccess) return IKR_ERR_DEVICE;
-    p.first_round = r == 0 ? 1 : 0;
-    const int rc = d->state_dtype == IKR_F32 ? launch_adjoint_tc<float>(tp, pl, st)
-                                             : launch_adjoint_tc<double>(tp, pl, st);
+  // When the adjoint kernel leaves SMs idle (fewer tiles than SMs: e.g. 4,096 datasets = 32 tiles), the
+  // weight-gradient GEMM of round r runs on a second stream UNDER the adjoint kernel of round r + 1:
+  // the stash and the round counters are double-buffered (half the steps per round each), events
+  // order producer and consumer.  The stream and the events live for this call only.
+  const bool overlap = pl.n_tiles * 2 <= pl.sms && R >= 3 && !(d->reserved & 512);
+  if (!overlap) {
+    const long long rounds = max_steps > 0 ? (max_steps + R - 1) / R : 1;
+    for (long long r = 0; r < rounds; ++r) {
+      if (cudaMemsetAsync(ws + pl.off_counters, 0, 256, st) != cudaSuccess) return IKR_ERR_DEVICE;
+      p.first_round = r == 0 ? 1 : 0;
+      const int rc = d->state_dtype == IKR_F32 ? launch_adjoint_tc<float>(tp, pl, st)
+                                               : launch_adjoint_tc<double>(tp, pl, st);
+      if (rc != 0) return rc;
+      ikr_wgrad_tc_kernel<<<(d->n_layers + 2) * pl.wg_S, kWgTcThreads, pl.wg_smem, st>>>(wp);
+      if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
+    }
+  } else {
+    const int R2 = (R - 1) / 2;      // 2 x (6 R2 + 1) slots per tile fit where (6 R + 1) did
+    const size_t half = (size_t)pl.n_tiles * (6 * (size_t)R2 + 1) * (size_t)pl.sg.slot;
+    const long long rounds = max_steps > 0 ? (max_steps + R2 - 1) / R2 : 1;
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_adj[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr};
+    bool ok = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&ev_adj[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ev_wg[i], cudaEventDisableTiming) == cudaSuccess;
+    int rc = ok ? 0 : IKR_ERR_DEVICE;
+    p.steps_per_round = R2;
+    for (long long r = 0; r < rounds && rc == 0; ++r) {
+      const int b = (int)(r & 1);
+      // buffer b was last read by the weight-gradient GEMM of round r - 2
+      if (r >= 2 && cudaStreamWaitEvent(st, ev_wg[b], 0) != cudaSuccess) { rc = IKR_ERR_DEVICE; break; }
+      unsigned char* cnt = ws + pl.off_counters + 128 * b;
+      if (cudaMemsetAsync(cnt, 0, 128, st) != cudaSuccess) { rc = IKR_ERR_DEVICE; break; }
+      p.first_round = r == 0 ? 1 : 0;
+      p.counters = reinterpret_cast<unsigned long long*>(cnt);
+      tp.stash = ws + off_stash + (size_t)b * half;
+      rc = d->state_dtype == IKR_F32 ? launch_adjoint_tc<float>(tp, pl, st)
+                                     : launch_adjoint_tc<double>(tp, pl, st);
+      if (rc != 0) break;
+      if (cudaEventRecord(ev_adj[b], st) != cudaSuccess || cudaStreamWaitEvent(s2, ev_adj[b], 0) != cudaSuccess) {
+        rc = IKR_ERR_DEVICE;
+        break;
+      }
+      wp.stash = tp.stash;
+      wp.counters = p.counters;
+      ikr_wgrad_tc_kernel<<<(d->n_layers + 2) * pl.wg_S, kWgTcThreads, pl.wg_smem, s2>>>(wp);
+      if (cudaGetLastError() != cudaSuccess) { rc = IKR_ERR_LAUNCH; break; }
+      if (cudaEventRecord(ev_wg[b], s2) != cudaSuccess) { rc = IKR_ERR_DEVICE; break; }
+    }
+    // the caller's stream continues after every weight-gradient launch
+    if (ok) {
+      for (int i = 0; i < 2; ++i)
+        if (cudaStreamWaitEvent(st, ev_wg[i], 0) != cudaSuccess && rc == 0) rc = IKR_ERR_DEVICE;
+    }
+    for (int i = 0; i < 2; ++i) {
+      if (ev_adj[i]) cudaEventDestroy(ev_adj[i]);
+      if (ev_wg[i]) cudaEventDestroy(ev_wg[i]);
+    }
+    if (s2) cudaStreamDestroy(s2);
     if (rc != 0) return rc;
-    ikr_wgrad_tc_kernel<<<(d->n_layers + 2) * pl.wg_S, kWgTcThreads, pl.wg_smem, st>>>(wp);
-    if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
   }
 
   TcReduceParams rp;

@@ -39,7 +39,7 @@ from .protocols import compact_table
 _ADAPTIVE_OPTS = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps'}
 _FIXED_OPTS = {'step_size', 'perturb'}
 _EXT_OPTS = {'tile_m', 'check_status', 'compact_table', 'ckpt_cap', 'lane_pool', 'tensor_cores',
-             'tc_groups', 'tc_timing', 'ping_pong', 'tc_split'}
+             'tc_groups', 'tc_timing', 'ping_pong', 'tc_split', 'bwd_overlap'}
 
 
 # =============================================================================================
@@ -173,7 +173,8 @@ def _make_desc(spec: ModelSpec, state_dtype, method, rtol, atol, opts, time_f32=
                   (0 if opts.get('tensor_cores', True) else 2) |
                   (8 if opts.get('tc_timing', False) else 0) | (groups << 4) |
                   (64 if pp is False else 0) | (128 if pp else 0) |
-                  (256 if opts.get('tc_split', None) == 'bf16x3' else 0))
+                  (256 if opts.get('tc_split', None) == 'bf16x3' else 0) |
+                  (0 if opts.get('bwd_overlap', True) else 512))
     return d
 
 

@@ -24,7 +24,7 @@ y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1
 n_out = int(sys.argv[4]) if len(sys.argv) > 4 else len(t_out)
 t = torch.tensor(t_out[:n_out], dtype=dtype)
 with torch.no_grad():
-    for _ in range(2):
+    for _ in range(int(os.environ.get('REPS', '2'))):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         r = ikr.integrate(f, y0, t, want_y=False, want_current=False, data=torch.zeros(len(t)),
@@ -39,6 +39,8 @@ with torch.no_grad():
         nfe = int(r.stats[:, 2].sum())
         ms = e0.elapsed_time(e1)
         st = r.stats.cpu().numpy()
+        if os.environ.get('REPS'):
+            print('  rep: %.2f ms' % ms, flush=True)
         print('%s B=%d %s: %.1f ms, NFE %d, %.2f M evals/s, %.2f TFLOP/s; steps/lane mean %.1f '
               'max %d min %d; geometry %s' % (name, B, dtype, ms, nfe, nfe / ms / 1e3,
                                               nfe * 401200 / ms / 1e9,

@@ -295,3 +295,30 @@ def test_ping_pong_kernel_equals_two_group_tile_kernel(sizes):
             k = int(ra.stats[bb, 0])
             assert torch.equal(ra.ckpt[1][:k, bb], rb.ckpt[1][:k, bb])
             assert torch.equal(ra.ckpt[0][:k, bb], rb.ckpt[0][:k, bb])
+
+
+def test_tc_backward_overlap_of_wgrad_and_next_adjoint_round():
+    """With fewer tiles than half the SMs `ikr_backward` runs the weight-gradient GEMM of round r on a
+    second stream under the adjoint kernel of round r + 1 (double-buffered stash and counters).  Same
+    gradient as the serial schedule up to the summation order of the (shorter) rounds, per-trajectory
+    losses and grad_y0 bit-identical."""
+    func, _ = _pair('d2')
+    func.cuda()
+    t_tab, v_tab = protocols.ap2hz()
+    func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 120., 61)
+    rng = np.random.RandomState(31)
+    B = 300
+    y0 = torch.tensor(np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1, B)], 1),
+                      dtype=torch.float32).cuda()
+    data = torch.from_numpy((rng.randn(len(t), B) * 0.1).astype(np.float32))
+    out = {}
+    with torch.enable_grad():
+        for ov in (True, False):
+            total, per, grads, res = ikr.loss_and_grad(func, y0, t, data, want_y0=True,
+                                                       options={'first_step': 0.05, 'bwd_overlap': ov})
+            out[ov] = (_flat(grads), per.clone(), res.grad_y0.clone())
+    assert torch.equal(out[True][1], out[False][1]) and torch.equal(out[True][2], out[False][2])
+    ref = out[False][0]
+    assert np.abs(out[True][0] - ref).max() <= 2e-5 * np.abs(ref).max()
+    assert np.abs(ref).max() > 0
