@@ -167,7 +167,9 @@ int ikr_launch_geometry(const ikr_desc* d, int32_t n_jobs, const int64_t* B, int
  * desc->reserved bit 1 opts out. */
 int32_t ikr_uses_tensor_cores(const ikr_desc* d);
 
-/* device workspace (caller-allocated) needed by ikr_forward / ikr_backward for n_jobs jobs   */
+/* device workspace (caller-allocated) needed by ikr_forward / ikr_backward for n_jobs jobs.
+ * with_backward: 0 forward only; 1 backward with the default stash of ~4 GiB; n > 1: a stash of ~n GiB
+ * (at most 128, and never more than 64 reversed steps per round need): fewer, longer rounds.      */
 size_t ikr_workspace_bytes(const ikr_desc* d, int32_t n_jobs, int64_t B_total,
                            int32_t with_backward);
 

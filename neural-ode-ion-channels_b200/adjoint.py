@@ -49,7 +49,14 @@ def _run_backward(func, res, *, grad_y=None, fused_loss=0, want_y0=True, want_g=
         bio.grad_weights = grad_flat.data_ptr()
         bio.grad_y0 = grad_y0.data_ptr() if want_y0 else None
         bio.grad_g = grad_g.data_ptr() if want_g else None
-        ws_bytes = workspace_bytes or lib.ikr_workspace_bytes(ctypes.byref(desc), 1, B, 1)
+        if workspace_bytes:
+            ws_bytes = workspace_bytes
+        else:
+            # stash budget: a quarter of the free device memory, between the 4 GiB default and 16 GiB
+            # (a larger stash means fewer, longer adjoint / weight-gradient rounds)
+            free, _ = torch.cuda.mem_get_info(dev)
+            gib = int(max(4, min(16, free // 4 // (1 << 30))))
+            ws_bytes = lib.ikr_workspace_bytes(ctypes.byref(desc), 1, B, gib)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev)
         _cabi.check(lib.ikr_backward(ctypes.byref(desc), ctypes.byref(io), ctypes.byref(bio),

@@ -452,10 +452,10 @@ int bwd_steps_per_round(const BwdPlan& pl, size_t bytes) {
   return (int)(R > 4096 ? 4096 : R);
 }
 
-size_t bwd_workspace_bytes(const ikr_desc* d, long long B) {
+size_t bwd_workspace_bytes(const ikr_desc* d, long long B, int gib = 4) {
   const BwdPlan pl = make_bwd_plan(d, B);
-  // default: a stash of about 4 GiB (both halves), at least one step per round
-  const double target = 4.0 * 1024 * 1024 * 1024;
+  // a stash of about `gib` GiB (both halves; default 4), at least one step per round
+  const double target = (double)gib * 1024 * 1024 * 1024;
   long long R = (long long)((target / 2 / (double)pl.slot_bytes / (double)pl.g.n_tiles - 1) / 6);
   if (R < 1) R = 1;
   if (R > 64) R = 64;
@@ -561,9 +561,9 @@ int tc_bwd_steps_per_round(const TcBwdPlan& pl, size_t bytes) {
   return (int)(R > 4096 ? 4096 : R);
 }
 
-size_t tc_bwd_workspace_bytes(const TcBwdPlan& pl) {
-  // default: a stash of about 4 GiB, at least one step per round
-  const double target = 4.0 * 1024 * 1024 * 1024;
+size_t tc_bwd_workspace_bytes(const TcBwdPlan& pl, int gib = 4) {
+  // a stash of about `gib` GiB (default 4), at least one step per round
+  const double target = (double)gib * 1024 * 1024 * 1024;
   long long R = (long long)((target / (double)pl.sg.slot / (double)pl.n_tiles - 1) / 6);
   if (R < 1) R = 1;
   if (R > 64) R = 64;
@@ -966,7 +966,8 @@ size_t ikr_workspace_bytes(const ikr_desc* d, int32_t n_jobs, int64_t B_total,
   if (tcp.ok) bytes += (tcp.img_bytes + 255) & ~(size_t)255;   // weight image of the tcgen05 path
   if (with_backward) {
     const TcBwdPlan tpl = make_tc_bwd_plan(d, B_total);
-    bytes += tpl.ok ? tc_bwd_workspace_bytes(tpl) : bwd_workspace_bytes(d, B_total);
+    const int gib = with_backward > 1 ? (with_backward > 128 ? 128 : with_backward) : 4;
+    bytes += tpl.ok ? tc_bwd_workspace_bytes(tpl, gib) : bwd_workspace_bytes(d, B_total, gib);
   }
   return bytes;
 }

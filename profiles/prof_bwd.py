@@ -30,7 +30,7 @@ t = torch.tensor(t_out[:n_out], dtype=dtype)
 data = torch.from_numpy(rng.randn(n_out, 1).astype(np.float32) * 0.1).to(dtype)
 f.cuda()
 cap = int(os.environ.get('CKPT_CAP', '0')) or None
-for _ in range(2):
+for _ in range(int(os.environ.get('REPS', '2'))):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
     opts = {'check_status': False, 'tensor_cores': not os.environ.get('NO_TC'),
