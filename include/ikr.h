@@ -41,6 +41,9 @@ extern "C" {
 #define IKR_MAX_STEPS 2     /* "max_num_steps exceeded"              */
 #define IKR_NONFINITE 3     /* "non-finite values in state `y`"      */
 #define IKR_CKPT_OVERFLOW 4 /* step-checkpoint capacity too small    */
+#define IKR_TC_RANGE 5      /* fp16x2 tensor-core forward: a hidden activation of an ACCEPTED step left
+                               the fp16 range (|h| >= 4094) in the physical domain; rerun with reserved bit 8
+                               (bf16x3 split) or bit 1 (FFMA2 kernel)                                 */
 /* return codes (0 ok, negative = argument / launch error) */
 #define IKR_ERR_ARG (-1)
 #define IKR_ERR_UNSUPPORTED (-2)
@@ -82,7 +85,8 @@ typedef struct ikr_desc {
                              bit 8: tensor-core forward with the bf16x3 operand split (six MMAs per
                              fp32 product, any activation range) instead of the default fp16x2
                              split (three MMAs; hidden activations must stay below 65504 / 16 in
-                             magnitude -- beyond that the conversion saturates);
+                             magnitude -- beyond that trial steps are rejected and, in the physical domain,
+                             the lane ends with IKR_TC_RANGE);
                              bit 9: ikr_backward never overlaps the weight-gradient GEMM with the next
                              adjoint round (default: on a second stream when the batch leaves SMs idle) */
 } ikr_desc;

@@ -17,6 +17,8 @@ STATUS_TEXT = {
     2: 'max_num_steps exceeded',
     3: 'non-finite values in state `y`',
     4: 'step-checkpoint capacity exceeded',
+    5: "a hidden activation left the range of the fp16x2 tensor-core split on an accepted step; "
+       "use options={'tc_split': 'bf16x3'} or {'tensor_cores': False}",
 }
 
 c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p

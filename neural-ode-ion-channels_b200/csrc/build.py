@@ -14,11 +14,15 @@ NVCC_FLAGS = [
     '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
     '-fmad=false',          # solver arithmetic must not be contracted (torchdiffeq semantics);
                             # the MLP inner loops use explicit fma intrinsics
-    '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v', '--expt-relaxed-constexpr',
+    '-Xcompiler', '-fPIC', '-shared', '--expt-relaxed-constexpr',
     # link the CUDA runtime dynamically: the process already holds libcudart.so.12 (torch's), and the
     # shipped binary then carries none of the runtime's unused entry-point names
     '-cudart', 'shared', '-Xlinker', '-rpath,/usr/local/cuda/lib64',
-    '-split-compile', '0',   # optimise the kernels of this one translation unit in parallel
+    # PTX -> SASS of the kernels in parallel.  Only ptxas: nvcc's own -split-compile also splits the
+    # NVVM optimiser, whose output then differs from build to build (two PTX variants of the same
+    # source were observed; in one of them %tid and the tile geometry are re-read at every use and
+    # the tensor-core forward is 24 % slower) -- tests/test_cabi_host.py checks the shipped SASS.
+    '-Xptxas', '-v,-split-compile=0',
 ]
 
 

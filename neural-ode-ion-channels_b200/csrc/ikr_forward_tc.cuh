@@ -787,6 +787,38 @@ __device__ __forceinline__ void tc_producer_thread(const TcGeom& g, const TcEngi
     mbar_wait(&c.bar_full[q % stages], (q / stages) & 1u);
 }
 
+// fp16x2 split, owner side: a non-finite MLP output for finite inputs means that a hidden activation
+// left the fp16 range (ikr_tc.cuh pack_f16x2).  The output is replaced by a huge finite value, so that
+// the dopri5 step is REJECTED with the controller's smallest factor -- what the reference does with
+// the finite, huge derivative it computes for such a wild trial stage -- and `hit` is raised.  A hit at
+// the initial evaluations, on an rk4 step, or on kTcRangeRejects rejected attempts in a row is a
+// range violation in the physical domain: the lane ends with LANE_RANGE (IKR_TC_RANGE).
+constexpr int kTcRangeRejects = 12;
+template <int TERMS>
+__device__ __forceinline__ float tc_range_filter(float out, double nv, double a, bool& hit) {
+  if (TERMS == 2 && !isfinite(out) && isfinite((float)nv) && isfinite((float)a)) {
+    hit = true;
+    return 1.0e30f;
+  }
+  return out;
+}
+template <int TERMS, typename S>
+__device__ __forceinline__ void tc_range_after_step(Lane<S>& L, bool accepted, bool& hit, int& rejects) {
+  if (TERMS != 2) return;
+  if (hit) {
+    rejects = accepted ? kTcRangeRejects : rejects + 1;
+    if (rejects >= kTcRangeRejects && (L.status == LANE_OK || L.status == LANE_DONE)) L.status = LANE_RANGE;
+  } else if (accepted) {
+    rejects = 0;
+  }
+  hit = false;
+}
+template <int TERMS, typename S>
+__device__ __forceinline__ void tc_range_fatal(Lane<S>& L, bool& hit) {
+  if (TERMS == 2 && hit && (L.status == LANE_OK || L.status == LANE_DONE)) L.status = LANE_RANGE;
+  hit = false;
+}
+
 // element i = (row, c) of the zero-padded small-parameter block kept in shared memory: rows w0a | w0b |
 // b0 | L x hidden bias | w_last, then b_last and the per-layer accumulator scales.  The fp16x2 path
 // works on 16 x the activations (kTcActShift): w0, b0 and the hidden biases are stored x 16, w_last
@@ -963,17 +995,20 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
         }
 
         double nv, ain;
+        bool range_hit = false;
+        int range_rejects = 0;
         if (p.method == 0) {
           init_prepare_f0<S>(L, cfg, &nv, &ain);
-          float out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain);
+          float out = tc_range_filter<TERMS>(tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain), nv, ain, range_hit);
           init_store_f0<S>(L, cfg, (double)out);
           if (cfg.first_step > 0) {
             L.dt = cfg.first_step;
           } else {
             init_prepare_f1<S>(L, cfg, &nv, &ain);
-            out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain);
+            out = tc_range_filter<TERMS>(tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain), nv, ain, range_hit);
             init_store_f1<S>(L, cfg, (double)out);
           }
+          tc_range_fatal<TERMS, S>(L, range_hit);
           if (T <= 1 && lane_active(L)) L.status = LANE_DONE;
 
           TimeCache tcache;
@@ -988,10 +1023,13 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
               out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain, [&]() {
                 if (s < 5 && lane_active(L)) dp_prefetch_stage_time<S>(L, cfg, s + 1, tcache);
               });
+              out = tc_range_filter<TERMS>(out, nv, ain, range_hit);
               dp_store_stage<S>(L, cfg, s, (double)out);
             }
             const long long cf0 = clock64();
+            const int acc0 = L.n_acc;
             dp_finish_step<S>(L, cfg, job.t_out, T, emit, ckpt);
+            tc_range_after_step<TERMS, S>(L, L.n_acc != acc0, range_hit, range_rejects);
             c_finish += clock64() - cf0;
           }
         } else {
@@ -1002,9 +1040,10 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_kernel(const 
 #pragma unroll 1
             for (int s = 0; s < 4; ++s) {
               rk4_prepare_stage<S>(L, cfg, s, g0, g1, p.time_f32 != 0, p.rk4_perturb != 0, &nv, &ain);
-              const float out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain);
+              const float out = tc_range_filter<TERMS>(tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain), nv, ain, range_hit);
               rk4_store_stage<S>(L, cfg, s, (double)out);
             }
+            tc_range_fatal<TERMS, S>(L, range_hit);
             if (lane_active(L)) {
               // step checkpoint for the backward sweep: (g0, g1), y0, k1..k4
               L.t0 = g0; L.dt = g1;
@@ -1145,6 +1184,8 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
       lane_reset<S>(L, (S)0, (S)1, 0.0, false);
       A.mode = POOL_EMPTY; A.job = 0; A.b = 0; A.g = (S)1; A.e = (S)0;
       bool queue_dry = false;
+      bool range_hit = false;
+      int range_rejects = 0;
 
       while (true) {
         // ---- round boundary: retire finished trajectories, refill free slots ----------------------
@@ -1174,6 +1215,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
             A.g = job.g ? reinterpret_cast<const S*>(job.g)[b] : (S)1;
             A.e = job.e_rev ? reinterpret_cast<const S*>(job.e_rev)[b] : (S)job.e_scalar;
             lane_reset<S>(L, y0[2 * b], y0[2 * b + 1], job.t_out[0], true);
+            range_hit = false; range_rejects = 0;
             obs[2 * tid] = 0.0; obs[2 * tid + 1] = 0.0;
           } else {
             queue_dry = true;
@@ -1194,9 +1236,10 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
             else if (what == 2) init_prepare_f0<S>(L, c, &nv, &ain);
             else init_prepare_f1<S>(L, c, &nv, &ain);
           }
-          const float out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain, [&]() {
+          float out = tc_owner_eval<G, TERMS>(g, tl, (float)nv, (float)ain, [&]() {
             if (what == 1 && s < 5) dp_prefetch_stage_time<S>(L, c, s + 1, tcache);
           });
+          if (what) out = tc_range_filter<TERMS>(out, nv, ain, range_hit);
           if (what == 1) dp_store_stage<S>(L, c, s, (double)out);
           else if (what == 2) {
             init_store_f0<S>(L, c, (double)out);
@@ -1250,8 +1293,11 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_forward_tc_pool_kernel(c
             }
             return true;
           };
+          const int acc0 = L.n_acc;
           dp_finish_step<S>(L, c, job.t_out, job.T, emit, ckpt);
+          tc_range_after_step<TERMS, S>(L, L.n_acc != acc0, range_hit, range_rejects);
         } else if (A.mode == POOL_INIT) {
+          tc_range_fatal<TERMS, S>(L, range_hit);      // f0 / the initial-step probe sit at y0
           // start-up done: emit y(t[0]) = y0 and start stepping (or finish if there is one output)
           const FwdJob& job = *jobp;
           const long long b = A.b;

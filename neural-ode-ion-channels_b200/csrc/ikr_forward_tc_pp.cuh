@@ -297,6 +297,8 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
       lane_reset<S>(L, (S)0, (S)1, 0.0, false);
       A.mode = POOL_EMPTY; A.job = 0; A.b = 0; A.g = (S)1; A.e = (S)0;
       bool queue_dry = false;
+      bool range_hit = false;
+      int range_rejects = 0;
 
       while (true) {
         // ---- round boundary: retire finished trajectories, refill free slots ----------------------
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
             A.g = job.g ? reinterpret_cast<const S*>(job.g)[b] : (S)1;
             A.e = job.e_rev ? reinterpret_cast<const S*>(job.e_rev)[b] : (S)job.e_scalar;
             lane_reset<S>(L, y0[2 * b], y0[2 * b + 1], job.t_out[0], true);
+            range_hit = false; range_rejects = 0;
             obs[2 * slot] = 0.0; obs[2 * slot + 1] = 0.0;
           } else {
             queue_dry = true;
@@ -346,9 +349,10 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
             else if (what == 2) init_prepare_f0<S>(L, c, &nv, &ain);
             else init_prepare_f1<S>(L, c, &nv, &ain);
           }
-          const float out = owner_eval((float)nv, (float)ain, [&]() {
+          float out = owner_eval((float)nv, (float)ain, [&]() {
             if (what == 1 && s < 5) dp_prefetch_stage_time<S>(L, c, s + 1, tcache);
           });
+          if (what) out = tc_range_filter<TERMS>(out, nv, ain, range_hit);
           if (what == 1) dp_store_stage<S>(L, c, s, (double)out);
           else if (what == 2) {
             init_store_f0<S>(L, c, (double)out);
@@ -402,8 +406,11 @@ __global__ void __launch_bounds__(tc_threads(3), 1) ikr_forward_tc_pp_kernel(con
             }
             return true;
           };
+          const int acc0 = L.n_acc;
           dp_finish_step<S>(L, c, job.t_out, job.T, emit, ckpt);
+          tc_range_after_step<TERMS, S>(L, L.n_acc != acc0, range_hit, range_rejects);
         } else if (A.mode == POOL_INIT) {
+          tc_range_fatal<TERMS, S>(L, range_hit);      // f0 / the initial-step probe sit at y0
           const FwdJob& job = *jobp;
           const long long b = A.b;
           if (job.y_out) {

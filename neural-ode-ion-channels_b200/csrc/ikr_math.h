@@ -393,7 +393,7 @@ IKR_HD S observe_current(S g, S a, S r, double v, S e) {
 // shared memory (one owner thread per lane); the host logic test keeps one on the stack.
 // ==========================================================================================
 enum LaneStatus { LANE_OK = 0, LANE_DT_UNDERFLOW = 1, LANE_MAX_STEPS = 2, LANE_NONFINITE = 3,
-                  LANE_CKPT_OVERFLOW = 4, LANE_DONE = 100, LANE_EMPTY = 101 };
+                  LANE_CKPT_OVERFLOW = 4, LANE_RANGE = 5, LANE_DONE = 100, LANE_EMPTY = 101 };
 
 template <typename S>
 struct Lane {

@@ -253,15 +253,15 @@ __device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
 // number (|x| >= 2^-2 after the caller's power-of-two scaling), |e| <= 2^-25 absolute below that.  With
 // both operands split this way the three products t1 u1 + t2 u1 + t1 u2 carry an fp32 product to
 // ~3 x 2^-24 relative -- the same bound as the six-product bf16x3 scheme -- at half the MMAs.
-// The caller scales its values by a power of two (exact) so that they sit inside the fp16 range.
-// The conversion SATURATES (a value beyond +-65504 becomes +-65504, never inf): an adaptive solver
-// probes wild trial states (a stage state far outside [0, 1] after a tenfold step growth) whose
-// activations can leave the range; the reference computes a finite, huge derivative there and rejects
-// the step, and so must this path -- an inf would turn into NaN inside the MMA (inf - inf) and poison
-// the step-size controller instead.  Values on accepted steps are 50 x inside the range.
+// The caller scales its values by a power of two (exact) so that they sit inside the fp16 range.  A
+// value beyond +-65504 converts to inf in the FIRST term and the MMA turns the products of that lane
+// into inf / NaN: the whole evaluation of the lane comes out non-finite and the OWNER handles it
+// (tc_range_filter in ikr_forward_tc.cuh) -- a wild trial stage of the adaptive solver is rejected
+// like the reference rejects it, a range violation in the physical domain ends the lane with
+// IKR_TC_RANGE.  No per-value check on the hot path.
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 __device__ __forceinline__ f32x2_t unpack_f16x2(uint32_t w) {

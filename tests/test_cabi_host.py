@@ -228,3 +228,33 @@ def test_no_cpu_fallback():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match='no CPU fallback'):
             ikr.odeint(f, torch.tensor([[0., 1.]]), torch.linspace(0., 1., 3))
+
+
+def test_shipped_sass_keeps_thread_index_and_geometry_in_registers(lib):
+    """Code-generation guard for the tensor-core forward kernels.  nvcc's `-split-compile` splits
+    the NVVM optimiser and was seen to emit two different PTX files for the same source from one
+    build to the next; in one of them %tid and the tile geometry are rematerialised at every use
+    (114 instead of 10-15 S2R in the tile kernel, 159 instead of 161-168 registers) and the
+    18,944-trajectory tile benchmark takes 32.5 instead of 26.3 ms.  csrc/build.py therefore
+    parallelises ptxas only; this test reads the shipped library's SASS so that a slow variant
+    cannot ship unnoticed."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    path = _cabi.LIB_PATH
+    sass = subprocess.run([cuobjdump, '-sass', path], capture_output=True, text=True, check=True).stdout
+    counts, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r'Function : (\S+)', line)
+        if m:
+            cur = m.group(1)
+            continue
+        if cur and ' S2R ' in line:
+            counts[cur] = counts.get(cur, 0) + 1
+    hot = {k: v for k, v in counts.items()
+           if re.match(r'_ZN3ikr(21ikr_forward_tc_kernel|26ikr_forward_tc_pool_kernel)IfLi2ELi2E', k)}
+    assert len(hot) == 2, sorted(counts)[:5]
+    for name, n in hot.items():
+        assert n < 40, '%s: %d S2R -- the slow code-generation variant (see csrc/build.py)' % (name, n)

@@ -238,7 +238,7 @@ def test_tc_lane_pool_kernel_equals_tile_scheduled_kernel():
 
 def test_fp16x2_split_survives_wild_trial_steps():
     """The default operand split of the tensor-core forward (fp16x2, three MMAs per fp32 product)
-    saturates instead of overflowing: a first step of 2,000 ms throws the stage states far outside
+    survives activations beyond the fp16 range: a first step of 2,000 ms throws the stage states far outside
     [0, 1] (hidden activations beyond the fp16 range); the reference computes finite garbage there
     and rejects the step, and so must this path -- every lane ends with status ok and the traces
     agree with the bf16x3 split and the FFMA2 kernel at the solver's fp32 noise level."""
@@ -322,3 +322,30 @@ def test_tc_backward_overlap_of_wgrad_and_next_adjoint_round():
     ref = out[False][0]
     assert np.abs(out[True][0] - ref).max() <= 2e-5 * np.abs(ref).max()
     assert np.abs(ref).max() > 0
+
+
+def test_fp16x2_range_violation_on_an_accepted_step_is_reported():
+    """A network whose hidden activations leave the fp16x2 range IN the physical domain (layer 4 scaled
+    by 1,000 and the next layer by 1 / 1,000: the same function, LeakyReLU is positively homogeneous)
+    must not integrate silently wrong: the lane ends with status IKR_TC_RANGE and `odeint` raises with
+    the remedy in the message; the bf16x3 split (no range restriction) integrates it like the FFMA2
+    kernel integrates the unscaled network."""
+    func, _ = _pair('d1')
+    big, _ = _pair('d1')
+    with torch.no_grad():
+        big.net[8].weight *= 1000.0
+        big.net[8].bias *= 1000.0
+        big.net[10].weight /= 1000.0
+    t_tab, v_tab = protocols.pr3_activation(20)
+    for f in (func, big):
+        f.set_fixed_form_voltage_protocol(t_tab, v_tab)
+    t = torch.linspace(0., 2000., 201)
+    y0 = torch.tensor([[0.01, 0.97], [0.03, 0.96]], dtype=torch.float32).cuda()
+    with pytest.raises(AssertionError, match='fp16x2'):
+        ikr.integrate(big, y0, t)
+    r = ikr.integrate(big, y0, t, options={'check_status': False})
+    assert set(r.stats[:, 3].tolist()) == {5}
+    ok = ikr.integrate(big, y0, t, options={'tc_split': 'bf16x3'})
+    ref = ikr.integrate(func, y0, t, options={'tensor_cores': False})
+    assert int((ok.stats[:, 3] != 0).sum()) == 0
+    assert (ok.y - ref.y).abs().max().item() < 5e-4
