@@ -37,6 +37,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The `sweep` leg runs up to 24 fits on as many CUDA streams; with the default of 8 hardware work
+# queues the launches of one fit queue behind another fit's long-running persistent kernel.  Must be
+# set before CUDA initialises (a user's own setting wins).
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 FAMILY_SWEEP = {'pr3': 4, 'pr4': 10, 'pr5': 4, 'sinewave': 0, 'aps': 0}   # sweep index per family
 WDIR = os.path.join(ROOT, 'neural-ode-ion-channels_b200', 'data', 'weights')
 WEIGHTS = os.path.join(WDIR, 'd1-model-state-dict.pt')
@@ -121,6 +126,8 @@ def parse_args():
     ap.add_argument('--sweep-batch', type=int, default=256)
     ap.add_argument('--sweep-outputs', type=int, default=200)
     ap.add_argument('--sweep-iters', type=int, default=2)
+    ap.add_argument('--sweep-concurrency', type=int, default=0,
+                    help='0: all fits of a rank concurrently (threads + streams); 1: one after the other')
     ap.add_argument('--train1m-total', type=int, default=1048576)
     ap.add_argument('--train1m-chunk', type=int, default=65536)
     return ap.parse_args()
@@ -499,80 +506,136 @@ def run_sweep_leg(args, ikr, dev, world, rank):
     rng = np.random.RandomState(4000)
     y0np = np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1.0, B)], 1)
     noise = rng.normal(0, 0.05, (len(t_out), B))
-    mine = []
-    for idx in assign[rank]:
+    # Every fit of this rank runs in its own host thread on its own CUDA stream: a fit on 256
+    # datasets is two tiles, i.e. a latency-bound chain on 2 of 148 SMs, so the fits of a rank
+    # overlap on the GPU (--sweep-concurrency 1: one after the other, the round-1 behaviour).
+    # Models are built here, in order, so that both modes start from the same seeded weights.
+    jobs = []
+    for idx in sorted(assign[rank], key=lambda i: -costs[i]):
         arch, f64 = fits[idx]
-        L, n = ikr.ARCHITECTURES[arch]
-        dtype = torch.float64 if f64 else torch.float32
         torch.manual_seed(0)
         func = ikr.ODEFuncNNf(arch=arch, params='r')
         if f64:
             func = func.double()
-        func = func.to(dev)
-        func.set_fixed_form_voltage_protocol(t_tab, v_tab)
-        t = torch.tensor(t_out, dtype=dtype)
-        y0 = torch.tensor(y0np, dtype=dtype, device=dev)
+        jobs.append((arch, f64, func.to(dev)))
+    concurrent = args.sweep_concurrency != 1 and len(jobs) > 1
+    wall = {'start': torch.cuda.Event(enable_timing=True), 'end': torch.cuda.Event(enable_timing=True)}
+
+    def start_clock():
+        torch.cuda.synchronize()
+        wall['start'].record()
+    gate = threading.Barrier(len(jobs), action=start_clock, timeout=900) if concurrent else None
+    start_clock()      # (re-recorded by the barrier when every fit has finished its warm-up)
+
+    def fit(arch, f64, func, stream):
+        L, n = ikr.ARCHITECTURES[arch]
+        dtype = torch.float64 if f64 else torch.float32
         entry = {'arch': arch, 'dtype': 'f64' if f64 else 'f32', 'L': L, 'n': n, 'macs': macs_of(L, n)}
+        waited = False
         try:
-            with torch.no_grad():
-                nominal = ikr.integrate(func, torch.tensor([[0.01, 0.98]], dtype=dtype, device=dev), t,
-                                        want_current=True, want_y=False, g=0.1339 * 1.2, E=-93.4).current
-            data = (0.8 * nominal + torch.tensor(noise, dtype=dtype, device=dev)).contiguous()
-            opt = torch.optim.Adam(func.net.parameters(), lr=1e-3)
-            plist = list(func.net.parameters())
-            opts = {'check_status': False, 'ckpt_cap': 1024}
-            evals = evals_b = 0.0
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-            for it in range(args.sweep_iters + 1):        # iteration 0 = warm-up
-                if it == 1:
-                    torch.cuda.synchronize()
-                    ev[0].record()
-                total, per, grads, res = ikr.loss_and_grad(func, y0, t, data, g=0.1339 * 1.2, E=-93.4,
-                                                           options=opts)
-                for p, g in zip(plist, grads):
-                    p.grad = (g / B).to(p.dtype)
-                opt.step()
-                if it >= 1:
-                    evals_b += float((6 * res.stats[:, 0] + 1).sum())
-                    evals += float(res.stats[:, 2].sum()) + float((6 * res.stats[:, 0] + 1).sum())
-                bad = int((res.stats[:, 3] != 0).sum())
-                tcores = bool(res.geometry.get('tensor_cores'))
-                del res
-            ev[1].record()
-            torch.cuda.synchronize()
+            with torch.cuda.stream(stream):
+                func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+                t = torch.tensor(t_out, dtype=dtype)
+                y0 = torch.tensor(y0np, dtype=dtype, device=dev)
+                with torch.no_grad():
+                    nominal = ikr.integrate(func, torch.tensor([[0.01, 0.98]], dtype=dtype, device=dev), t,
+                                            want_current=True, want_y=False, g=0.1339 * 1.2, E=-93.4).current
+                data = (0.8 * nominal + torch.tensor(noise, dtype=dtype, device=dev)).contiguous()
+                opt = torch.optim.Adam(func.net.parameters(), lr=1e-3)
+                plist = list(func.net.parameters())
+                opts = {'check_status': False, 'ckpt_cap': 1024, 'stash_gib': 2}
+                evals = evals_b = 0.0
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                for it in range(args.sweep_iters + 1):        # iteration 0 = warm-up
+                    if it == 1:
+                        stream.synchronize()
+                        if gate is not None:
+                            waited = True
+                            gate.wait()                       # all fits of the rank start together
+                        ev[0].record(stream)
+                    total, per, grads, res = ikr.loss_and_grad(func, y0, t, data, g=0.1339 * 1.2, E=-93.4,
+                                                               options=opts)
+                    for p, g in zip(plist, grads):
+                        p.grad = (g / B).to(p.dtype)
+                    opt.step()
+                    if it >= 1:
+                        evals_b += float((6 * res.stats[:, 0] + 1).sum())
+                        evals += float(res.stats[:, 2].sum()) + float((6 * res.stats[:, 0] + 1).sum())
+                    bad = int((res.stats[:, 3] != 0).sum())
+                    tcores = bool(res.geometry.get('tensor_cores'))
+                    del res
+                ev[1].record(stream)
+                stream.synchronize()
             ms = ev[0].elapsed_time(ev[1])
             entry.update({'ms': ms, 'evals': evals, 'evals_per_s': evals / (ms * 1e-3),
                           # forward eval = 2 MACs FLOP, adjoint eval = 2 x that
                           'tflops': (evals + evals_b) * 2 * macs_of(L, n) / (ms * 1e-3) / 1e12,
                           'kernel': 'tcgen05' if tcores else ('DFMA' if f64 else 'FFMA2'),
                           'status_bad': bad, 'loss': float(total), 'rank': rank})
-        except RuntimeError as exc:   # an unsupported configuration is reported, not hidden
-            entry.update({'ms': 0.0, 'evals': 0.0, 'error': str(exc)[:160], 'rank': rank})
-        mine.append(entry)
-        del func
-        torch.cuda.empty_cache()
+        except threading.BrokenBarrierError:
+            entry.update({'ms': 0.0, 'evals': 0.0, 'error': 'another fit of this rank never reached the start',
+                          'rank': rank})
+        except Exception as exc:      # an unsupported configuration is reported, not hidden
+            entry.update({'ms': 0.0, 'evals': 0.0, 'error': ('%s: %s' % (type(exc).__name__, exc))[:160],
+                          'rank': rank})
+            if gate is not None and not waited:
+                try:
+                    gate.wait()       # the other fits of the rank must not wait for this one
+                except threading.BrokenBarrierError:
+                    pass
+        return entry
+
+    if concurrent:
+        mine = [None] * len(jobs)
+
+        def worker(k):
+            torch.cuda.set_device(dev)
+            mine[k] = fit(*jobs[k], torch.cuda.Stream(device=dev))
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(jobs))]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        torch.cuda.synchronize()
+        wall['end'].record()
+        wall['end'].synchronize()
+        rank_ms = wall['start'].elapsed_time(wall['end'])
+    else:
+        mine = []
+        for job in jobs:
+            mine.append(fit(*job, torch.cuda.current_stream(dev)))
+            torch.cuda.empty_cache()
+        rank_ms = sum(e['ms'] for e in mine)
+    del jobs
+    torch.cuda.empty_cache()
+    mine = [{'rank_ms': rank_ms, 'fits': mine}]
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
-        entries = [e for part in gathered for e in part]
+        parts = [part[0] for part in gathered]
     else:
-        entries = mine
+        parts = mine
     if rank != 0:
         return None
-    per_rank = [sum(e['ms'] for e in entries if e['rank'] == r) for r in range(world)]
-    total_ms = sum(per_rank)
+    entries = [e for part in parts for e in part['fits']]
+    per_rank = [part['rank_ms'] for part in parts]
+    serial_ms = sum(e['ms'] for e in entries)
     longest = max(e['ms'] for e in entries)
-    ideal = max(total_ms / world, longest)
+    # lower bound of the makespan: the longest single fit; one fit after the other on every rank
+    # (concurrency 1) cannot beat the mean load per rank either
+    ideal = longest if args.sweep_concurrency != 1 else max(serial_ms / world, longest)
     order = {a: i for i, a in enumerate(ikr.ARCHITECTURES)}
     entries.sort(key=lambda e: (order[e['arch']], e['dtype']))
     return {
         'workload': 'configs[3]: %d independent NN-f fits (s00-s11 x fp32/fp64), %d Adam iterations of '
                     'loss + gradient through dopri5 on %d noisy %s datasets (%d outputs) each, LPT-'
-                    'assigned to %d rank(s), no data-path collective'
-                    % (len(fits), args.sweep_iters, B, name, len(t_out), world),
+                    'assigned to %d rank(s), %s, no data-path collective'
+                    % (len(fits), args.sweep_iters, B, name, len(t_out), world,
+                       'the fits of a rank concurrently (one host thread and CUDA stream each)'
+                       if args.sweep_concurrency != 1 else 'one fit after the other on a rank'),
         'value': sum(e['evals'] for e in entries) / (max(per_rank) * 1e-3), 'unit': 'evals/s (fwd + adjoint)',
         'makespan_ms': max(per_rank), 'ideal_ms': ideal, 'makespan_over_ideal': max(per_rank) / ideal,
-        'per_rank_ms': per_rank, 'fits': entries,
+        'per_rank_ms': per_rank, 'sum_of_fit_ms': serial_ms, 'longest_fit_ms': longest, 'fits': entries,
     }
 
 

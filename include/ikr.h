@@ -6,7 +6,9 @@
  * backward.  Each entry point cites the reference interface it replaces (paths relative to the
  * reference checkout).  Plain pointers and sizes only; no torch types; every buffer (including
  * the workspace) is owned by the caller; the library keeps no device allocation and no global
- * state; calls are stream-ordered and never synchronise.
+ * state; calls are stream-ordered and never synchronise.  Thread safety: any number of host
+ * threads may call into the library at the same time, each on its own stream with its own
+ * buffers (independent fits of an architecture sweep share one GPU that way).
  *
  * Replaces, on the reference side:
  *   - `torchdiffeq.odeint(func, y0, t[, method='dopri5'])`     train-s1.py:322,327; table-1.py:404,413;

@@ -24,7 +24,7 @@ _LOSSES = {'sse': 1, 'sae': 2}
 
 
 def _run_backward(func, res, *, grad_y=None, fused_loss=0, want_y0=True, want_g=False,
-                  workspace_bytes=None):
+                  workspace_bytes=None, stash_gib=None):
     """Call ``ikr_backward`` for the forward result ``res`` (needs ``want_ckpt=True``).
     Returns (flat fp64 parameter gradient, grad_y0 or None, grad_g or None)."""
     desc, io = res._desc, res._io
@@ -54,8 +54,9 @@ def _run_backward(func, res, *, grad_y=None, fused_loss=0, want_y0=True, want_g=
         else:
             # stash budget: a quarter of the free device memory, between the 4 GiB default and 16 GiB
             # (a larger stash means fewer, longer adjoint / weight-gradient rounds)
+            # (`stash_gib`: the caller's own figure, e.g. many small fits sharing one GPU)
             free, _ = torch.cuda.mem_get_info(dev)
-            gib = int(max(4, min(16, free // 4 // (1 << 30))))
+            gib = int(stash_gib) if stash_gib else int(max(4, min(16, free // 4 // (1 << 30))))
             ws_bytes = lib.ikr_workspace_bytes(ctypes.byref(desc), 1, B, gib)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev)
@@ -165,7 +166,8 @@ def loss_and_grad(func, y0, t, data, *, g=None, E=-86.0, loss='sse', rtol=1e-7, 
                              g=g, E=E, data=data, want_y=True, want_current=False)
     per_traj = res.sse if loss == 'sse' else res.sae
     flat, grad_y0, grad_g = _run_backward(func, res, fused_loss=_LOSSES[loss], want_y0=want_y0,
-                                          want_g=want_g, workspace_bytes=workspace_bytes)
+                                          want_g=want_g, workspace_bytes=workspace_bytes,
+                                          stash_gib=(options or {}).get('stash_gib'))
     spec = describe(func)
     grads = unpack_grads(spec, flat)
     if accumulate:

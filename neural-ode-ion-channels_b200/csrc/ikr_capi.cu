@@ -48,6 +48,20 @@ int device_sms() {
   return sms > 0 ? sms : 148;
 }
 
+// Dynamic shared memory limit of a kernel.  The attribute belongs to the kernel, i.e. to every host
+// thread of the process: it is always raised to the device's opt-in maximum, never to the size of
+// the launch at hand, so that concurrent callers with different geometries (one fit per thread and
+// stream, bench.py `sweep`) cannot undercut each other between the attribute call and the launch.
+template <typename K>
+cudaError_t allow_max_smem(K kern, size_t needed) {
+  int dev = 0, optin = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+    return cudaErrorUnknown;
+  if (needed > (size_t)optin) return cudaErrorInvalidValue;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+}
+
 bool valid_desc(const ikr_desc* d) {
   if (!d) return false;
   if (d->n_layers < 1 || d->n_nodes < 1 || d->n_nodes > 4096) return false;
@@ -305,7 +319,7 @@ TcPpPlan make_tc_pp_plan(const ikr_desc* d, const TcPlan& fw) {
 template <typename S>
 int launch_forward_tc_pp(const TcFwdParams& tp, const TcPpPlan& t, int grid, cudaStream_t st) {
   auto kern = tp.g.terms == 2 ? ikr_forward_tc_pp_kernel<S, 2> : ikr_forward_tc_pp_kernel<S, 3>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) !=
+  if (allow_max_smem(kern, t.smem) !=
       cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
@@ -321,7 +335,7 @@ size_t fwd_fixed_workspace(int n_jobs) {
 template <typename S, int G, int TERMS>
 int launch_forward_tc_g(const TcFwdParams& tp, const TcPlan& t, int grid, cudaStream_t st, bool pool) {
   auto kern = pool ? ikr_forward_tc_pool_kernel<S, G, TERMS> : ikr_forward_tc_kernel<S, G, TERMS>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) !=
+  if (allow_max_smem(kern, t.smem) !=
       cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
@@ -346,7 +360,7 @@ int launch_forward_tc(const TcFwdParams& tp, const TcPlan& t, int grid, cudaStre
 template <typename S, typename W, int TN>
 int launch_forward_tn(const FwdParams& p, const Geometry& g, cudaStream_t st, bool pool) {
   auto kern = pool ? ikr_forward_pool_kernel<S, W, TN> : ikr_forward_kernel<S, W, TN>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) !=
+  if (allow_max_smem(kern, g.smem) !=
       cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
@@ -465,7 +479,7 @@ size_t bwd_workspace_bytes(const ikr_desc* d, long long B, int gib = 4) {
 template <typename S, typename W, int TN>
 int launch_adjoint_tn(const BwdParams& p, const Geometry& g, cudaStream_t st) {
   auto kern = ikr_adjoint_kernel<S, W, TN>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) !=
+  if (allow_max_smem(kern, g.smem) !=
       cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
@@ -484,7 +498,7 @@ int launch_adjoint(const BwdParams& p, const Geometry& g, cudaStream_t st) {
 template <typename W>
 int launch_wgrad(const WgradParams& p, const BwdPlan& pl, cudaStream_t st) {
   auto kern = ikr_wgrad_kernel<W>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.wg_smem) !=
+  if (allow_max_smem(kern, pl.wg_smem) !=
       cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
@@ -573,7 +587,7 @@ size_t tc_bwd_workspace_bytes(const TcBwdPlan& pl, int gib = 4) {
 template <typename S, int G>
 int launch_adjoint_tc_g(const TcAdjParams& tp, const TcBwdPlan& pl, cudaStream_t st) {
   auto kern = ikr_adjoint_tc_kernel<S, G>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) !=
+  if (allow_max_smem(kern, pl.smem) !=
       cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
@@ -644,8 +658,7 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
   wp.S = pl.wg_S;
   wp.stages = pl.wg_stages;
   wp.partial = reinterpret_cast<double*>(ws + pl.off_partial);
-  if (cudaFuncSetAttribute(ikr_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)pl.wg_smem) != cudaSuccess) {
+  if (allow_max_smem(ikr_wgrad_tc_kernel, pl.wg_smem) != cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
   }
@@ -846,7 +859,7 @@ TcRegPlan make_tc_reg_plan(const ikr_desc* d, long long N) {
 template <int G>
 int launch_regress_g(const TcRegParams& tp, const TcBwdPlan& pl, int grid, cudaStream_t st) {
   auto kern = ikr_regress_tc_kernel<G>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) !=
+  if (allow_max_smem(kern, pl.smem) !=
       cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
@@ -1206,8 +1219,7 @@ int ikr_regression_loss_grad(const ikr_desc* d, const void* weights, const void*
   wp.S = pl.wg_S;
   wp.stages = pl.wg_stages;
   wp.partial = reinterpret_cast<double*>(ws + r.off_partial);
-  if (cudaFuncSetAttribute(ikr_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)pl.wg_smem) != cudaSuccess) {
+  if (allow_max_smem(ikr_wgrad_tc_kernel, pl.wg_smem) != cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
   }

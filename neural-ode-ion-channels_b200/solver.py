@@ -39,7 +39,7 @@ from .protocols import compact_table
 _ADAPTIVE_OPTS = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps'}
 _FIXED_OPTS = {'step_size', 'perturb'}
 _EXT_OPTS = {'tile_m', 'check_status', 'compact_table', 'ckpt_cap', 'lane_pool', 'tensor_cores',
-             'tc_groups', 'tc_timing', 'ping_pong', 'tc_split', 'bwd_overlap'}
+             'tc_groups', 'tc_timing', 'ping_pong', 'tc_split', 'bwd_overlap', 'stash_gib'}
 
 
 # =============================================================================================

@@ -329,3 +329,67 @@ def test_rk4_fused_loss_fp32_tensor_core_backward():
         assert np.abs(got[o:o + size] - want[o:o + size]).max() <= 1e-4 * ref
         o += size
     assert np.abs(res.grad_y0.cpu().numpy() - want_y0).max() <= 1e-4 * np.abs(want_y0).max()
+
+
+def test_concurrent_fits_on_separate_streams_equal_serial_fits():
+    """bench.py's `sweep` leg runs the fits of a rank concurrently, one host thread and one CUDA
+    stream each (a 256-dataset fit is a latency-bound chain on 2 of 148 SMs).  The library keeps no
+    global state, so every fit must return what it returns alone: same loss and accepted steps,
+    gradients equal to the summation-order noise of the weight-gradient partials.  Covers the
+    three kernel families (tcgen05 fp32, FFMA2 n = 500, DFMA fp64)."""
+    import threading
+    name, t_tab, v_tab, t_out = protocols.protocol_set('pr4')[10]
+    t_out = t_out[:60]
+    rng = np.random.RandomState(5)
+    B = 200
+    y0np = np.stack([rng.uniform(0, 0.05, B), rng.uniform(0.95, 1.0, B)], 1)
+    noise = rng.normal(0, 0.05, (len(t_out), B))
+    cases = [('s00', False), ('s06', False), ('s03', True), ('s10', True), ('s02', False), ('s00', True)]
+
+    def build(arch, f64):
+        torch.manual_seed(0)
+        func = ikr.ODEFuncNNf(arch=arch, params='r')
+        return (func.double() if f64 else func).cuda()
+
+    def fit(func, f64, out, k):
+        dtype = torch.float64 if f64 else torch.float32
+        func.set_fixed_form_voltage_protocol(t_tab, v_tab)
+        t = torch.tensor(t_out, dtype=dtype)
+        y0 = torch.tensor(y0np, dtype=dtype).cuda()
+        data = torch.tensor(0.01 * noise, dtype=dtype).cuda()
+        total, per, grads, res = ikr.loss_and_grad(func, y0, t, data, g=0.16, E=-93.4,
+                                                   options={'ckpt_cap': 512, 'stash_gib': 2})
+        out[k] = (float(total), res.stats[:, :2].cpu().numpy().copy(), _flat(grads))
+
+    serial = [None] * len(cases)
+    for k, (arch, f64) in enumerate(cases):
+        fit(build(arch, f64), f64, serial, k)
+    torch.cuda.synchronize()
+
+    funcs = [build(arch, f64) for arch, f64 in cases]
+    conc = [None] * len(cases)
+    errors = []
+    gate = threading.Barrier(len(cases), timeout=300)
+
+    def worker(k):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                gate.wait()
+                for _ in range(2):            # two rounds each, so that the launches interleave
+                    fit(funcs[k], cases[k][1], conc, k)
+                torch.cuda.current_stream().synchronize()
+        except Exception as exc:              # noqa: BLE001 -- reported below, never swallowed
+            errors.append((cases[k], repr(exc)))
+            gate.abort()
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(cases))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for (arch, f64), a, b in zip(cases, serial, conc):
+        tol = 1e-10 if f64 else 2e-5
+        assert (a[1] == b[1]).all(), (arch, f64)                       # same accepted / rejected steps
+        assert abs(a[0] - b[0]) <= tol * abs(a[0]), (arch, f64, a[0], b[0])
+        assert np.abs(a[2] - b[2]).max() <= tol * np.abs(a[2]).max(), (arch, f64)
