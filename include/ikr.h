@@ -90,7 +90,10 @@ typedef struct ikr_desc {
                              magnitude -- beyond that trial steps are rejected and, in the physical domain,
                              the lane ends with IKR_TC_RANGE);
                              bit 9: ikr_backward never overlaps the weight-gradient GEMM with the next
-                             adjoint round (default: on a second stream when the batch leaves SMs idle) */
+                             adjoint round (default: on a second stream when the batch leaves SMs idle);
+                             bit 10: the tensor-core adjoint kernel issues all six bf16x3 products per
+                             fp32 product (default: three, a1 b1 + a2 b1 + a1 b2, the ~2^-16 per
+                             product that the weight-gradient GEMM carries anyway) */
 } ikr_desc;
 
 /* One JOB = one protocol table + one batch of trajectories, i.e. the shape of one reference

@@ -119,7 +119,8 @@ __device__ __forceinline__ tc::f32x2_t tc_leaky_grad2(uint32_t bits, int q, floa
 // MODE 1: forward LAST layer (H_L): stash Hc_L; dz_L = up w_last leaky'(H_L) -> A operand, stash dz_L
 // MODE 2: backward layer: dz = v * leaky'(sign bits) -> A operand, stash dz
 // MODE 3: backward FIRST layer (dz_0): stash dz_0, reduce dz_0 . w0b
-template <int NK, int MODE>
+// LITE: see tc_mma_warp -- units that feed a three-product pass carry no third term
+template <int NK, int MODE, int LITE = 0>
 __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& sg, const TcLane& tl,
                                             const TcAdjLane& al, int u, unsigned gi, int w_idx, int layer,
                                             const float* bias, uint32_t (&v)[16 * NK], float up,
@@ -174,12 +175,13 @@ __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& 
   if (MODE != 3) {
     tc_unit_acquire(g, tl, u);
     const uint32_t dst = tl.taddr + tc_unit_slot_col(g, tl, u);
+    constexpr bool third = LITE == 0 || (LITE == 1 && MODE == 0);
     if (NK == 2) {
       tc::st32(dst, reinterpret_cast<uint32_t(&)[32]>(w12));
-      tc::st16(dst + 32, reinterpret_cast<uint32_t(&)[16]>(w3));
+      if (third) tc::st16(dst + 32, reinterpret_cast<uint32_t(&)[16]>(w3));
     } else {
       tc::st16(dst, reinterpret_cast<uint32_t(&)[16]>(w12));
-      tc::st8(dst + 16, reinterpret_cast<uint32_t(&)[8]>(w3));
+      if (third) tc::st8(dst + 16, reinterpret_cast<uint32_t(&)[8]>(w3));
     }
     tc_unit_publish(g, tl, u);
   } else {
@@ -199,7 +201,7 @@ __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& 
 }
 
 // the 8 tail features (feature group 2 KSf) -- same four modes; also writes the constant-1 feature of Hc
-template <int MODE>
+template <int MODE, int LITE = 0>
 __device__ __forceinline__ void tc_adj_tail(const TcGeom& g, const TcStashGeom& sg, const TcLane& tl,
                                             const TcAdjLane& al, unsigned gi, int w_idx, int layer,
                                             const float* bias, uint32_t (&v)[8], float up, float& acc) {
@@ -287,7 +289,7 @@ __device__ __forceinline__ void tc_adj_tail(const TcGeom& g, const TcStashGeom& 
 
 // One forward + backward MLP evaluation of the tile (every lane thread of every group).
 // xin[lane] = (nv, a, up, -); result: partial sums of up * d net / d a in tl.part.
-template <int G, typename Hook = TcNoHook>
+template <int G, int LITE = 0, typename Hook = TcNoHook>
 __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& sg, TcLane& tl,
                                             const TcAdjLane& al, Hook hook = Hook()) {
   const int NP = g.NP;
@@ -325,16 +327,16 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
         if (2 * u + 1 < g.KSf) {
           uint32_t v[32];
           tc_layer0_sums<32>(tl, NP, 32 * u, nv, a, v);
-          tc_adj_unit<2, 0>(g, sg, tl, al, u, gi, w, 0, b0, v, up, acc);
+          tc_adj_unit<2, 0, LITE>(g, sg, tl, al, u, gi, w, 0, b0, v, up, acc);
         } else {
           uint32_t v[16];
           tc_layer0_sums<16>(tl, NP, 32 * u, nv, a, v);
-          tc_adj_unit<1, 0>(g, sg, tl, al, u, gi, w, 0, b0, v, up, acc);
+          tc_adj_unit<1, 0, LITE>(g, sg, tl, al, u, gi, w, 0, b0, v, up, acc);
         }
       } else {
         uint32_t v[8];
         tc_layer0_sums<8>(tl, NP, 16 * g.KSf, nv, a, v);
-        tc_adj_tail<0>(g, sg, tl, al, gi, w_tail, 0, b0, v, up, acc);
+        tc_adj_tail<0, LITE>(g, sg, tl, al, gi, w_tail, 0, b0, v, up, acc);
       }
     }
     tc_pass_advance(tl, UT);
@@ -355,21 +357,21 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
           uint32_t v[32];
           tc::ld32(tl.taddr + dcol + 32 * u, v);
           tc::wait_ld();
-          if (!last) tc_adj_unit<2, 0>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
-          else tc_adj_unit<2, 1>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
+          if (!last) tc_adj_unit<2, 0, LITE>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
+          else tc_adj_unit<2, 1, LITE>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
         } else {
           uint32_t v[16];
           tc::ld16(tl.taddr + dcol + 32 * u, v);
           tc::wait_ld();
-          if (!last) tc_adj_unit<1, 0>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
-          else tc_adj_unit<1, 1>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
+          if (!last) tc_adj_unit<1, 0, LITE>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
+          else tc_adj_unit<1, 1, LITE>(g, sg, tl, al, u, gi, w, l, bias, v, up, acc);
         }
       } else {
         uint32_t v[8];
         tc::ld8(tl.taddr + dcol + 16 * g.KSf, v);
         tc::wait_ld();
-        if (!last) tc_adj_tail<0>(g, sg, tl, al, gi, w_tail, l, bias, v, up, acc);
-        else tc_adj_tail<1>(g, sg, tl, al, gi, w_tail, l, bias, v, up, acc);
+        if (!last) tc_adj_tail<0, LITE>(g, sg, tl, al, gi, w_tail, l, bias, v, up, acc);
+        else tc_adj_tail<1, LITE>(g, sg, tl, al, gi, w_tail, l, bias, v, up, acc);
       }
     }
     tc_pass_advance(tl, UT);
@@ -388,21 +390,21 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
           uint32_t v[32];
           tc::ld32(tl.taddr + dcol + 32 * u, v);
           tc::wait_ld();
-          if (!first) tc_adj_unit<2, 2>(g, sg, tl, al, u, gi, w, l - 1, nullptr, v, up, acc);
-          else tc_adj_unit<2, 3>(g, sg, tl, al, u, gi, w, 0, nullptr, v, up, acc);
+          if (!first) tc_adj_unit<2, 2, LITE>(g, sg, tl, al, u, gi, w, l - 1, nullptr, v, up, acc);
+          else tc_adj_unit<2, 3, LITE>(g, sg, tl, al, u, gi, w, 0, nullptr, v, up, acc);
         } else {
           uint32_t v[16];
           tc::ld16(tl.taddr + dcol + 32 * u, v);
           tc::wait_ld();
-          if (!first) tc_adj_unit<1, 2>(g, sg, tl, al, u, gi, w, l - 1, nullptr, v, up, acc);
-          else tc_adj_unit<1, 3>(g, sg, tl, al, u, gi, w, 0, nullptr, v, up, acc);
+          if (!first) tc_adj_unit<1, 2, LITE>(g, sg, tl, al, u, gi, w, l - 1, nullptr, v, up, acc);
+          else tc_adj_unit<1, 3, LITE>(g, sg, tl, al, u, gi, w, 0, nullptr, v, up, acc);
         }
       } else {
         uint32_t v[8];
         tc::ld8(tl.taddr + dcol + 16 * g.KSf, v);
         tc::wait_ld();
-        if (!first) tc_adj_tail<2>(g, sg, tl, al, gi, w_tail, l - 1, nullptr, v, up, acc);
-        else tc_adj_tail<3>(g, sg, tl, al, gi, w_tail, 0, nullptr, v, up, acc);
+        if (!first) tc_adj_tail<2, LITE>(g, sg, tl, al, gi, w_tail, l - 1, nullptr, v, up, acc);
+        else tc_adj_tail<3, LITE>(g, sg, tl, al, gi, w_tail, 0, nullptr, v, up, acc);
       }
     }
     if (!first) tc_pass_advance(tl, UT);
@@ -412,7 +414,7 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
 }
 
 // Owner-side wrapper of one adjoint evaluation: publish (nv, a, up), take a stash slot, run, collect.
-template <int G, typename Hook = TcNoHook>
+template <int G, int LITE = 0, typename Hook = TcNoHook>
 __device__ __forceinline__ float tc_adj_owner_eval(const TcGeom& g, const TcStashGeom& sg, TcLane& tl,
                                                    TcAdjLane& al, unsigned char* stash,
                                                    volatile long long* stash_slot,
@@ -424,7 +426,7 @@ __device__ __forceinline__ float tc_adj_owner_eval(const TcGeom& g, const TcStas
   if (tid == 0) *stash_slot = (long long)atomicAdd(&counters[1], 1ULL);
   if (G > 1) lanes_sync<G>(); else owners_sync();
   al.slot = stash + (size_t)(*stash_slot) * sg.slot;
-  tc_adj_eval<G, Hook>(g, sg, tl, al, hook);
+  tc_adj_eval<G, LITE, Hook>(g, sg, tl, al, hook);
   if (G > 1) lanes_sync<G>(); else owners_sync();
   float da = tl.part[tid];
 #pragma unroll
@@ -432,7 +434,7 @@ __device__ __forceinline__ float tc_adj_owner_eval(const TcGeom& g, const TcStas
   return da;
 }
 
-template <typename S, int G>
+template <typename S, int G, int LITE = 0>
 __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const TcAdjParams tp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   typedef typename Vec2<S>::type V2;
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
   const uint32_t tbase = *tmem_slot;
 
   if (warp == kMmaWarp) {
-    tc_mma_warp(g, eng, tbase, tp.timing && blockIdx.x == 0);
+    tc_mma_warp<3, LITE>(g, eng, tbase, tp.timing && blockIdx.x == 0);
   } else if (warp == kLoadWarp) {
     if ((tid & 31) == 0)
       tc_producer_thread(g, eng, reinterpret_cast<const unsigned char*>(tp.img), (unsigned)(2 * g.L * g.KST));
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
         lanes_sync<G>();
         if (*cmd_exit) break;
         al.slot = tp.stash + (size_t)(*stash_slot) * sg.slot;
-        tc_adj_eval<G>(g, sg, tl, al);
+        tc_adj_eval<G, LITE>(g, sg, tl, al);
         lanes_sync<G>();
       }
     } else {
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
               if (rk4) brk4_stage_inputs<S>(L, cfg, s, p.time_f32 != 0, p.rk4_perturb != 0, &nv, &ain, &up);
               else bdp_stage_inputs_cached<S>(L, cfg, s, &nv, &ain, &up, tcache);
             }
-            const float da = tc_adj_owner_eval<G>(g, sg, tl, al, tp.stash, stash_slot, p.counters, act, nv,
+            const float da = tc_adj_owner_eval<G, LITE>(g, sg, tl, al, tp.stash, stash_slot, p.counters, act, nv,
                                                   ain, up, [&]() {
                                                     if (act && s > 0 && !rk4) bdp_prefetch_stage_time<S>(L, cfg, s - 1, tcache);
                                                   });
@@ -631,7 +633,7 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
               y0a = y0[2 * b];
               bdp_f0_inputs<S>(L, cfg, p.t_out[0], y0a, &nv, &ain, &up);
             }
-            const float da = tc_adj_owner_eval<G>(g, sg, tl, al, tp.stash, stash_slot, p.counters, p1 != 0,
+            const float da = tc_adj_owner_eval<G, LITE>(g, sg, tl, al, tp.stash, stash_slot, p.counters, p1 != 0,
                                                   nv, ain, up);
             if (p1) {
               S g0a, g0r;

@@ -584,22 +584,32 @@ size_t tc_bwd_workspace_bytes(const TcBwdPlan& pl, int gib = 4) {
   return pl.fixed_bytes + 512 + (size_t)pl.n_tiles * (6 * R + 1) * (size_t)pl.sg.slot;
 }
 
-template <typename S, int G>
-int launch_adjoint_tc_g(const TcAdjParams& tp, const TcBwdPlan& pl, cudaStream_t st) {
-  auto kern = ikr_adjoint_tc_kernel<S, G>;
-  if (allow_max_smem(kern, pl.smem) !=
-      cudaSuccess) {
+// desc.reserved bit 10: products per fp32 product in the adjoint kernel's MMA passes.  Default
+// (0): three of the six bf16x3 products (a1 b1 + a2 b1 + a1 b2, ~2^-16 per product, rounded splits:
+// unbiased) -- the precision the weight-gradient GEMM has anyway, which is what bounds the gradient
+// (measured on identical checkpoints: same deviation from the fp32-FMA backward in both modes,
+// profiles/adjoint_products_accuracy.py).  1: all six.
+int tc_adjoint_lite(const ikr_desc* d) { return (d->reserved & 1024u) ? 0 : 2; }
+template <typename S, int G, int LITE>
+int launch_adjoint_tc_gl(const TcAdjParams& tp, const TcBwdPlan& pl, cudaStream_t st) {
+  auto kern = ikr_adjoint_tc_kernel<S, G, LITE>;
+  if (allow_max_smem(kern, pl.smem) != cudaSuccess) {
     cudaGetLastError();
     return IKR_ERR_LAUNCH;
   }
   kern<<<pl.grid, tc_threads(G), pl.smem, st>>>(tp);
   return cudaGetLastError() == cudaSuccess ? 0 : IKR_ERR_LAUNCH;
 }
+template <typename S, int G>
+int launch_adjoint_tc_g(const TcAdjParams& tp, const TcBwdPlan& pl, int lite, cudaStream_t st) {
+  if (lite == 2) return launch_adjoint_tc_gl<S, G, 2>(tp, pl, st);
+  return launch_adjoint_tc_gl<S, G, 0>(tp, pl, st);
+}
 template <typename S>
-int launch_adjoint_tc(const TcAdjParams& tp, const TcBwdPlan& pl, cudaStream_t st) {
-  if (pl.groups == 1) return launch_adjoint_tc_g<S, 1>(tp, pl, st);
-  if (pl.groups == 2) return launch_adjoint_tc_g<S, 2>(tp, pl, st);
-  return launch_adjoint_tc_g<S, 3>(tp, pl, st);
+int launch_adjoint_tc(const TcAdjParams& tp, const TcBwdPlan& pl, int lite, cudaStream_t st) {
+  if (pl.groups == 1) return launch_adjoint_tc_g<S, 1>(tp, pl, lite, st);
+  if (pl.groups == 2) return launch_adjoint_tc_g<S, 2>(tp, pl, lite, st);
+  return launch_adjoint_tc_g<S, 3>(tp, pl, lite, st);
 }
 
 int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, const TcBwdPlan& pl,
@@ -675,8 +685,8 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
     for (long long r = 0; r < rounds; ++r) {
       if (cudaMemsetAsync(ws + pl.off_counters, 0, 256, st) != cudaSuccess) return IKR_ERR_DEVICE;
       p.first_round = r == 0 ? 1 : 0;
-      const int rc = d->state_dtype == IKR_F32 ? launch_adjoint_tc<float>(tp, pl, st)
-                                               : launch_adjoint_tc<double>(tp, pl, st);
+      const int rc = d->state_dtype == IKR_F32 ? launch_adjoint_tc<float>(tp, pl, tc_adjoint_lite(d), st)
+                                               : launch_adjoint_tc<double>(tp, pl, tc_adjoint_lite(d), st);
       if (rc != 0) return rc;
       ikr_wgrad_tc_kernel<<<(d->n_layers + 2) * pl.wg_S, kWgTcThreads, pl.wg_smem, st>>>(wp);
       if (cudaGetLastError() != cudaSuccess) return IKR_ERR_LAUNCH;
@@ -702,8 +712,8 @@ int bwd_dispatch_tc(const ikr_desc* d, const ikr_io* io, const ikr_bwd_io* bio, 
       p.first_round = r == 0 ? 1 : 0;
       p.counters = reinterpret_cast<unsigned long long*>(cnt);
       tp.stash = ws + off_stash + (size_t)b * half;
-      rc = d->state_dtype == IKR_F32 ? launch_adjoint_tc<float>(tp, pl, st)
-                                     : launch_adjoint_tc<double>(tp, pl, st);
+      rc = d->state_dtype == IKR_F32 ? launch_adjoint_tc<float>(tp, pl, tc_adjoint_lite(d), st)
+                                     : launch_adjoint_tc<double>(tp, pl, tc_adjoint_lite(d), st);
       if (rc != 0) break;
       if (cudaEventRecord(ev_adj[b], st) != cudaSuccess || cudaStreamWaitEvent(s2, ev_adj[b], 0) != cudaSuccess) {
         rc = IKR_ERR_DEVICE;

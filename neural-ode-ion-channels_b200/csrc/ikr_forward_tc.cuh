@@ -685,7 +685,10 @@ __device__ __forceinline__ void tc_release_engines(const TcLane& tl) {
 // MMA issuer.  The whole warp runs the loop (warp-uniform control flow and operands => the descriptors
 // live in uniform registers and each MMA is one UTCHMMA); one elected lane issues the MMAs and commits.
 // A layer pass = the units 0 .. UT-1 in order; every unit is issued as soon as its slot is filled.
-template <int TERMS = 3>
+// LITE (bf16x3 only, adjoint kernel): three of the six products (a1 b1 + a2 b1 + a1 b2: products to
+// ~2^-16, what the weight-gradient GEMM carries anyway) on the backward passes of an evaluation
+// (LITE = 1: passes L .. 2L-1 of every 2L) or on all passes (LITE = 2).
+template <int TERMS = 3, int LITE = 0>
 __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& c, uint32_t tbase, bool timing) {
   const unsigned stages = (unsigned)g.stages;
   constexpr bool f16 = TERMS == 2;      // compile time: the six / three MMAs stay back-to-back UTCHMMAs
@@ -698,6 +701,7 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
   bool stop = false;
   while (!stop) {
     const uint32_t dcol = tbase + ((pass & 1u) ? (uint32_t)g.NP : 0u);
+    const bool lite = LITE == 2 || (LITE == 1 && (pass % (2u * (unsigned)g.L)) >= (unsigned)g.L);
     bool first = true;
     for (int u = 0; u < UT; ++u, ++gi) {
       const unsigned slot = gi % tc_ring_slots<TERMS>();
@@ -733,14 +737,16 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
             const uint32_t a1 = a_slot + 8u * (uint32_t)jj;
             tc::mma_ts(dcol, a1, b1, idesc, first ? 0u : 1u);
             tc::mma_ts(dcol, a1 + dt, b1, idesc, 1u);
-            tc::mma_ts(dcol, a1 + 2 * dt, b1, idesc, 1u);
+            if (LITE == 0 || !lite) tc::mma_ts(dcol, a1 + 2 * dt, b1, idesc, 1u);
             tc::mma_ts(dcol, a1, b2, idesc, 1u);
-            tc::mma_ts(dcol, a1 + dt, b2, idesc, 1u);
-            tc::mma_ts(dcol, a1, b3, idesc, 1u);
+            if (LITE == 0 || !lite) {
+              tc::mma_ts(dcol, a1 + dt, b2, idesc, 1u);
+              tc::mma_ts(dcol, a1, b3, idesc, 1u);
+            }
           } else {
             tc::mma_ts(dcol, a_slot, b1, idesc, first ? 0u : 1u);
             tc::mma_ts(dcol, a_slot, b2, idesc, 1u);
-            tc::mma_ts(dcol, a_slot + 8u, b3, idesc, 1u);
+            if (LITE == 0 || !lite) tc::mma_ts(dcol, a_slot + 8u, b3, idesc, 1u);
           }
           tc::commit(smem_u32(&c.bar_empty[s]));   // weight slot free once these MMAs have read it
         }

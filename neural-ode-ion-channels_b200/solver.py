@@ -39,7 +39,8 @@ from .protocols import compact_table
 _ADAPTIVE_OPTS = {'first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps'}
 _FIXED_OPTS = {'step_size', 'perturb'}
 _EXT_OPTS = {'tile_m', 'check_status', 'compact_table', 'ckpt_cap', 'lane_pool', 'tensor_cores',
-             'tc_groups', 'tc_timing', 'ping_pong', 'tc_split', 'bwd_overlap', 'stash_gib'}
+             'tc_groups', 'tc_timing', 'ping_pong', 'tc_split', 'bwd_overlap', 'stash_gib',
+             'adjoint_products'}
 
 
 # =============================================================================================
@@ -169,7 +170,11 @@ def _make_desc(spec: ModelSpec, state_dtype, method, rtol, atol, opts, time_f32=
     groups = int(opts.get('tc_groups', 0) or 0)
     if groups not in (0, 1, 2, 3):
         raise ValueError('odeint: tc_groups must be 1, 2 or 3')
-    d.reserved = ((1 if lp else 0) | (4 if lp is False else 0) |
+    # bit 10: bf16 products per fp32 product in the adjoint kernel's MMAs: 'three' (default) / 'six'
+    adj = {None: 0, 'three': 0, 'six': 1}.get(opts.get('adjoint_products', None), -1)
+    if adj < 0:
+        raise ValueError("odeint: adjoint_products must be 'three' or 'six'")
+    d.reserved = ((adj << 10) | (1 if lp else 0) | (4 if lp is False else 0) |
                   (0 if opts.get('tensor_cores', True) else 2) |
                   (8 if opts.get('tc_timing', False) else 0) | (groups << 4) |
                   (64 if pp is False else 0) | (128 if pp else 0) |

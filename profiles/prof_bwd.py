@@ -38,7 +38,8 @@ for _ in range(int(os.environ.get('REPS', '2'))):
                                    'tc_split': os.environ.get('TC_SPLIT') or None,
                                    'tc_groups': int(os.environ.get('TC_GROUPS', '0')),
                                    'ping_pong': {'1': True, '0': False}.get(os.environ.get('PP', ''), None),
-            'lane_pool': {'1': True, '0': False}.get(os.environ.get('POOL', ''), None)}
+            'lane_pool': {'1': True, '0': False}.get(os.environ.get('POOL', ''), None),
+            'adjoint_products': os.environ.get('ADJ') or None}
     if cap:
         opts['ckpt_cap'] = cap
     res = ikr.integrate(f, y0, t, data=data, want_y=True, want_ckpt=True, options=opts)
