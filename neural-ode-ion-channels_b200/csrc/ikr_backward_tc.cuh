@@ -75,7 +75,7 @@ struct TcAdjSmemLayout {
     off_part = o; o += (size_t)G * kTcM * sizeof(float);
     off_mask = o; o += (size_t)g.L * mask_words * 128 * G * sizeof(uint32_t);
     off_sp = o; o += (size_t)g.small_elems * sizeof(float); o = (o + 127) & ~(size_t)127;
-    off_ring = o; o += (size_t)stages * g.stage_bytes;
+    off_ring = o; o += (size_t)stages * g.ring_stride;
     total = o;
   }
 };
@@ -483,7 +483,8 @@ __global__ void __launch_bounds__(tc_threads(G), 1) ikr_adjoint_tc_kernel(const 
     tc_mma_warp<3, LITE>(g, eng, tbase, tp.timing && blockIdx.x == 0);
   } else if (warp == kLoadWarp) {
     if ((tid & 31) == 0)
-      tc_producer_thread(g, eng, reinterpret_cast<const unsigned char*>(tp.img), (unsigned)(2 * g.L * g.KST));
+      tc_producer_thread(g, eng, reinterpret_cast<const unsigned char*>(tp.img), (unsigned)(2 * g.L * g.KST),
+                         LITE == 2 ? 2u * (unsigned)g.block_bytes : 0u);
   } else {
     TcLane tl;
     tl.group = warp >> 2;

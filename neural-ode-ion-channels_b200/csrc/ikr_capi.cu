@@ -523,6 +523,13 @@ struct TcBwdPlan {
   size_t off_counters, off_lanes, off_partial, off_img, fixed_bytes, partial_bytes, img_bytes;
 };
 
+// desc.reserved bit 10: products per fp32 product in the adjoint kernel's MMA passes.  Default
+// (0): three of the six bf16x3 products (a1 b1 + a2 b1 + a1 b2, ~2^-16 per product, rounded splits:
+// unbiased) -- the precision the weight-gradient GEMM has anyway, which is what bounds the gradient
+// (measured on identical checkpoints: same deviation from the fp32-FMA backward in both modes,
+// profiles/adjoint_products_accuracy.py).  1: all six.
+int tc_adjoint_lite(const ikr_desc* d) { return (d->reserved & 1024u) ? 0 : 2; }
+
 TcBwdPlan make_tc_bwd_plan(const ikr_desc* d, long long B) {
   TcBwdPlan pl;
   pl.ok = false;
@@ -535,11 +542,14 @@ TcBwdPlan make_tc_bwd_plan(const ikr_desc* d, long long B) {
   const size_t fixed = d->state_dtype == IKR_F32
                            ? TcAdjSmemLayout<float>(pl.g, 0, pl.groups, pl.mask_words).total
                            : TcAdjSmemLayout<double>(pl.g, 0, pl.groups, pl.mask_words).total;
-  if (fixed + (size_t)kTcMinStages * pl.g.stage_bytes > kSmemLimit) return pl;
-  int stages = (int)((kSmemLimit - fixed) / pl.g.stage_bytes);
+  // three-product passes never read the third term block of a stage: it is neither streamed nor
+  // given ring space, so more k-steps of weights are in flight
+  if (tc_adjoint_lite(d) == 2) pl.g.ring_stride = 2 * pl.g.block_bytes;
+  if (fixed + (size_t)kTcMinStages * pl.g.ring_stride > kSmemLimit) return pl;
+  int stages = (int)((kSmemLimit - fixed) / pl.g.ring_stride);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   pl.g.stages = stages;
-  pl.smem = fixed + (size_t)stages * pl.g.stage_bytes;
+  pl.smem = fixed + (size_t)stages * pl.g.ring_stride;
   pl.sms = device_sms();
   pl.tile_lanes = tc_tile_lanes(B, pl.sms);
   pl.n_tiles = (B + pl.tile_lanes - 1) / pl.tile_lanes;
@@ -584,12 +594,6 @@ size_t tc_bwd_workspace_bytes(const TcBwdPlan& pl, int gib = 4) {
   return pl.fixed_bytes + 512 + (size_t)pl.n_tiles * (6 * R + 1) * (size_t)pl.sg.slot;
 }
 
-// desc.reserved bit 10: products per fp32 product in the adjoint kernel's MMA passes.  Default
-// (0): three of the six bf16x3 products (a1 b1 + a2 b1 + a1 b2, ~2^-16 per product, rounded splits:
-// unbiased) -- the precision the weight-gradient GEMM has anyway, which is what bounds the gradient
-// (measured on identical checkpoints: same deviation from the fp32-FMA backward in both modes,
-// profiles/adjoint_products_accuracy.py).  1: all six.
-int tc_adjoint_lite(const ikr_desc* d) { return (d->reserved & 1024u) ? 0 : 2; }
 template <typename S, int G, int LITE>
 int launch_adjoint_tc_gl(const TcAdjParams& tp, const TcBwdPlan& pl, cudaStream_t st) {
   auto kern = ikr_adjoint_tc_kernel<S, G, LITE>;

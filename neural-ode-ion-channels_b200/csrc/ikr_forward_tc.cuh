@@ -64,6 +64,8 @@ struct TcGeom {
   int cols;          // TMEM columns used
   int block_bytes;   // one B block: NP x 16 16-bit values = NP * 32 bytes
   int stage_bytes;   // one k-step: `terms` blocks
+  int ring_stride;   // bytes per slot of the shared-memory weight ring (= stage_bytes unless only the
+                     // leading blocks of a stage are streamed: adjoint kernel, three-product passes)
   int stages;        // ring depth
   int small_elems;   // zero-padded small-parameter block: (4 + L) NP + 8 floats, then L per-layer
                      // accumulator scales (1 for bf16x3), padded to 8
@@ -85,6 +87,7 @@ __host__ __device__ inline TcGeom tc_geometry(int n, int L, int terms = 3) {
   g.cols = g.col_ring + g.ring_slots * g.unit_cols;
   g.block_bytes = g.NP * 32;
   g.stage_bytes = terms * g.block_bytes;
+  g.ring_stride = g.stage_bytes;
   g.stages = 0;
   g.small_elems = (4 + L) * g.NP + 8 + (L + 7) / 8 * 8;
   return g;
@@ -694,7 +697,7 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
   constexpr bool f16 = TERMS == 2;      // compile time: the six / three MMAs stay back-to-back UTCHMMAs
   const uint32_t idesc = f16 ? tc::idesc_f16_f32(kTcM, g.NP) : tc::idesc_bf16_f32(kTcM, g.NP);
   const uint64_t desc0 = tc::smem_desc(smem_u32(c.ring), 128, 256);
-  const uint32_t blk16 = (uint32_t)g.block_bytes >> 4, stage16 = (uint32_t)g.stage_bytes >> 4;
+  const uint32_t blk16 = (uint32_t)g.block_bytes >> 4, stage16 = (uint32_t)g.ring_stride >> 4;
   const int UT = g.units + g.tail;
   unsigned s = 0, round = 0, consumed = 0, gi = 0, pass = 0;
   long long e_wait = 0, e_wait0 = 0, e_wait00 = 0, e_issue = 0, ec = clock64();
@@ -776,17 +779,21 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
 }
 
 // Weight producer (one thread): streams the image cyclically (`per_cycle` k-steps) through the ring.
+// `copy_bytes` < g.stage_bytes: only the leading term blocks of every stage are needed (the adjoint
+// kernel's three-product passes never read the third block)
 __device__ __forceinline__ void tc_producer_thread(const TcGeom& g, const TcEngineCtx& c,
-                                                   const unsigned char* img, unsigned per_cycle) {
+                                                   const unsigned char* img, unsigned per_cycle,
+                                                   unsigned copy_bytes = 0u) {
+  if (copy_bytes == 0u) copy_bytes = (unsigned)g.stage_bytes;
   const unsigned stages = (unsigned)g.stages;
   unsigned issued = 0;
   for (;; ++issued) {
     const unsigned q = issued, s = q % stages;
     if (q >= stages) mbar_wait(&c.bar_empty[s], ((q / stages) - 1u) & 1u);
     if (*c.stop_flag) break;
-    mbar_expect_tx(&c.bar_full[s], (unsigned)g.stage_bytes);
-    bulk_g2s(c.ring + (size_t)s * g.stage_bytes, img + (size_t)(q % per_cycle) * g.stage_bytes,
-             (unsigned)g.stage_bytes, &c.bar_full[s]);
+    mbar_expect_tx(&c.bar_full[s], copy_bytes);
+    bulk_g2s(c.ring + (size_t)s * g.ring_stride, img + (size_t)(q % per_cycle) * g.stage_bytes,
+             copy_bytes, &c.bar_full[s]);
   }
   // wait for the copies still in flight (the last `stages` issued chunks cover every slot once)
   for (unsigned q = issued > stages ? issued - stages : 0; q < issued; ++q)
