@@ -173,8 +173,8 @@ __device__ __forceinline__ void tc_adj_unit(const TcGeom& g, const TcStashGeom& 
     }
   }
   if (MODE != 3) {
-    tc_unit_acquire(g, tl, u);
-    const uint32_t dst = tl.taddr + tc_unit_slot_col(g, tl, u);
+    tc_unit_acquire<tc_ring_terms<3, LITE>()>(g, tl, u);
+    const uint32_t dst = tl.taddr + tc_unit_slot_col<tc_ring_terms<3, LITE>()>(g, tl, u);
     constexpr bool third = LITE == 0 || (LITE == 1 && MODE == 0);
     if (NK == 2) {
       tc::st32(dst, reinterpret_cast<uint32_t(&)[32]>(w12));
@@ -270,8 +270,8 @@ __device__ __forceinline__ void tc_adj_tail(const TcGeom& g, const TcStashGeom& 
   if (MODE != 3) {
     const uint32_t t[16] = {t1[0], t1[1], t1[2], t1[3], t2[0], t2[1], t2[2], t2[3],
                             t1[0], t1[1], t1[2], t1[3], t3[0], t3[1], t3[2], t3[3]};
-    tc_unit_acquire(g, tl, g.units);
-    tc::st16(tl.taddr + tc_unit_slot_col(g, tl, g.units), t);
+    tc_unit_acquire<tc_ring_terms<3, LITE>()>(g, tl, g.units);
+    tc::st16(tl.taddr + tc_unit_slot_col<tc_ring_terms<3, LITE>()>(g, tl, g.units), t);
     tc_unit_publish(g, tl, g.units);
   } else {
     const float* w0b = tl.sp + g.NP + c0;
@@ -339,7 +339,7 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
         tc_adj_tail<0, LITE>(g, sg, tl, al, gi, w_tail, 0, b0, v, up, acc);
       }
     }
-    tc_pass_advance(tl, UT);
+    tc_pass_advance<tc_ring_terms<3, LITE>()>(tl, UT);
     hook();      // owners: time-only terms of the next reversed stage, under the first layer's MMAs
   }
   // ---- hidden layers forward (l = 1..L; H_l has sign-bit row l, the last one is consumed at once) ----
@@ -374,7 +374,7 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
         else tc_adj_tail<1, LITE>(g, sg, tl, al, gi, w_tail, l, bias, v, up, acc);
       }
     }
-    tc_pass_advance(tl, UT);
+    tc_pass_advance<tc_ring_terms<3, LITE>()>(tl, UT);
   }
   // ---- backward: D = dz_l W_l  ->  dz_{l-1} = D * leaky'(H_{l-1}) ---------------------------------------
   for (int l = g.L; l >= 1; --l) {
@@ -407,7 +407,7 @@ __device__ __forceinline__ void tc_adj_eval(const TcGeom& g, const TcStashGeom& 
         else tc_adj_tail<3, LITE>(g, sg, tl, al, gi, w_tail, 0, nullptr, v, up, acc);
       }
     }
-    if (!first) tc_pass_advance(tl, UT);
+    if (!first) tc_pass_advance<tc_ring_terms<3, LITE>()>(tl, UT);
   }
   tl.part[tl.group * kTcM + tl.lane] = acc;
   { const long long c1 = clock64(); tl.c_epi += c1 - c0; }

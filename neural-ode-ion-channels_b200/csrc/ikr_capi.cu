@@ -856,6 +856,7 @@ TcRegPlan make_tc_reg_plan(const ikr_desc* d, long long N) {
   ikr_desc dd = *d;
   dd.method = IKR_DOPRI5;
   dd.state_dtype = IKR_F32;
+  dd.reserved |= 1024;          // the regression kernel issues all six products: full-width weight ring
   r.b = make_tc_bwd_plan(&dd, N);
   if (!r.b.ok) return r;
   r.n_tiles = (N + kTcM - 1) / kTcM;

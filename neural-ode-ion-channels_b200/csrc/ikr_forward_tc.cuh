@@ -306,6 +306,10 @@ constexpr int kTcMaxUnits = 8;     // NP <= 208: at most 7 units of two K-steps 
 // unit loop costs ~70 cycles per k-step: measured)
 template <int TERMS>
 __host__ __device__ constexpr unsigned tc_ring_slots() { return TERMS == 2 ? 3u : 2u; }
+// ring geometry of a kernel: bf16x3 units without their third term (adjoint kernel, LITE = 2) are
+// 32 columns wide like fp16x2 units, so three of them fit
+template <int TERMS, int LITE>
+__host__ __device__ constexpr int tc_ring_terms() { return (TERMS == 3 && LITE == 2) ? 2 : TERMS; }
 // slot of unit u of the pass this thread is producing (tl.ring_base = first unit of the pass mod R)
 template <int TERMS = 3>
 __device__ __forceinline__ uint32_t tc_unit_slot_col(const TcGeom& g, const TcLane& tl, int u) {
@@ -707,13 +711,13 @@ __device__ __forceinline__ void tc_mma_warp(const TcGeom& g, const TcEngineCtx& 
     const bool lite = LITE == 2 || (LITE == 1 && (pass % (2u * (unsigned)g.L)) >= (unsigned)g.L);
     bool first = true;
     for (int u = 0; u < UT; ++u, ++gi) {
-      const unsigned slot = gi % tc_ring_slots<TERMS>();
+      const unsigned slot = gi % tc_ring_slots<tc_ring_terms<TERMS, LITE>()>();
       { const long long c1 = clock64(); e_issue += c1 - ec; ec = c1; }
       mbar_wait(&c.unit_ready[u], pass & 1u);
       if (*c.stop_flag) { stop = true; break; }
       tc::fence_after_sync();
       { const long long c1 = clock64(); e_wait += c1 - ec; if (u == 0) { e_wait0 += c1 - ec; if (pass % (unsigned)g.L == 0) e_wait00 += c1 - ec; } ec = c1; }
-      const uint32_t a_slot = tbase + (uint32_t)g.col_ring + (uint32_t)(16 * TERMS) * slot;
+      const uint32_t a_slot = tbase + (uint32_t)g.col_ring + (uint32_t)(16 * tc_ring_terms<TERMS, LITE>()) * slot;
       const bool is_tail = u >= g.units;
       const int nk = is_tail ? 1 : ((2 * u + 1 < g.KSf) ? 2 : 1);
 #pragma unroll 1
