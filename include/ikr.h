@@ -81,7 +81,7 @@ typedef struct ikr_desc {
                              tensor-core path for launches with more tiles than SMs);
                              bit 3: debug, CTA 0 prints its phase clocks (device printf);
                              bits 4-5: epilogue column groups of the tensor-core kernels, 1..3
-                             (0 = default 3; fixes the output-layer summation order, i.e. results);
+                             (0 = default 2; fixes the output-layer summation order, i.e. results);
                              bit 6: never use the two-tile ping-pong kernel; bit 7: use it (experimental,
                              never chosen automatically);
                              bit 8: tensor-core forward with the bf16x3 operand split (six MMAs per

@@ -231,7 +231,7 @@ struct TcPlan {
   size_t smem, img_bytes;
 };
 
-constexpr int kTcDefaultGroups = 3;
+constexpr int kTcDefaultGroups = 2;   // measured: 2 and 3 tie on full grids, 2 is ~3 % ahead on one-tile-per-SM launches (no register spills at 161-168 registers)
 
 // Operand split of the tensor-core FORWARD kernels: fp16x2 (three MMAs per fp32 product) unless
 // desc.reserved bit 8 asks for bf16x3 (six; no range restriction on the activations).  The adjoint /
