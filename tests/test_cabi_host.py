@@ -96,7 +96,7 @@ def test_packed_layout_and_param_count(lib):
     d = _desc()
     geo = _cabi.launch_geometry(d, [13107] * 4 + [13108])
     assert lib.ikr_uses_tensor_cores(ctypes.byref(d)) == 1 and geo['tensor_cores']
-    assert (geo['tile_m'], geo['threads']) == (128, 448)
+    assert (geo['tile_m'], geo['threads']) == (128, 320)      # two column groups + two engine warps
     # opting out (reserved bit 1) gives the FFMA2 kernel its 16-warp, 160-trajectory tile
     d.reserved = 2
     geo = _cabi.launch_geometry(d, [13107] * 4 + [13108])
